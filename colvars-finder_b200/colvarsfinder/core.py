@@ -1,0 +1,349 @@
+"""Training tasks with the reference's public API (reference colvarsfinder/core.py) on top of the CUDA step.
+
+``EigenFunctionTask`` and ``AutoEncoderTask`` keep the constructor signatures, attributes, return values and
+logging names of the reference; what changes is where the arithmetic runs:
+
+* the trajectory shard lives in device memory (this rank's contiguous slice of the frames when launched
+  under ``torch.distributed``); the train / test split consumes numpy's global RNG exactly like the
+  reference's ``train_test_split`` calls (core.py:465,468 / 672) and mini-batches are slices of the
+  device-resident shuffled copy (``shuffle=False``, ``drop_last=True`` semantics of core.py:472-481);
+* ``loss_func`` / ``weighted_MSE_loss`` return tensors whose ``backward()`` fills ``param.grad`` from the
+  fused CUDA passes (``colvarsfinder._ops``); ``optimizer.step()`` is stock ``torch.optim``.
+
+Outside the envelope (non-Tanh activations, transfer-operator loss ``lag_tau > 0``, arbitrary pp_layer
+modules, non-CUDA devices) the constructors raise: there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import copy
+import itertools
+import os
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import _ops
+from .nn import AutoEncoder, EigenFunctions
+
+
+class _NullWriter:
+    def add_scalar(self, *a, **k):
+        pass
+
+    def close(self):
+        pass
+
+
+def _make_writer(path):
+    """tensorboardX.SummaryWriter of the reference (core.py:143); torch's own writer when available."""
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        return SummaryWriter(path)
+    except Exception:
+        return _NullWriter()
+
+
+def _split(n, test_ratio, draws):
+    """Index split drawn like the reference: sklearn on numpy's global RNG, `draws` calls, last one kept."""
+    from sklearn.model_selection import train_test_split
+    for _ in range(draws):
+        tr, te = train_test_split(np.arange(n), test_size=test_ratio)
+    return tr, te
+
+
+class TrainingTask(ABC):
+    """Common state of the training tasks (reference core.py:60-249)."""
+
+    def __init__(self, traj_obj, pp_layer, model, model_path, learning_rate, load_model_filename, save_model_every_step, k,
+                 batch_size, num_epochs, test_ratio, optimizer_name, device, plot_class, plot_frequency, verbose, debug_mode):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError(f"device={device}: this build of colvarsfinder runs the training step in sm_100a CUDA "
+                               "kernels only; pass device=torch.device('cuda')")
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.traj_obj = traj_obj
+        self.preprocessing_layer = pp_layer.to(device)
+        self.learning_rate = learning_rate
+        self.batch_size = batch_size
+        self.num_epochs = num_epochs
+        self.test_ratio = test_ratio
+        self.k = k
+        self.model = model.to(device)
+        self.load_model_filename = load_model_filename
+        self.save_model_every_step = save_model_every_step
+        self.model_path = model_path
+        self.optimizer_name = optimizer_name
+        self.device = device
+        self.plot_class = plot_class
+        self.plot_frequency = plot_frequency
+        self.verbose = verbose
+        self.debug_mode = debug_mode
+        self.model_name = type(self).__name__
+        self._rank, self._world = _ops.rank(), _ops.world_size()
+        if self.verbose:
+            print('\n[Info] Log directory: {}\n'.format(self.model_path), flush=True)
+        self.writer = _make_writer(self.model_path) if self._rank == 0 else _NullWriter()
+
+    def init_model_and_optimizer(self):
+        """Optionally load weights (strict=False), then Adam ('adam', any case) or SGD (reference core.py:145-166)."""
+        if self.load_model_filename:
+            if os.path.isfile(self.load_model_filename):
+                self.model.load_state_dict(torch.load(self.load_model_filename, map_location=self.device), strict=False)
+                if self.verbose:
+                    print(f'model parameters loaded from: {self.load_model_filename}')
+            elif self.verbose:
+                print(f'model file not found: {self.load_model_filename}')
+        if self.optimizer_name.lower() == 'adam':
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.learning_rate)
+        else:
+            self.optimizer = torch.optim.SGD(self.model.parameters(), lr=self.learning_rate)
+
+    def save_model(self, epoch, description="latest"):
+        """model.pt + per-CV parameter text files (reference core.py:168-208).  Rank 0 only."""
+        if self._rank != 0:
+            return
+        if self.verbose:
+            print(f"\n\nEpoch={epoch}:")
+        if self.debug_mode is True:
+            d = f'{self.model_path}/models'
+            os.makedirs(d, exist_ok=True)
+            torch.save(self.model.state_dict(), f'{d}/model_{epoch}.pt')
+        d = f'{self.model_path}/{description}'
+        os.makedirs(d, exist_ok=True)
+        torch.save(self.model.state_dict(), f'{d}/model.pt')
+        for idx in range(self.k):
+            for name, param in self.model.get_params_of_cv(idx):
+                np.savetxt('%s/%d_' % (d, idx) + name.replace('.', '_') + '.txt', param.detach().cpu().numpy())
+        if self.verbose:
+            print(f'  trained model saved at:\n\t{d}/model.pt')
+
+    def _shard(self, n):
+        return _ops.shard_range(n, self._rank, self._world)
+
+    @abstractmethod
+    def train(self):
+        pass
+
+    @abstractmethod
+    def colvar_model(self):
+        pass
+
+    @abstractmethod
+    def reg_model(self):
+        pass
+
+
+class EigenFunctionTask(TrainingTask):
+    """Eigenfunctions of the generator by the variational (Rayleigh-quotient) loss (reference core.py:251-566)."""
+
+    def __init__(self, traj_obj, pp_layer, model, model_path, alpha, eig_weights, diag_coeff=None, beta=1.0, lag_tau=0,
+                 learning_rate=0.01, load_model_filename=None, save_model_every_step=10, sort_eigvals_in_training=True, k=1,
+                 batch_size=1000, num_epochs=10, test_ratio=0.2, optimizer_name='Adam', device=torch.device('cuda'),
+                 plot_class=None, plot_frequency=0, verbose=True, debug_mode=True):
+        super().__init__(traj_obj, pp_layer, model, model_path, learning_rate, load_model_filename, save_model_every_step, k,
+                         batch_size, num_epochs, test_ratio, optimizer_name, device, plot_class, plot_frequency, verbose,
+                         debug_mode)
+        assert isinstance(model, EigenFunctions), 'model must be an object of the class EigenFunctions'
+        assert k == len(model.eigen_funcs), \
+            f'number of cv ({k}) must equal the number of eigenfunctions ({len(model.eigen_funcs)})'
+        self._alpha = alpha
+        self._sort_eigvals_in_training = sort_eigvals_in_training
+        self._eig_w = eig_weights
+        self._cvec = None
+        self.traj_dt = traj_obj.dt
+        lag_idx = lag_tau / self.traj_dt
+        assert abs(lag_idx - int(lag_idx)) < 1e-6, \
+            f'lag-time ({lag_tau}) not divisable by the timestep {self.traj_dt} of the trajectory'
+        self.lag_idx = int(lag_idx)
+        if self.lag_idx > 0:
+            raise NotImplementedError(
+                "transfer-operator loss (lag_tau > 0, reference core.py:412-416,428,440) is not built yet in the CUDA "
+                "step; only the generator loss (lag_tau = 0) is available and there is no PyTorch fallback")
+        self._ij_list = list(itertools.combinations(range(self.k), 2))
+        self._num_ij_pairs = len(self._ij_list)
+        if self.verbose:
+            print('\nEigenfunctions:\n', self.model, flush=True)
+        self.init_model_and_optimizer()
+        traj = np.asarray(traj_obj.trajectory)
+        weights = np.asarray(traj_obj.weights)
+        self.tot_dim = traj[0, ...].size
+        self._beta = beta
+        if diag_coeff is not None:
+            assert diag_coeff.dim() == 1 and diag_coeff.size(dim=0) == self.tot_dim, \
+                f'diag_coeff should be a 1d tensor of length {self.tot_dim}, current shape: {diag_coeff}'
+            self._diag_coeff = diag_coeff
+        else:
+            self._diag_coeff = torch.ones(self.tot_dim)
+        # this rank's contiguous shard of the frames, resident in HBM
+        lo, hi = self._shard(traj.shape[0])
+        self._traj = torch.as_tensor(traj[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
+        self._weights = torch.as_tensor(weights[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
+        self._ctx = _ops.EigenContext(self.model, self.preprocessing_layer, traj.shape[1:], self.device, alpha, eig_weights,
+                                      beta, diag_coeff, sort_eigvals_in_training)
+
+    def get_reordered_eigenfunctions(self, model, cvec):
+        """Deep copy of `model` with its eigenfunctions permuted by cvec (reference core.py:356-370)."""
+        new = copy.deepcopy(model)
+        new.eigen_funcs = torch.nn.ModuleList([copy.deepcopy(model.eigen_funcs[int(i)]) for i in cvec])
+        return new
+
+    def colvar_model(self):
+        if self._cvec is None:
+            self._cvec = torch.arange(self.k)
+        return torch.nn.Sequential(self.preprocessing_layer, self.get_reordered_eigenfunctions(self.model, self._cvec))
+
+    def reg_model(self):
+        return None
+
+    def loss_func(self, X, weight, X_lagged=None, weight_lagged=None):
+        """Total loss, eigenvalues (sorted when sort_eigvals_in_training), variational objective, penalty and
+        the ordering cvec -- reference core.py:387-457, generator branch.  ``loss.backward()`` runs pass 2."""
+        if X_lagged is not None or weight_lagged is not None:
+            raise NotImplementedError("time-lagged data belong to the transfer-operator loss, which is not built yet")
+        return _ops.eigen_loss(self._ctx, X, weight)
+
+    def _epoch_batches(self, X, w, bs):
+        n = X.shape[0]
+        for s in range(0, n - bs + 1, bs):
+            yield X[s:s + bs], w[s:s + bs]
+
+    def train(self):
+        """Epoch / mini-batch loop of reference core.py:459-566 on device-resident shards."""
+        ll = self._traj.shape[0] - self.lag_idx
+        idx_train, idx_test = _split(ll, self.test_ratio, draws=2)      # the reference splits twice (core.py:465,468)
+        it, ie = torch.as_tensor(idx_train, device=self.device), torch.as_tensor(idx_test, device=self.device)
+        X_train, w_train = self._traj[it], self._weights[it]
+        X_test, w_test = self._traj[ie], self._weights[ie]
+        bs_train = min(self.batch_size, X_train.shape[0])
+        bs_test = min(self.batch_size, X_test.shape[0])
+        n_it_train, n_it_test = X_train.shape[0] // bs_train, X_test.shape[0] // bs_test
+        self.loss_list = []
+        min_loss = float("inf")
+        if self._rank == 0:
+            print("\nTraining starts.\n%d epochs in total, batch sizes (train/test): %d/%d" % (self.num_epochs, bs_train, bs_test))
+            print("\nTrain set:\n\t%d data, %d iterations per epoch, %d iterations in total." %
+                  (len(idx_train), n_it_train, n_it_train * self.num_epochs), flush=True)
+            print("Test set:\n\t%d data, %d iterations per epoch, %d iterations in total." %
+                  (len(idx_test), n_it_test, n_it_test * self.num_epochs), flush=True)
+        loss_names = ['loss', 'eigen_non_penalty', 'eigen_penalty'] + ['eig_%d' % (i + 1) for i in range(self.k)]
+        for epoch in range(self.num_epochs):
+            self.model.train()
+            train_rows = []
+            loss = None
+            for X, weight in self._epoch_batches(X_train, w_train, bs_train):
+                self.optimizer.zero_grad(set_to_none=True)
+                loss, eig_vals, non_penalty_loss, penalty, self._cvec = self.loss_func(X, weight, None, None)
+                loss.backward()
+                train_rows.append(torch.cat([torch.stack([loss.detach(), non_penalty_loss, penalty]), eig_vals]))
+                self.optimizer.step()
+            if self.save_model_every_step > 0 and epoch % self.save_model_every_step == self.save_model_every_step - 1:
+                self.save_model(epoch)
+                if loss is not None and loss < min_loss:
+                    min_loss = loss
+                    self.save_model(epoch, 'best')
+            if self.plot_frequency > 0 and epoch % self.plot_frequency == self.plot_frequency - 1:
+                if self.plot_class is not None:
+                    self.plot_class.plot(self.colvar_model(), epoch=epoch)
+            test_rows = []
+            for X, weight in self._epoch_batches(X_test, w_test, bs_test):
+                loss_t, eig_vals, non_penalty_loss, penalty, _ = self.loss_func(X, weight, None, None)
+                test_rows.append(torch.cat([torch.stack([loss_t.detach(), non_penalty_loss, penalty]), eig_vals]))
+            # one device->host transfer per epoch for the whole log
+            tr = torch.stack(train_rows).cpu() if train_rows else torch.zeros(0, 3 + self.k)
+            te = torch.stack(test_rows).cpu() if test_rows else torch.zeros(0, 3 + self.k)
+            self.loss_list.append([tr, te])
+            mean_tr, mean_te = torch.mean(tr, 0), torch.mean(te, 0)
+            for i, name in enumerate(loss_names):
+                self.writer.add_scalar('%s/train' % name, mean_tr[i], epoch)
+                self.writer.add_scalar('%s/test' % name, mean_te[i], epoch)
+        import pandas as pd
+        self.train_loss_df = pd.DataFrame(torch.cat([torch.mean(l[0], dim=0, keepdim=True) for l in self.loss_list]).numpy(),
+                                          columns=loss_names)
+        self.test_loss_df = pd.DataFrame(torch.cat([torch.mean(l[1], dim=0, keepdim=True) for l in self.loss_list]).numpy(),
+                                         columns=loss_names)
+
+
+class AutoEncoderTask(TrainingTask):
+    """Autoencoder with the weighted reconstruction loss (reference core.py:569-744)."""
+
+    def __init__(self, traj_obj, pp_layer, model, model_path, learning_rate=0.01, load_model_filename=None,
+                 save_model_every_step=10, batch_size=1000, num_epochs=10, test_ratio=0.2, optimizer_name='Adam',
+                 device=torch.device('cuda'), plot_class=None, plot_frequency=0, verbose=True, debug_mode=True):
+        super().__init__(traj_obj, pp_layer, model, model_path, learning_rate, load_model_filename, save_model_every_step,
+                         model.encoded_dim, batch_size, num_epochs, test_ratio, optimizer_name, device, plot_class,
+                         plot_frequency, verbose, debug_mode)
+        assert isinstance(model, AutoEncoder), 'model must be an object of the class AutoEncoder'
+        self.init_model_and_optimizer()
+        traj = np.asarray(traj_obj.trajectory)
+        lo, hi = self._shard(traj.shape[0])
+        self._weights = torch.as_tensor(np.asarray(traj_obj.weights)[lo:hi]).to(device=self.device, dtype=torch.float32)
+        x = torch.as_tensor(traj[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
+        # whole-trajectory pre-pass (reference core.py:635) on the device
+        self._feature_traj = self.preprocessing_layer(x)
+        if self._feature_traj.dim() != 2:
+            self._feature_traj = self._feature_traj.reshape(self._feature_traj.shape[0], -1)
+        self._feature_traj = self._feature_traj.contiguous()
+        if self.verbose:
+            print('\nShape of trajectory data array:\n {}'.format(self._feature_traj.shape), flush=True)
+        self._ctx = _ops.AEContext(self.model, self.device)
+
+    def colvar_model(self):
+        return torch.nn.Sequential(self.preprocessing_layer, self.model.encoder)
+
+    def reg_model(self):
+        return None
+
+    def weighted_MSE_loss(self, X, weight):
+        """sum_l w_l |dec(enc(X_l)) - X_l|^2 / sum_l w_l  (reference core.py:652-666)."""
+        return _ops.ae_loss(self._ctx, X, weight)
+
+    def train(self):
+        """Loop of reference core.py:668-744."""
+        n = self._feature_traj.shape[0]
+        idx_train, idx_test = _split(n, self.test_ratio, draws=1)
+        it, ie = torch.as_tensor(idx_train, device=self.device), torch.as_tensor(idx_test, device=self.device)
+        X_train, w_train = self._feature_traj[it], self._weights[it]
+        X_test, w_test = self._feature_traj[ie], self._weights[ie]
+        bs_train = min(self.batch_size, X_train.shape[0])
+        bs_test = min(self.batch_size, X_test.shape[0])
+        n_it_train, n_it_test = X_train.shape[0] // bs_train, X_test.shape[0] // bs_test
+        self.loss_list = []
+        min_loss = float("inf")
+        if self._rank == 0:
+            print("\nTraining starts.\n%d epochs in total, batch sizes (train/test): %d/%d" % (self.num_epochs, bs_train, bs_test))
+            print("\nTrain set:\n\t%d data, %d iterations per epoch, %d iterations in total." %
+                  (len(idx_train), n_it_train, n_it_train * self.num_epochs), flush=True)
+            print("Test set:\n\t%d data, %d iterations per epoch, %d iterations in total." %
+                  (len(idx_test), n_it_test, n_it_test * self.num_epochs), flush=True)
+        for epoch in range(self.num_epochs):
+            self.model.train()
+            train_loss = []
+            loss = None
+            for s in range(0, X_train.shape[0] - bs_train + 1, bs_train):
+                self.optimizer.zero_grad(set_to_none=True)
+                loss = self.weighted_MSE_loss(X_train[s:s + bs_train], w_train[s:s + bs_train])
+                loss.backward()
+                train_loss.append(loss.detach())
+                self.optimizer.step()
+            if self.save_model_every_step > 0 and epoch % self.save_model_every_step == self.save_model_every_step - 1:
+                self.save_model(epoch)
+                if loss is not None and loss < min_loss:
+                    min_loss = loss
+                    self.save_model(epoch, 'best')
+            if self.plot_frequency > 0 and epoch % self.plot_frequency == self.plot_frequency - 1:
+                if self.plot_class is not None:
+                    self.plot_class.plot(self.colvar_model(), epoch=epoch)
+            self.model.eval()
+            with torch.no_grad():
+                test_loss = [self.weighted_MSE_loss(X_test[s:s + bs_test], w_test[s:s + bs_test])
+                             for s in range(0, X_test.shape[0] - bs_test + 1, bs_test)]
+            tr = torch.stack(train_loss).cpu() if train_loss else torch.zeros(0)
+            te = torch.stack(test_loss).cpu() if test_loss else torch.zeros(0)
+            self.loss_list.append([tr, te])
+            self.writer.add_scalar('Loss/train', torch.mean(tr), epoch)
+            self.writer.add_scalar('Loss/test', torch.mean(te), epoch)
+        import pandas as pd
+        self.train_loss_df = pd.DataFrame(torch.stack([torch.mean(l[0]) for l in self.loss_list]).numpy(), columns=['loss'])
+        self.test_loss_df = pd.DataFrame(torch.stack([torch.mean(l[1]) for l in self.loss_list]).numpy(), columns=['loss'])

@@ -1,0 +1,203 @@
+"""Trajectory holder and the pre-processing layers r(x) of the B200 training step.
+
+* ``WeightedTrajectory`` -- same contract as the reference's holder (reference utils.py:62-169): ``trajectory``
+  ([n,N,3] from an MDAnalysis-like universe or [n,d] from a text file), ``weights`` (mean 1, optionally
+  filtered to (min_w, max_w)), ``dt``, ``n_frames``.  Host side only.
+* ``Align`` / ``FeatureMap`` / ``Preprocessing`` -- the alignment + feature layer the reference borrows from
+  the third-party ``molann`` package (examples/dipeptide/main.ipynb:335-348).  Here they are descriptors:
+  the task classes lower them into ``cvf_preproc`` and the CUDA kernels evaluate alignment, features and
+  their (transpose-)Jacobians; calling the modules directly runs the stand-alone CUDA pre-pass
+  (``cvf_align_fwd`` / ``cvf_features_fwd``).  The integrators / weight calculators of the reference's
+  utils.py (data generation) are outside this package's scope.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_FEATURE_TYPES = {"position": (_lib.FEAT_POSITION, None, 3), "bond": (_lib.FEAT_BOND, 2, 1),
+                  "angle": (_lib.FEAT_ANGLE, 3, 1), "dihedral": (_lib.FEAT_DIHEDRAL, 4, 2)}
+
+
+class WeightedTrajectory:
+    """Trajectory data + statistical weights (reference utils.py:62-169)."""
+
+    def __init__(self, universe=None, input_ag=None, traj_filename=None, weight_filename=None, min_w=0.0,
+                 max_w=float("inf"), verbose=True):
+        if universe is not None:
+            ix = universe.atoms.ix if input_ag is None else input_ag.ix
+            self.trajectory = universe.trajectory.timeseries(order='fac')[:, ix, :]
+            self.n_frames = universe.trajectory.n_frames
+            self.dt = universe.trajectory.dt * 1e-3          # ps -> ns
+            if verbose:
+                print('\nTrajectory Info:\n  no. of frames in trajectory data: {}\n  stepsize: {:.1f}ps\n'
+                      '  shape of trajectory data array: {}\n'.format(self.n_frames, universe.trajectory.dt,
+                                                                       self.trajectory.shape))
+        else:
+            if traj_filename is None or not os.path.exists(traj_filename):
+                raise FileNotFoundError('trajectory file not found')
+            block = np.loadtxt(traj_filename)                  # column 0: time, the rest: state
+            self.n_frames = block.shape[0]
+            self.trajectory = block[:, 1:]
+            self.dt = block[1, 0] - block[0, 0]
+        if weight_filename:
+            import pandas as pd
+            w = pd.read_csv(weight_filename, usecols=[0], header=None)[0].to_numpy(dtype=np.float64)
+            w = w / w.mean()
+            if verbose:
+                print('\nloading weights from file: ', weight_filename)
+            if self.n_frames != len(w):
+                raise ValueError('length in weight file does match the trajectory data!\n')
+            keep = (w > min_w) & (w < max_w)
+            self.trajectory = self.trajectory[keep, ...]
+            w = w[keep]
+            self.weights = w / w.mean()
+            if verbose:
+                print('\nAfter selecting states whose weights are in [{:.3e}, {:.3e}] and renormalization:\n'
+                      '\nShape of trajectory: {}'.format(min_w, max_w, self.trajectory.shape))
+        else:
+            self.weights = np.ones(self.n_frames)
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda_f32(x, what):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise RuntimeError(f"{what}: input must be a CUDA tensor (this build has no CPU path)")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{what}: input must be float32, got {x.dtype}")
+    return x.contiguous()
+
+
+class Align(torch.nn.Module):
+    """Kabsch alignment of every frame onto a reference structure.
+
+    x [B,N,3] -> (x - c) R with c the centroid of the alignment atoms and R the proper rotation that best
+    superimposes them onto ``ref_positions`` (centred internally).  ``align_indices`` index the N input atoms.
+    """
+
+    def __init__(self, ref_positions, align_indices):
+        super().__init__()
+        ref = np.asarray(ref_positions, dtype=np.float64).reshape(-1, 3)
+        idx = np.asarray(align_indices, dtype=np.int64).reshape(-1)
+        if len(idx) != ref.shape[0]:
+            raise ValueError(f"{ref.shape[0]} reference positions for {len(idx)} alignment atoms")
+        if len(idx) < 3:
+            raise ValueError("alignment needs at least 3 atoms")
+        ref = ref - ref.mean(0, keepdims=True)
+        self.register_buffer("ref_pos", torch.as_tensor(ref, dtype=torch.float32))
+        self.register_buffer("align_idx", torch.as_tensor(idx, dtype=torch.int32))
+
+    @classmethod
+    def from_atom_groups(cls, align_atom_group, input_atom_group):
+        """molann-style construction (examples/dipeptide/main.ipynb:343-345): atom groups expose .ix and .positions."""
+        pos_of = {int(a): i for i, a in enumerate(np.asarray(input_atom_group.ix))}
+        local = [pos_of[int(a)] for a in np.asarray(align_atom_group.ix)]
+        return cls(np.asarray(align_atom_group.positions), local)
+
+    def show_info(self):
+        print('\natom indices used for alignment: \n', self.align_idx.cpu().numpy())
+        print('\npositions of reference state used in aligment:\n', self.ref_pos.cpu().numpy())
+
+    def forward(self, x):
+        x = _require_cuda_f32(x, "Align")
+        if x.dim() != 3 or x.shape[2] != 3:
+            raise RuntimeError(f"Align expects [B,N,3], got {tuple(x.shape)}")
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().cvf_align_fwd(x.data_ptr(), x.shape[0], x.shape[1], self.align_idx.data_ptr(),
+                                                self.align_idx.numel(), self.ref_pos.data_ptr(), y.data_ptr(), None,
+                                                None, _stream_ptr()), "cvf_align_fwd")
+        return y
+
+    def rotation(self, x):
+        """Aligned frames plus the rotation R [B,3,3] and centroid c [B,3] of every frame."""
+        x = _require_cuda_f32(x, "Align")
+        y = torch.empty_like(x)
+        R = torch.empty(x.shape[0], 3, 3, device=x.device, dtype=torch.float32)
+        c = torch.empty(x.shape[0], 3, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().cvf_align_fwd(x.data_ptr(), x.shape[0], x.shape[1], self.align_idx.data_ptr(),
+                                                self.align_idx.numel(), self.ref_pos.data_ptr(), y.data_ptr(),
+                                                R.data_ptr(), c.data_ptr(), _stream_ptr()), "cvf_align_fwd")
+        return y, R, c
+
+
+class FeatureMap(torch.nn.Module):
+    """Feature map on (aligned) coordinates [B,N,3] -> [B,d_r].
+
+    ``features``: list of ``(type, atom_indices)`` with type 'position' (any number of atoms, 3 outputs each),
+    'bond' (2 atoms, distance), 'angle' (3 atoms, cosine of the angle at the middle atom), 'dihedral'
+    (4 atoms, (cos, sin) of the dihedral angle); outputs are concatenated in list order.
+    """
+
+    def __init__(self, features):
+        super().__init__()
+        self.features = []
+        for ftype, atoms in features:
+            atoms = [int(a) for a in atoms]
+            if ftype not in _FEATURE_TYPES:
+                raise ValueError(f"unknown feature type {ftype!r} (position, bond, angle, dihedral)")
+            need = _FEATURE_TYPES[ftype][1]
+            if need is not None and len(atoms) != need:
+                raise ValueError(f"feature {ftype!r} takes {need} atoms, got {len(atoms)}")
+            self.features.append((ftype, atoms))
+        if not self.features:
+            raise ValueError("empty feature list")
+
+    def output_dimension(self):
+        return sum(3 * len(a) if t == "position" else _FEATURE_TYPES[t][2] for t, a in self.features)
+
+    def records(self):
+        """One (type id, atoms) record per kernel feature: multi-atom 'position' entries are split."""
+        out = []
+        for t, atoms in self.features:
+            if t == "position":
+                out += [(_lib.FEAT_POSITION, [a]) for a in atoms]
+            else:
+                out.append((_FEATURE_TYPES[t][0], atoms))
+        return out
+
+    def forward(self, x):
+        return Preprocessing(None, self)(x)
+
+
+class Preprocessing(torch.nn.Module):
+    """r(x) = features(align(x)); either part may be None (molann.ann.PreprocessingANN analogue,
+    examples/dipeptide/main.ipynb:348)."""
+
+    def __init__(self, align_layer=None, feature_layer=None):
+        super().__init__()
+        if align_layer is not None and not isinstance(align_layer, Align):
+            raise TypeError("align_layer must be colvarsfinder.utils.Align")
+        if feature_layer is not None and not isinstance(feature_layer, FeatureMap):
+            raise TypeError("feature_layer must be colvarsfinder.utils.FeatureMap")
+        self.align = align_layer
+        self.feature_mapper = feature_layer
+        self._spec_cache = {}
+
+    def output_dimension(self, n_atoms):
+        return 3 * n_atoms if self.feature_mapper is None else self.feature_mapper.output_dimension()
+
+    def forward(self, x):
+        from . import _ops
+        x = _require_cuda_f32(x, "Preprocessing")
+        if x.dim() != 3 or x.shape[2] != 3:
+            raise RuntimeError(f"Preprocessing expects [B,N,3], got {tuple(x.shape)}")
+        if self.feature_mapper is None:
+            return (self.align(x) if self.align is not None else x).reshape(x.shape[0], -1)
+        key = (x.device, x.shape[1])
+        if key not in self._spec_cache:
+            self._spec_cache[key] = _ops.PreprocSpec(self, x.shape[1:], x.device, None)
+        spec = self._spec_cache[key]
+        out = torch.empty(x.shape[0], spec.d_r, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().cvf_features_fwd(x.data_ptr(), x.shape[0], spec.struct_ptr(), out.data_ptr(),
+                                                   _stream_ptr()), "cvf_features_fwd")
+        return out

@@ -1,0 +1,233 @@
+// cvf_ae.cu -- AutoEncoderTask.weighted_MSE_loss + backward on sm_100a.
+//
+// Replaces, per mini-batch (reference file:line under /root/reference/colvarsfinder):
+//   core.py:664      out = model(X) = decoder(encoder(X))  (nn.py:114)  -> forward phases over the enc+dec chain
+//   core.py:666      (weight * ((out-X)**2).sum(1)).sum() / weight.sum() -> fp64 sums {sum w|e|^2, sum w}
+//   core.py:708      loss.backward()                                     -> reverse sweep + outer-product phases
+// The division by sum(w) happens after the cross-GPU sum, on the caller's side.
+//
+// Same row engine as the eigenfunction kernel (cvf_common.cuh): activations of every layer stay in
+// shared memory as [unit][frame] rows, weights stay resident, one persistent CTA per SM.
+#include <string.h>
+
+#include "cvf_common.cuh"
+
+namespace cvf {
+
+struct AePlan {
+  NetPlan net;
+  int F, FS, FB, nthreads;
+  int a_row[kMaxLayers + 1];   // activations A_0 (input) .. A_L (output)
+  int s_row[kMaxLayers + 1];   // adjoints of z_l, l = 1..L
+  int row_w, row_err;
+  int n_rows;
+  int off_params, off_rows, off_red;
+  size_t smem_bytes;
+};
+
+static size_t ae_layout(AePlan* P, int F) {
+  const NetPlan& np = P->net;
+  P->F = F, P->FS = F + 4, P->FB = F / 4;
+  int r = 0;
+  P->row_w = r++;
+  P->row_err = r++;
+  for (int l = 0; l <= np.L; ++l) P->a_row[l] = r, r += np.dims[l];
+  for (int l = 1; l <= np.L; ++l) P->s_row[l] = r, r += np.dims[l];
+  P->n_rows = r;
+  int off = 0;
+  P->off_params = off, off += np.smem_floats;
+  P->off_red = off, off += 2 * 2 * 4;
+  off = (off + 3) & ~3;
+  P->off_rows = off, off += r * P->FS;
+  P->smem_bytes = (size_t)off * sizeof(float);
+  return P->smem_bytes;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(256, 1)
+ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restrict__ w, long long B,
+          const float* __restrict__ params, double* __restrict__ partial) {
+  extern __shared__ __align__(16) float smem[];
+  const NetPlan& np = P.net;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int FS = P.FS, F = P.F, FB = P.FB, L = np.L;
+  float* Wsm = smem + P.off_params;
+  float* rows = smem + P.off_rows;
+  double* red = reinterpret_cast<double*>(smem + P.off_red);
+  load_net_params(np, params, Wsm, tid, nt);
+  const int n_part = 2 + (GRAD ? np.n_params : 0);
+  double* part = partial + (size_t)blockIdx.x * n_part;
+  for (int i = tid; i < n_part; i += nt) part[i] = 0.0;
+  double stat_acc = 0.0;   // thread 0: sum w |e|^2, thread 1: sum w
+  __syncthreads();
+  const int d0 = np.dims[0], dL = np.dims[L];
+  const long long n_tiles = (B + F - 1) / F;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long f_base = tile * F;
+    for (int idx = tid; idx < F * d0; idx += nt) {
+      const int f = idx / d0, j = idx - f * d0;
+      const long long fr = min(f_base + f, B - 1);
+      rows[(P.a_row[0] + j) * FS + f] = feat[fr * d0 + j];
+    }
+    for (int f = tid; f < F; f += nt) rows[P.row_w * FS + f] = f_base + f < B ? w[f_base + f] : 0.0f;
+    __syncthreads();
+    // ---- forward through encoder and decoder (nn.py:52-57,114)
+    for (int l = 0; l < L; ++l) {
+      const int nin = np.dims[l], nout = np.dims[l + 1];
+      const float* in = rows + P.a_row[l] * FS;
+      float* out = rows + P.a_row[l + 1] * FS;
+      const bool act = np.act[l] != 0;
+      const int items = ((nout + 3) >> 2) * FB;
+      for (int it = tid; it < items; it += nt) {
+        const int ob = it / FB, fb = it - ob * FB;
+        float acc[4][4];
+        tile_fwd(acc, Wsm + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, 4 * fb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = 4 * ob + j;
+          if (o < nout) {
+            const float b = Wsm[np.b_off[l] + o];
+            float4 v = make_float4(acc[j][0] + b, acc[j][1] + b, acc[j][2] + b, acc[j][3] + b);
+            if (act) v = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+            st4(out + o * FS + 4 * fb, v);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- per-frame squared error, batch sums, and the seed s_L = 2 w (out - X)   (core.py:666)
+    if (tid < F) {
+      const int f = tid;
+      const float wf = rows[P.row_w * FS + f];
+      const float* X = rows + P.a_row[0] * FS;
+      const float* O = rows + P.a_row[L] * FS;
+      float* S = rows + P.s_row[L] * FS;
+      double e = 0.0;
+      for (int o = 0; o < dL; ++o) {
+        const float d = O[o * FS + f] - X[o * FS + f];
+        e += (double)d * (double)d;
+        if (GRAD) S[o * FS + f] = 2.0f * wf * d;
+      }
+      double v0 = (double)wf * e, v1 = (double)wf;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      if ((tid & 31) == 0) red[(tid >> 5)] = v0, red[4 + (tid >> 5)] = v1;
+    }
+    __syncthreads();
+    if (tid < 2) {
+      double v = 0.0;
+      for (int q = 0; q < F / 32; ++q) v += red[tid * 4 + q];
+      stat_acc += v;
+    }
+    if (GRAD) {
+      // ---- reverse sweep: dW_l += s_l (x) A_{l-1}, db_l += sum_f s_l, s_{l-1} = (W_l^T s_l) .* act'(A_{l-1})
+      for (int l = L - 1; l >= 0; --l) {
+        const int nin = np.dims[l], nout = np.dims[l + 1];
+        const float* S = rows + P.s_row[l + 1] * FS;
+        const float* Ain = rows + P.a_row[l] * FS;
+        const int n_outer = ((nout + 3) >> 2) * ((nin + 3) >> 2);
+        const int n_back = l > 0 ? ((nin + 3) >> 2) * FB : 0;
+        // both kinds of work item only read s_l and A_{l-1}: run them in the same phase
+        for (int it = tid; it < n_outer + n_back; it += nt) {
+          if (it < n_outer) {
+            outer_item(it, nout, nin, S, Ain, nullptr, nullptr, FS, F, part + 2 + np.gw_off[l], part + 2 + np.gb_off[l]);
+          } else {
+            const int it2 = it - n_outer;
+            const int ib = it2 / FB, fb = it2 - ib * FB;
+            float acc[4][4];
+            tile_tr(acc, Wsm + np.w_off[l], np.ld[l], 4 * ib, nout, S, FS, 4 * fb);
+            float* Sout = rows + P.s_row[l] * FS;
+            const bool act = np.act[l - 1] != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * ib + j;
+              if (i < nin) {
+                float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                if (act) {
+                  const float4 a = ld4(Ain + i * FS + 4 * fb);
+                  v = make_float4(v.x * (1.f - a.x * a.x), v.y * (1.f - a.y * a.y), v.z * (1.f - a.z * a.z), v.w * (1.f - a.w * a.w));
+                }
+                st4(Sout + i * FS + 4 * fb, v);
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+    } else {
+      __syncthreads();
+    }
+  }
+  if (tid < 2) part[tid] = stat_acc;
+}
+
+}  // namespace cvf
+
+using namespace cvf;
+
+static int ae_plan(const cvf_mlp* net, AePlan* P) {
+  memset(P, 0, sizeof(*P));
+  int e = make_net_plan(net, &P->net);
+  if (e) return e;
+  if (P->net.dims[0] != P->net.dims[P->net.L]) {
+    set_error("autoencoder chain must map R^d to R^d (got %d -> %d)", P->net.dims[0], P->net.dims[P->net.L]);
+    return CVF_E_ARG;
+  }
+  const size_t cap = (size_t)max_smem_optin();
+  static const int Fs[3] = {128, 64, 32};
+  for (int c = 0; c < 3; ++c) {
+    if (ae_layout(P, Fs[c]) <= cap) break;
+    if (c == 2) {
+      set_error("autoencoder state does not fit shared memory (%zu B at 32 frames, %zu available); wide layers need the "
+                "tensor-core path, which this build does not have", P->smem_bytes, cap);
+      return CVF_E_UNSUPPORTED;
+    }
+  }
+  P->nthreads = 256;
+  return 0;
+}
+
+extern "C" size_t cvf_ae_workspace_bytes(const cvf_mlp* net) {
+  NetPlan np;
+  if (make_net_plan(net, &np)) return 0;
+  return (size_t)(2 + np.n_params) * sizeof(double) * (size_t)sm_count();
+}
+
+extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
+                           double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AePlan P;
+  int e = ae_plan(net, &P);
+  if (e) return e;
+  if (!feat || !w || !params || !sums_out || !workspace || B < 1) {
+    set_error("cvf_ae_step: null pointer or empty batch");
+    return CVF_E_ARG;
+  }
+  const bool grad = grad_out != nullptr;
+  const int n_part = 2 + (grad ? P.net.n_params : 0);
+  const long long n_tiles = (B + P.F - 1) / P.F;
+  int grid = sm_count();
+  if (n_tiles < grid) grid = (int)n_tiles;
+  if ((size_t)grid * n_part * sizeof(double) > workspace_bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, (size_t)grid * n_part * sizeof(double));
+    return CVF_E_WORKSPACE;
+  }
+  if (grad) {
+    CVF_CUDA(cudaFuncSetAttribute(ae_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    ae_kernel<true><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
+  } else {
+    CVF_CUDA(cudaFuncSetAttribute(ae_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    ae_kernel<false><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
+  }
+  CVF_CUDA(cudaGetLastError());
+  // partial layout per CTA: [sum w|e|^2, sum w, grad...]; two reductions keep the output buffers separate
+  reduce_partials_kernel<<<1, 32, 0, stream>>>((const double*)workspace, grid, n_part, 0, 2, sums_out);
+  if (grad)
+    reduce_partials_kernel<<<(P.net.n_params + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 2,
+                                                                             P.net.n_params, grad_out);
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}

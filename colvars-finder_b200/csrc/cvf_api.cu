@@ -1,0 +1,49 @@
+// cvf_api.cu -- version, error reporting and device queries of libcvf_sm100.so.
+#include <stdarg.h>
+
+#include "cvf_common.cuh"
+
+namespace cvf {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+static int g_sms[64];
+static int g_smem[64];
+
+static int device_attr(int* cache, cudaDeviceAttr attr, int fallback) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fallback;
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, attr, dev) != cudaSuccess || v <= 0) return fallback;
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
+int sm_count() { return device_attr(g_sms, cudaDevAttrMultiProcessorCount, 148); }
+int max_smem_optin() { return device_attr(g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, 232448); }
+
+}  // namespace cvf
+
+extern "C" int cvf_version(void) { return CVF_VERSION; }
+extern "C" const char* cvf_last_error_string(void) { return cvf::g_err; }
+
+extern "C" int64_t cvf_mlp_param_count(const cvf_mlp* net) {
+  cvf::NetPlan np;
+  if (cvf::make_net_plan(net, &np)) return -1;
+  return np.n_params;
+}

@@ -1,0 +1,790 @@
+// cvf_eigen.cu -- EigenFunctionTask.loss_func (generator branch) + backward on sm_100a.
+//
+// Replaces, per mini-batch (reference file:line under /root/reference/colvarsfinder):
+//   core.py:403      y = model(pp_layer(X))                          -> load_tile / preprocess_frame / forward phases
+//   core.py:406-410  total weight, weighted means / variances         -> fp64 batch sums S0, S1, S2
+//   core.py:424      torch.autograd.grad(y_i.sum(), X, create_graph)  -> reverse phases + closed-form J_r^T (jphase)
+//   core.py:426,438  Rayleigh quotients / objective                   -> SD + cvf_eigen_combine
+//   core.py:446-455  penalty, total loss                              -> cvf_eigen_combine
+//   core.py:517      loss.backward() (double backward)                -> pass 2: one tangent sweep + one reverse sweep
+//
+// One persistent CTA per SM walks over tiles of F frames.  See cvf_common.cuh for the row layout.  The k
+// networks are processed one after the other inside a tile so that one network's state
+// (activations A, adjoints G, tangents T, second adjoints S) fits in shared memory next to the frame.
+#include <math.h>
+#include <string.h>
+
+#include "cvf_common.cuh"
+#include "cvf_math.cuh"
+
+namespace cvf {
+
+struct EigenPlan {
+  NetPlan net;
+  int k;
+  int F, FS, FB;  // frames per tile, row stride, 4-frame blocks per tile
+  int nthreads;
+  // pre-processing
+  int kind, dim, n_atoms, n_used, n_align, n_feat, d_r;
+  const int32_t* used_atoms;
+  const int32_t* align_used;
+  const float* ref;
+  const int32_t* feat;
+  const float* diag;
+  int pos_alias;   // features are exactly the positions of the used atoms in order: r rows alias the y rows
+  // rows (units of FS floats from the row base)
+  int row_w, row_one, row_seed, row_R, row_Kinv, row_y, row_D, row_Y, row_r, row_net;
+  int a_row[kMaxLayers + 1], g_row[kMaxLayers + 1], t_row[kMaxLayers + 1], s_row[kMaxLayers + 1];  // relative to row_net
+  int v_row, gx_row;   // relative to row_net
+  int n_rows;
+  // shared memory carve-up (floats)
+  int off_params, off_rows, off_comb, off_red;
+  size_t smem_bytes;
+  int n_stats;
+};
+
+static int build_plan(const cvf_preproc* pp, const cvf_mlp* net, int k, EigenPlan* P) {
+  memset(P, 0, sizeof(*P));
+  if (!pp || !net) {
+    set_error("null descriptor");
+    return CVF_E_ARG;
+  }
+  if (k < 1 || k > kMaxK) {
+    set_error("k = %d outside [1,%d]", k, kMaxK);
+    return CVF_E_UNSUPPORTED;
+  }
+  int e = make_net_plan(net, &P->net);
+  if (e) return e;
+  const NetPlan& np = P->net;
+  if (np.dims[np.L] != 1) {
+    set_error("eigenfunction networks must be scalar valued (nn.py:270)");
+    return CVF_E_ARG;
+  }
+  for (int l = 0; l < np.L; ++l)
+    if (np.act[l] != (l < np.L - 1 ? 1 : 0)) {
+      set_error("eigenfunction networks: tanh after every layer but the last");
+      return CVF_E_UNSUPPORTED;
+    }
+  P->k = k;
+  P->kind = pp->kind;
+  if (pp->kind == 0) {
+    if (pp->dim < 1 || pp->dim != np.dims[0]) {
+      set_error("identity pre-processing: dim %d != network input %d", pp->dim, np.dims[0]);
+      return CVF_E_ARG;
+    }
+    P->dim = pp->dim;
+    P->d_r = pp->dim;
+  } else if (pp->kind == 1) {
+    if (pp->n_atoms < 1 || pp->n_used < 1 || pp->n_used > pp->n_atoms || !pp->used_atoms || pp->n_feat < 1 || !pp->feat ||
+        pp->d_r != np.dims[0] || (pp->n_align > 0 && (!pp->align_used || !pp->ref)) || pp->n_align < 0) {
+      set_error("molecular pre-processing descriptor inconsistent (d_r %d, network input %d)", pp->d_r, np.dims[0]);
+      return CVF_E_ARG;
+    }
+    if (pp->n_align > 0 && pp->n_align < 3) {
+      set_error("alignment needs at least 3 atoms");
+      return CVF_E_ARG;
+    }
+    P->n_atoms = pp->n_atoms, P->n_used = pp->n_used, P->n_align = pp->n_align, P->n_feat = pp->n_feat, P->d_r = pp->d_r;
+    P->used_atoms = pp->used_atoms, P->align_used = pp->align_used, P->ref = pp->ref, P->feat = pp->feat;
+    if (pp->positions_only && (pp->n_feat != pp->n_used || pp->d_r != 3 * pp->n_used)) {
+      set_error("positions_only needs n_feat == n_used and d_r == 3 n_used");
+      return CVF_E_ARG;
+    }
+  } else {
+    set_error("unknown pre-processing kind %d", pp->kind);
+    return CVF_E_ARG;
+  }
+  P->diag = pp->diag;
+  P->n_stats = 1 + 2 * k + k * k;
+  return 0;
+}
+
+// Decide the row map for a given tile size; returns the shared-memory bytes needed.
+static size_t layout_plan(EigenPlan* P, int F, bool pos_alias) {
+  const NetPlan& np = P->net;
+  P->F = F, P->FS = F + 4, P->FB = F / 4;
+  P->pos_alias = pos_alias ? 1 : 0;
+  int r = 0;
+  P->row_w = r++;
+  P->row_one = r++;
+  P->row_seed = r++;
+  P->row_R = r, r += 9;
+  P->row_Kinv = r, r += 6;
+  P->row_y = r, r += P->k;
+  P->row_D = r, r += P->k;
+  if (P->kind == 1) {
+    P->row_Y = r, r += 3 * P->n_used;
+    if (pos_alias) P->row_r = P->row_Y;
+    else P->row_r = r, r += P->d_r;
+  } else {
+    P->row_Y = r;
+    P->row_r = r, r += P->d_r;
+  }
+  P->row_net = r;
+  int sumH = 0;
+  for (int l = 1; l < np.L; ++l) sumH += np.dims[l];
+  int q = 0;
+  for (int l = 1; l < np.L; ++l) P->a_row[l] = q, q += np.dims[l];
+  for (int l = 1; l < np.L; ++l) P->g_row[l] = q, q += np.dims[l];
+  // region shared by (T,S) and, before the tangent sweep starts, by V (d_r rows) and GX (3 n_used rows):
+  //   [ T_1 | S_1 | T_2 .. | S_2 .. ]   and   [ T_1 | S_1 | V | GX ]
+  const int ts0 = q;
+  int t = ts0;
+  if (np.L > 1) {
+    P->t_row[1] = t, t += np.dims[1];
+    P->s_row[1] = t, t += np.dims[1];
+  }
+  const int after1 = t;
+  for (int l = 2; l < np.L; ++l) P->t_row[l] = t, t += np.dims[l];
+  for (int l = 2; l < np.L; ++l) P->s_row[l] = t, t += np.dims[l];
+  P->v_row = after1;
+  int vend = after1 + P->d_r;
+  if (P->kind == 1 && !pos_alias) {
+    P->gx_row = vend;
+    vend += 3 * P->n_used;
+  } else {
+    P->gx_row = P->v_row;   // positions only: dg/dy is u itself and dy is v itself
+  }
+  q = t > vend ? t : vend;
+  (void)sumH;
+  P->n_rows = P->row_net + q;
+  // floats
+  int off = 0;
+  P->off_params = off, off += P->k * np.smem_floats;
+  P->off_comb = off, off += round4(2 * (3 + 4 * P->k + P->k * P->k));    // combine vector as doubles
+  P->off_red = off, off += 2 * 4 * P->n_stats;   // warp-reduction scratch: n_stats x 4 warps, doubles
+  off = (off + 3) & ~3;
+  P->off_rows = off, off += P->n_rows * P->FS;
+  P->smem_bytes = (size_t)off * sizeof(float);
+  return P->smem_bytes;
+}
+
+static int finish_plan(EigenPlan* P, bool pos_alias) {
+  const size_t cap = (size_t)max_smem_optin();
+  static const int Fs[3] = {128, 64, 32};
+  for (int c = 0; c < 3; ++c) {
+    if (layout_plan(P, Fs[c], pos_alias) <= cap) break;
+    if (c == 2) {
+      set_error("network/pre-processing state does not fit shared memory (%zu B needed at 32 frames, %zu available)",
+                P->smem_bytes, cap);
+      return CVF_E_UNSUPPORTED;
+    }
+  }
+  P->nthreads = 256;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cvf_v3 ldv(const float* rows, int FS, int atom, int f) {
+  return v3(rows[(3 * atom + 0) * FS + f], rows[(3 * atom + 1) * FS + f], rows[(3 * atom + 2) * FS + f]);
+}
+__device__ __forceinline__ void stv(float* rows, int FS, int atom, int f, cvf_v3 v) {
+  rows[(3 * atom + 0) * FS + f] = v.x;
+  rows[(3 * atom + 1) * FS + f] = v.y;
+  rows[(3 * atom + 2) * FS + f] = v.z;
+}
+__device__ __forceinline__ void addv(float* rows, int FS, int atom, int f, cvf_v3 v) {
+  rows[(3 * atom + 0) * FS + f] += v.x;
+  rows[(3 * atom + 1) * FS + f] += v.y;
+  rows[(3 * atom + 2) * FS + f] += v.z;
+}
+
+// Kabsch alignment of frame f in place on the Y rows + feature values into the r rows (thread per frame).
+__device__ void preprocess_frame(const EigenPlan& P, float* rows, int f) {
+  const int FS = P.FS;
+  float* Y = rows + P.row_Y * FS;
+  if (P.n_align > 0) {
+    double cx = 0, cy = 0, cz = 0;
+    for (int a = 0; a < P.n_align; ++a) {
+      const cvf_v3 p = ldv(Y, FS, P.align_used[a], f);
+      cx += p.x, cy += p.y, cz += p.z;
+    }
+    const double inv = 1.0 / P.n_align;
+    cx *= inv, cy *= inv, cz *= inv;
+    double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < P.n_align; ++a) {
+      const cvf_v3 p = ldv(Y, FS, P.align_used[a], f);
+      const double px = p.x - cx, py = p.y - cy, pz = p.z - cz;
+      const double rx = P.ref[3 * a], ry = P.ref[3 * a + 1], rz = P.ref[3 * a + 2];
+      H[0] += px * rx, H[1] += px * ry, H[2] += px * rz;
+      H[3] += py * rx, H[4] += py * ry, H[5] += py * rz;
+      H[6] += pz * rx, H[7] += pz * ry, H[8] += pz * rz;
+    }
+    float R[9], Ki[6];
+    cvf_rotation(H, R, Ki);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rows[(P.row_R + i) * FS + f] = R[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rows[(P.row_Kinv + i) * FS + f] = Ki[i];
+    const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+    for (int a = 0; a < P.n_used; ++a) {
+      const cvf_v3 p = ldv(Y, FS, a, f);
+      stv(Y, FS, a, f, mul_rowvec(v3(p.x - fx, p.y - fy, p.z - fz), R));
+    }
+  }
+  if (P.pos_alias) return;
+  float* r = rows + P.row_r * FS;
+  int col = 0;
+  for (int j = 0; j < P.n_feat; ++j) {
+    const int32_t* fr = P.feat + 5 * j;
+    const int type = fr[0];
+    if (type == CVF_FEAT_POSITION) {
+      const cvf_v3 p = ldv(Y, FS, fr[1], f);
+      r[(col + 0) * FS + f] = p.x, r[(col + 1) * FS + f] = p.y, r[(col + 2) * FS + f] = p.z;
+      col += 3;
+    } else if (type == CVF_FEAT_BOND) {
+      cvf_v3 g;
+      r[col * FS + f] = cvf_bond(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), g);
+      col += 1;
+    } else if (type == CVF_FEAT_ANGLE) {
+      cvf_v3 ga, gc;
+      r[col * FS + f] = cvf_angle(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), ldv(Y, FS, fr[3], f), ga, gc);
+      col += 1;
+    } else {
+      float cs, sn;
+      cvf_v3 g[4];
+      cvf_dihedral(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), ldv(Y, FS, fr[3], f), ldv(Y, FS, fr[4], f), cs, sn, g);
+      r[col * FS + f] = cs, r[(col + 1) * FS + f] = sn;
+      col += 2;
+    }
+  }
+}
+
+// J phase for frame f of one network.  In: V rows = u = dg/dr.  Out: returns the Dirichlet density
+// D = sum_j a_j (df/dx_j)^2;  if `tangent`, V rows <- scale * J_r (a .* J_r^T u).
+__device__ float jphase_frame(const EigenPlan& P, float* rows, float* netrows, int f, bool tangent, float scale) {
+  const int FS = P.FS;
+  float* V = netrows + P.v_row * FS;
+  float D = 0.0f;
+  if (P.kind == 0) {
+    for (int j = 0; j < P.dim; ++j) {
+      const float u = V[j * FS + f];
+      const float a = P.diag ? P.diag[j] : 1.0f;
+      D = fmaf(a * u, u, D);
+      if (tangent) V[j * FS + f] = scale * a * u;
+    }
+    return D;
+  }
+  const float* Y = rows + P.row_Y * FS;
+  float* GX = netrows + P.gx_row * FS;
+  // 1. G = (d r / d y)^T u
+  if (!P.pos_alias) {
+    for (int j = 0; j < 3 * P.n_used; ++j) GX[j * FS + f] = 0.0f;
+    int col = 0;
+    for (int j = 0; j < P.n_feat; ++j) {
+      const int32_t* fr = P.feat + 5 * j;
+      const int type = fr[0];
+      if (type == CVF_FEAT_POSITION) {
+        addv(GX, FS, fr[1], f, v3(V[col * FS + f], V[(col + 1) * FS + f], V[(col + 2) * FS + f]));
+        col += 3;
+      } else if (type == CVF_FEAT_BOND) {
+        cvf_v3 g;
+        cvf_bond(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), g);
+        const float u = V[col * FS + f];
+        addv(GX, FS, fr[2], f, u * g);
+        addv(GX, FS, fr[1], f, (-u) * g);
+        col += 1;
+      } else if (type == CVF_FEAT_ANGLE) {
+        cvf_v3 ga, gc;
+        cvf_angle(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), ldv(Y, FS, fr[3], f), ga, gc);
+        const float u = V[col * FS + f];
+        addv(GX, FS, fr[1], f, u * ga);
+        addv(GX, FS, fr[3], f, u * gc);
+        addv(GX, FS, fr[2], f, (-u) * (ga + gc));
+        col += 1;
+      } else {
+        float cs, sn;
+        cvf_v3 g[4];
+        cvf_dihedral(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), ldv(Y, FS, fr[3], f), ldv(Y, FS, fr[4], f), cs, sn, g);
+        const float s = -sn * V[col * FS + f] + cs * V[(col + 1) * FS + f];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) addv(GX, FS, fr[1 + a], f, s * g[a]);
+        col += 2;
+      }
+    }
+  }
+  // 2. through the alignment, weight by diag_coeff, and back (J_r of the alignment)
+  float R[9], Ki[6];
+  if (P.n_align > 0) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = rows[(P.row_R + i) * FS + f];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Ki[i] = rows[(P.row_Kinv + i) * FS + f];
+    cvf_v3 tau = v3(0, 0, 0), gs = v3(0, 0, 0);
+    for (int a = 0; a < P.n_used; ++a) {
+      const cvf_v3 g = ldv(GX, FS, a, f);
+      tau = tau + cross(g, ldv(Y, FS, a, f));
+      gs = gs + g;
+    }
+    const cvf_v3 q = mul_sym(Ki, tau);
+    const cvf_v3 gm = (1.0f / P.n_align) * gs;
+    for (int a = 0; a < P.n_align; ++a) {
+      const int at = P.align_used[a];
+      const cvf_v3 rf = v3(P.ref[3 * a], P.ref[3 * a + 1], P.ref[3 * a + 2]);
+      addv(GX, FS, at, f, (-1.0f) * (gm + cross(rf, q)));
+    }
+  }
+  // GX now holds  (df/dx) R  (i.e. the x-space gradient rotated into the aligned frame)
+  if (P.diag == nullptr) {
+    for (int a = 0; a < P.n_used; ++a) {
+      const cvf_v3 g = ldv(GX, FS, a, f);
+      D += dot(g, g);
+    }
+  } else {
+    for (int a = 0; a < P.n_used; ++a) {
+      cvf_v3 g = ldv(GX, FS, a, f);
+      if (P.n_align > 0) g = mul_rowvec_T(g, R);          // df/dx
+      const cvf_v3 h = v3(P.diag[3 * a] * g.x, P.diag[3 * a + 1] * g.y, P.diag[3 * a + 2] * g.z);
+      D += dot(g, h);
+      if (tangent) stv(GX, FS, a, f, P.n_align > 0 ? mul_rowvec(h, R) : h);   // h R
+    }
+  }
+  if (!tangent) return D;
+  if (P.n_align > 0) {
+    cvf_v3 dc = v3(0, 0, 0);
+    for (int a = 0; a < P.n_align; ++a) dc = dc + ldv(GX, FS, P.align_used[a], f);
+    dc = (1.0f / P.n_align) * dc;
+    cvf_v3 tq = v3(0, 0, 0);
+    for (int a = 0; a < P.n_align; ++a) {
+      const cvf_v3 rf = v3(P.ref[3 * a], P.ref[3 * a + 1], P.ref[3 * a + 2]);
+      tq = tq + cross(ldv(GX, FS, P.align_used[a], f) - dc, rf);
+    }
+    const cvf_v3 om = mul_sym(Ki, tq);
+    for (int a = 0; a < P.n_used; ++a) {
+      const cvf_v3 u = ldv(GX, FS, a, f) - dc;
+      stv(GX, FS, a, f, scale * (u + cross(om, ldv(Y, FS, a, f))));
+    }
+  } else {
+    for (int j = 0; j < 3 * P.n_used; ++j) GX[j * FS + f] *= scale;
+  }
+  // 3. v = (d r / d y) dy
+  if (!P.pos_alias) {
+    int col = 0;
+    for (int j = 0; j < P.n_feat; ++j) {
+      const int32_t* fr = P.feat + 5 * j;
+      const int type = fr[0];
+      if (type == CVF_FEAT_POSITION) {
+        const cvf_v3 d = ldv(GX, FS, fr[1], f);
+        V[col * FS + f] = d.x, V[(col + 1) * FS + f] = d.y, V[(col + 2) * FS + f] = d.z;
+        col += 3;
+      } else if (type == CVF_FEAT_BOND) {
+        cvf_v3 g;
+        cvf_bond(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), g);
+        V[col * FS + f] = dot(g, ldv(GX, FS, fr[2], f) - ldv(GX, FS, fr[1], f));
+        col += 1;
+      } else if (type == CVF_FEAT_ANGLE) {
+        cvf_v3 ga, gc;
+        cvf_angle(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), ldv(Y, FS, fr[3], f), ga, gc);
+        const cvf_v3 dm = ldv(GX, FS, fr[2], f);
+        V[col * FS + f] = dot(ga, ldv(GX, FS, fr[1], f) - dm) + dot(gc, ldv(GX, FS, fr[3], f) - dm);
+        col += 1;
+      } else {
+        float cs, sn;
+        cvf_v3 g[4];
+        cvf_dihedral(ldv(Y, FS, fr[1], f), ldv(Y, FS, fr[2], f), ldv(Y, FS, fr[3], f), ldv(Y, FS, fr[4], f), cs, sn, g);
+        float dphi = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dphi += dot(g[a], ldv(GX, FS, fr[1 + a], f));
+        V[col * FS + f] = -sn * dphi, V[(col + 1) * FS + f] = cs * dphi;
+        col += 2;
+      }
+    }
+  }
+  return D;
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void __launch_bounds__(256, 1)
+eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __restrict__ w, long long B,
+             const float* __restrict__ params, float* __restrict__ y_io, const double* __restrict__ combine,
+             double* __restrict__ partial) {
+  extern __shared__ __align__(16) float smem[];
+  const NetPlan& np = P.net;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int FS = P.FS, F = P.F, FB = P.FB, k = P.k;
+  float* Wsm = smem + P.off_params;
+  float* rows = smem + P.off_rows;
+  double* comb = reinterpret_cast<double*>(smem + P.off_comb);
+  double* red = reinterpret_cast<double*>(smem + P.off_red);
+
+  for (int i = 0; i < k; ++i) load_net_params(np, params + (size_t)i * np.n_params, Wsm + i * np.smem_floats, tid, nt);
+  for (int f = tid; f < FS; f += nt) rows[P.row_one * FS + f] = 1.0f;
+  const int n_part = GRAD ? k * np.n_params : P.n_stats;
+  double* part = partial + (size_t)blockIdx.x * n_part;
+  if (GRAD) {
+    const int nc = 3 + 4 * k + k * k;
+    for (int i = tid; i < nc; i += nt) comb[i] = combine[i];
+    for (int i = tid; i < n_part; i += nt) part[i] = 0.0;
+  }
+  double stat_acc = 0.0;   // thread `tid` owns batch sum number `tid` (stats pass)
+  __syncthreads();
+  // combine vector layout: loss, obj, pen, eig[k], cvec[k], mean[k], cD[k], C2[k*k]
+  const double* c_mean = comb + 3 + 2 * k;
+  const double* c_cD = comb + 3 + 3 * k;
+  const double* c_C2 = comb + 3 + 4 * k;
+
+  const long long n_tiles = (B + F - 1) / F;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long f_base = tile * F;
+    // ---- load the tile: frames -> rows (transposed), weights, (pass 2) y of every network
+    if (P.kind == 0) {
+      const int d = P.dim;
+      for (int idx = tid; idx < F * d; idx += nt) {
+        const int f = idx / d, j = idx - f * d;
+        const long long fr = min(f_base + f, B - 1);
+        rows[(P.row_r + j) * FS + f] = x[fr * d + j];
+      }
+    } else {
+      const int nu3 = 3 * P.n_used;
+      const long long stride = 3LL * P.n_atoms;
+      for (int idx = tid; idx < F * nu3; idx += nt) {
+        const int f = idx / nu3, j = idx - f * nu3;
+        const int a = j / 3, c = j - 3 * a;
+        const long long fr = min(f_base + f, B - 1);
+        rows[(P.row_Y + j) * FS + f] = x[fr * stride + 3 * P.used_atoms[a] + c];
+      }
+    }
+    for (int f = tid; f < F; f += nt) {
+      const long long fr = f_base + f;
+      rows[P.row_w * FS + f] = fr < B ? w[fr] : 0.0f;
+      if (GRAD)
+        for (int i = 0; i < k; ++i) rows[(P.row_y + i) * FS + f] = y_io[(size_t)i * B + min(fr, B - 1)];
+    }
+    __syncthreads();
+    if (P.kind == 1) {
+      if (tid < F) preprocess_frame(P, rows, tid);
+      __syncthreads();
+    }
+    float* netrows = rows + P.row_net * FS;
+    const float* r_in = rows + P.row_r * FS;
+
+    for (int n = 0; n < k; ++n) {
+      const float* Wn = Wsm + n * np.smem_floats;
+      // ---- forward (nn.py:52-57): A_l = tanh(W_l A_{l-1} + b_l), y = W_L A_{L-1} + b_L
+      for (int l = 0; l < (GRAD ? np.L - 1 : np.L); ++l) {   // pass 2 keeps the y of pass 1
+        const int nin = np.dims[l], nout = np.dims[l + 1];
+        const float* in = l == 0 ? r_in : netrows + P.a_row[l] * FS;
+        const bool last = l == np.L - 1;
+        float* out = last ? rows + (P.row_y + n) * FS : netrows + P.a_row[l + 1] * FS;
+        const int items = ((nout + 3) >> 2) * FB;
+        for (int it = tid; it < items; it += nt) {
+          const int ob = it / FB, fb = it - ob * FB;
+          float acc[4][4];
+          tile_fwd(acc, Wn + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, 4 * fb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int o = 4 * ob + j;
+            if (o < nout) {
+              const float b = Wn[np.b_off[l] + o];
+              float4 v = make_float4(acc[j][0] + b, acc[j][1] + b, acc[j][2] + b, acc[j][3] + b);
+              if (!last) v = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+              st4(out + o * FS + 4 * fb, v);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // ---- reverse: G_l = adjoint of z_l for the seed dy = 1;  u = dy/dr -> V rows
+      for (int l = np.L - 1; l >= 0; --l) {
+        const int nin = np.dims[l], nout = np.dims[l + 1];
+        const float* in = l == np.L - 1 ? rows + P.row_one * FS : netrows + P.g_row[l + 1] * FS;
+        float* out = l == 0 ? netrows + P.v_row * FS : netrows + P.g_row[l] * FS;
+        const float* A = l == 0 ? nullptr : netrows + P.a_row[l] * FS;
+        const int items = ((nin + 3) >> 2) * FB;
+        for (int it = tid; it < items; it += nt) {
+          const int ib = it / FB, fb = it - ib * FB;
+          float acc[4][4];
+          tile_tr(acc, Wn + np.w_off[l], np.ld[l], 4 * ib, nout, in, FS, 4 * fb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * ib + j;
+            if (i < nin) {
+              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+              if (l > 0) {
+                const float4 a = ld4(A + i * FS + 4 * fb);
+                v = make_float4(v.x * (1.f - a.x * a.x), v.y * (1.f - a.y * a.y), v.z * (1.f - a.z * a.z), v.w * (1.f - a.w * a.w));
+              }
+              st4(out + i * FS + 4 * fb, v);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // ---- J phase (thread per frame): Dirichlet density; pass 2: tangent direction and output seed
+      if (tid < F) {
+        const int f = tid;
+        float scale = 0.0f;
+        if (GRAD) {
+          const float wf = rows[P.row_w * FS + f];
+          scale = (float)(2.0 * (double)wf * c_cD[n]);
+          double s = 0.0;
+          for (int j = 0; j < k; ++j) s += c_C2[n * k + j] * ((double)rows[(P.row_y + j) * FS + f] - c_mean[j]);
+          rows[P.row_seed * FS + f] = (float)((double)wf * s);
+        }
+        const float D = jphase_frame(P, rows, netrows, f, GRAD, scale);
+        if (!GRAD) rows[(P.row_D + n) * FS + f] = D;
+      }
+      __syncthreads();
+      if (GRAD) {
+        double* pn = part + (size_t)n * np.n_params;
+        // ---- tangent sweep along v:  T_l = (1-A_l^2) zdot_l,  S_l = -2 A_l G_l zdot_l   (zdot_l = W_l T_{l-1})
+        for (int l = 0; l < np.L - 1; ++l) {
+          const int nin = np.dims[l], nout = np.dims[l + 1];
+          const float* in = l == 0 ? netrows + P.v_row * FS : netrows + P.t_row[l] * FS;
+          float* T = netrows + P.t_row[l + 1] * FS;
+          float* S = netrows + P.s_row[l + 1] * FS;
+          const float* A = netrows + P.a_row[l + 1] * FS;
+          const float* G = netrows + P.g_row[l + 1] * FS;
+          const int items = ((nout + 3) >> 2) * FB;
+          for (int it = tid; it < items; it += nt) {
+            const int ob = it / FB, fb = it - ob * FB;
+            float acc[4][4];
+            tile_fwd(acc, Wn + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, 4 * fb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int o = 4 * ob + j;
+              if (o < nout) {
+                const float4 a = ld4(A + o * FS + 4 * fb), g = ld4(G + o * FS + 4 * fb);
+                st4(T + o * FS + 4 * fb, make_float4((1.f - a.x * a.x) * acc[j][0], (1.f - a.y * a.y) * acc[j][1],
+                                                     (1.f - a.z * a.z) * acc[j][2], (1.f - a.w * a.w) * acc[j][3]));
+                st4(S + o * FS + 4 * fb, make_float4(-2.f * a.x * g.x * acc[j][0], -2.f * a.y * g.y * acc[j][1],
+                                                     -2.f * a.z * g.z * acc[j][2], -2.f * a.w * g.w * acc[j][3]));
+              }
+            }
+          }
+          if (l == 0) {
+            // tangent part of dW_1 while V is still alive: dW_1 += G_1 (x) v
+            __syncthreads();
+            const int n1 = ((np.dims[1] + 3) >> 2) * ((np.dims[0] + 3) >> 2);
+            const float* X = np.L > 1 ? netrows + P.g_row[1] * FS : rows + P.row_one * FS;
+            for (int it = tid; it < n1; it += nt)
+              outer_item(it, np.dims[1], np.dims[0], X, netrows + P.v_row * FS, nullptr, nullptr, FS, F, pn + np.gw_off[0], nullptr);
+          }
+          __syncthreads();
+        }
+        if (np.L == 1) {
+          // single linear layer: only the tangent part exists besides the seed part below
+          const int n1 = ((np.dims[1] + 3) >> 2) * ((np.dims[0] + 3) >> 2);
+          for (int it = tid; it < n1; it += nt)
+            outer_item(it, np.dims[1], np.dims[0], rows + P.row_one * FS, netrows + P.v_row * FS, nullptr, nullptr, FS, F,
+                       pn + np.gw_off[0], nullptr);
+          __syncthreads();
+        }
+        // ---- second reverse sweep: s_l (adjoint of z_l) in place of S_l;  s_L = seed
+        for (int l = np.L - 1; l >= 1; --l) {
+          const int nin = np.dims[l], nout = np.dims[l + 1];
+          const float* in = l == np.L - 1 ? rows + P.row_seed * FS : netrows + P.s_row[l + 1] * FS;
+          float* S = netrows + P.s_row[l] * FS;
+          const float* A = netrows + P.a_row[l] * FS;
+          const int items = ((nin + 3) >> 2) * FB;
+          for (int it = tid; it < items; it += nt) {
+            const int ib = it / FB, fb = it - ib * FB;
+            float acc[4][4];
+            tile_tr(acc, Wn + np.w_off[l], np.ld[l], 4 * ib, nout, in, FS, 4 * fb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = 4 * ib + j;
+              if (i < nin) {
+                const float4 a = ld4(A + i * FS + 4 * fb);
+                const float4 e = ld4(S + i * FS + 4 * fb);
+                st4(S + i * FS + 4 * fb, make_float4(fmaf(acc[j][0], 1.f - a.x * a.x, e.x), fmaf(acc[j][1], 1.f - a.y * a.y, e.y),
+                                                     fmaf(acc[j][2], 1.f - a.z * a.z, e.z), fmaf(acc[j][3], 1.f - a.w * a.w, e.w)));
+              }
+            }
+          }
+          __syncthreads();
+        }
+        // ---- parameter gradients: dW_l += s_l (x) A_{l-1} + G_l (x) T_{l-1},  db_l += sum_f s_l
+        {
+          int base = 0;
+          for (int l = 0; l < np.L; ++l) {
+            const int nin = np.dims[l], nout = np.dims[l + 1];
+            const int n_it = ((nout + 3) >> 2) * ((nin + 3) >> 2);
+            const bool last = l == np.L - 1;
+            const float* X1 = last ? rows + P.row_seed * FS : netrows + P.s_row[l + 1] * FS;
+            const float* Z1 = l == 0 ? r_in : netrows + P.a_row[l] * FS;
+            const float* X2 = l == 0 ? nullptr : (last ? rows + P.row_one * FS : netrows + P.g_row[l + 1] * FS);
+            const float* Z2 = l == 0 ? nullptr : netrows + P.t_row[l] * FS;
+            // spread the items of all layers over the CTA: item index space is the concatenation of the layers
+            for (int it = tid - base; it < n_it; it += nt) {
+              if (it >= 0) outer_item(it, nout, nin, X1, Z1, X2, Z2, FS, F, pn + np.gw_off[l], pn + np.gb_off[l]);
+            }
+            base = (base + n_it) % nt;
+          }
+        }
+        __syncthreads();
+      }
+    }  // networks
+
+    if (!GRAD) {
+      // ---- batch sums of this tile in fp64: S0, S1[i], S2[i][j], SD[i]
+      const int ns = P.n_stats;
+      for (int f = tid; f < F; f += nt) {
+        const long long fr = f_base + f;
+        if (fr < B)
+          for (int i = 0; i < k; ++i) y_io[(size_t)i * B + fr] = rows[(P.row_y + i) * FS + f];
+      }
+      const int lane = tid & 31, warp = tid >> 5, nwarp_f = F / 32;
+      for (int s = 0; s < ns; ++s) {
+        double v = 0.0;
+        if (tid < F) {
+          const double wf = rows[P.row_w * FS + tid];
+          if (s == 0) v = wf;
+          else if (s < 1 + k) v = wf * rows[(P.row_y + s - 1) * FS + tid];
+          else if (s < 1 + k + k * k) {
+            const int i = (s - 1 - k) / k, j = (s - 1 - k) % k;
+            v = wf * (double)rows[(P.row_y + i) * FS + tid] * (double)rows[(P.row_y + j) * FS + tid];
+          } else v = wf * rows[(P.row_D + s - 1 - k - k * k) * FS + tid];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) red[s * 4 + warp] = v;
+        }
+      }
+      __syncthreads();
+      if (tid < ns) {
+        double v = 0.0;
+        for (int q = 0; q < nwarp_f; ++q) v += red[tid * 4 + q];
+        stat_acc += v;
+      }
+      __syncthreads();
+    }
+  }  // tiles
+  if (!GRAD && tid < P.n_stats) part[tid] = stat_acc;
+}
+
+struct EigW {
+  double v[kMaxK];
+};
+
+// loss, eigenvalues, ordering, objective, penalty and the pass-2 coefficients (core.py:406-410,426-455).
+__global__ void eigen_combine_kernel(const double* __restrict__ S, int k, double alpha, double beta, int sort,
+                                     const EigW eig_w, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double S0 = S[0];
+  const double* S1 = S + 1;
+  const double* S2 = S + 1 + k;
+  const double* SD = S + 1 + k + k * k;
+  double mean[kMaxK], var[kMaxK], E[kMaxK], eig[kMaxK], omega[kMaxK];
+  int cvec[kMaxK];
+  for (int i = 0; i < k; ++i) {
+    mean[i] = S1[i] / S0;
+    var[i] = S2[i * k + i] / S0 - mean[i] * mean[i];
+    E[i] = SD[i] / (beta * S0);
+    eig[i] = E[i] / var[i];
+    cvec[i] = i;
+  }
+  if (sort) {   // ascending, stable (np.argsort, core.py:432)
+    for (int i = 1; i < k; ++i) {
+      const int c = cvec[i];
+      int j = i - 1;
+      while (j >= 0 && eig[cvec[j]] > eig[c]) cvec[j + 1] = cvec[j], --j;
+      cvec[j + 1] = c;
+    }
+  }
+  for (int r = 0; r < k; ++r) omega[cvec[r]] = eig_w.v[r];
+  double obj = 0.0, pen = 0.0;
+  for (int i = 0; i < k; ++i) {
+    obj += omega[i] * eig[i];
+    pen += (var[i] - 1.0) * (var[i] - 1.0);
+  }
+  double* C2 = out + 3 + 4 * k;
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) {
+      if (i == j) {
+        const double cv = -omega[i] * E[i] / (var[i] * var[i]) + 2.0 * alpha * (var[i] - 1.0);
+        C2[i * k + j] = 2.0 * cv / S0;
+      } else {
+        const double cov = S2[i * k + j] / S0 - mean[i] * mean[j];
+        if (j > i) pen += cov * cov;
+        C2[i * k + j] = 2.0 * alpha * cov / S0;
+      }
+    }
+  out[0] = obj + alpha * pen;
+  out[1] = obj;
+  out[2] = pen;
+  for (int r = 0; r < k; ++r) {
+    out[3 + r] = eig[cvec[r]];
+    out[3 + k + r] = (double)cvec[r];
+    out[3 + 2 * k + r] = mean[r];
+    out[3 + 3 * k + r] = omega[r] / (beta * S0 * var[r]);
+  }
+}
+
+static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
+                        int k, const float* params, float* y_io, const double* combine, double* out, void* workspace,
+                        size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EigenPlan P;
+  int e = build_plan(pp, net, k, &P);
+  if (e) return e;
+  if (!x || !w || !params || !y_io || !out || !workspace || B < 1 || (grad && !combine)) {
+    set_error("null pointer or empty batch");
+    return CVF_E_ARG;
+  }
+  e = finish_plan(&P, pp->kind == 1 && pp->positions_only != 0);   // largest tile that fits
+  if (e) return e;
+  const int n_part = grad ? k * P.net.n_params : P.n_stats;
+  const long long n_tiles = (B + P.F - 1) / P.F;
+  int grid = sm_count();
+  if (n_tiles < grid) grid = (int)n_tiles;
+  if ((size_t)grid * n_part * sizeof(double) > ws_bytes) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, (size_t)grid * n_part * sizeof(double));
+    return CVF_E_WORKSPACE;
+  }
+  if (grad) {
+    CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    eigen_kernel<true><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
+  } else {
+    CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    eigen_kernel<false><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
+  }
+  CVF_CUDA(cudaGetLastError());
+  reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 0, n_part, out);
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cvf
+
+using namespace cvf;
+
+extern "C" int32_t cvf_eigen_num_stats(int32_t k) { return 1 + 2 * k + k * k; }
+extern "C" int32_t cvf_eigen_num_combine(int32_t k) { return 3 + 4 * k + k * k; }
+
+extern "C" size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k) {
+  NetPlan np;
+  (void)pp;
+  if (make_net_plan(net, &np) || k < 1 || k > kMaxK) return 0;
+  size_t n = (size_t)k * np.n_params;
+  const size_t ns = (size_t)cvf_eigen_num_stats(k);
+  if (ns > n) n = ns;
+  return n * sizeof(double) * (size_t)sm_count();
+}
+
+extern "C" int cvf_eigen_stats(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net, int32_t k,
+                               const float* params, float* y_out, double* stats_out, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  return eigen_launch(false, x, w, B, pp, net, k, params, y_out, nullptr, stats_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cvf_eigen_combine(const double* stats, int32_t k, double alpha, const double* eig_w, double beta, int32_t sort,
+                                 double* combine_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!stats || !eig_w || !combine_out || k < 1 || k > kMaxK) {
+    set_error("cvf_eigen_combine: bad argument");
+    return CVF_E_ARG;
+  }
+  EigW ew;   // eig_w is a HOST array: it travels by value as a kernel parameter
+  for (int i = 0; i < kMaxK; ++i) ew.v[i] = i < k ? eig_w[i] : 0.0;
+  eigen_combine_kernel<<<1, 32, 0, stream>>>(stats, k, alpha, beta, sort, ew, combine_out);
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cvf_eigen_grad(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net, int32_t k,
+                              const float* params, const float* y_in, const double* combine, double* grad_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return eigen_launch(true, x, w, B, pp, net, k, params, const_cast<float*>(y_in), combine, grad_out, workspace, workspace_bytes,
+                      stream);
+}

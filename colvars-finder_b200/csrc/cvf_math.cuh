@@ -1,0 +1,223 @@
+// cvf_math.cuh -- per-frame geometry shared by every kernel (and compiled for the host by
+// tests/host_math_check.cpp so the numerics can be checked against the oracle without a GPU).
+//
+//  * cvf_rotation(): optimal proper rotation of the Kabsch problem  min_R sum |(x_i-c) R - ref_i|^2
+//    from the 3x3 covariance H = (x_A-c)^T ref.  The reference path gets this from torch.linalg.svd
+//    inside the third-party alignment layer (examples/dipeptide/main.ipynb:345); here: Horn's 4x4
+//    quaternion matrix, cyclic Jacobi in fp32 registers, then Newton steps on the rotation in fp64
+//    (the optimum is where M = R^T H is symmetric), which also yields K = tr(M) I - M whose inverse the
+//    closed-form alignment Jacobian needs.
+//  * bond / angle / dihedral values with their gradient stencils.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CVF_HD __host__ __device__ __forceinline__
+#else
+#define CVF_HD inline
+#endif
+
+struct cvf_v3 {
+  float x, y, z;
+};
+CVF_HD cvf_v3 v3(float x, float y, float z) { return cvf_v3{x, y, z}; }
+CVF_HD cvf_v3 operator+(cvf_v3 a, cvf_v3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+CVF_HD cvf_v3 operator-(cvf_v3 a, cvf_v3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+CVF_HD cvf_v3 operator*(float s, cvf_v3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+CVF_HD float dot(cvf_v3 a, cvf_v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+CVF_HD cvf_v3 cross(cvf_v3 a, cvf_v3 b) {
+  return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// row vector times 3x3 row-major matrix:  (a R)_b = sum_a a_a R[a][b]
+CVF_HD cvf_v3 mul_rowvec(cvf_v3 a, const float* R) {
+  return v3(a.x * R[0] + a.y * R[3] + a.z * R[6], a.x * R[1] + a.y * R[4] + a.z * R[7],
+            a.x * R[2] + a.y * R[5] + a.z * R[8]);
+}
+// row vector times R^T
+CVF_HD cvf_v3 mul_rowvec_T(cvf_v3 a, const float* R) {
+  return v3(a.x * R[0] + a.y * R[1] + a.z * R[2], a.x * R[3] + a.y * R[4] + a.z * R[5],
+            a.x * R[6] + a.y * R[7] + a.z * R[8]);
+}
+// symmetric 3x3 (xx,xy,xz,yy,yz,zz) times vector
+CVF_HD cvf_v3 mul_sym(const float* S, cvf_v3 a) {
+  return v3(S[0] * a.x + S[1] * a.y + S[2] * a.z, S[1] * a.x + S[3] * a.y + S[4] * a.z,
+            S[2] * a.x + S[4] * a.y + S[5] * a.z);
+}
+
+// One Jacobi rotation in the (p,q) plane of the symmetric 4x4 `a`, accumulated into `v`.
+template <int p, int q>
+CVF_HD void cvf_jacobi_rot(float (&a)[4][4], float (&v)[4][4]) {
+  const float apq = a[p][q];
+  if (fabsf(apq) > 1e-30f) {
+    const float theta = (a[q][q] - a[p][p]) / (2.0f * apq);
+    const float t = copysignf(1.0f, theta) / (fabsf(theta) + sqrtf(theta * theta + 1.0f));
+    const float c = 1.0f / sqrtf(t * t + 1.0f);
+    const float s = t * c;
+    a[p][p] -= t * apq;
+    a[q][q] += t * apq;
+    a[p][q] = 0.0f;
+    a[q][p] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (r != p && r != q) {
+        const float arp = a[r][p], arq = a[r][q];
+        a[r][p] = a[p][r] = c * arp - s * arq;
+        a[r][q] = a[q][r] = s * arp + c * arq;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float vrp = v[r][p], vrq = v[r][q];
+      v[r][p] = c * vrp - s * vrq;
+      v[r][q] = s * vrp + c * vrq;
+    }
+  }
+}
+
+// H[9] row-major covariance (x_A-c)^T ref in double.  Outputs R[9] (row-major, y = (x-c) R) and,
+// if Kinv != nullptr, the inverse of K = tr(M) I - M, M = sym(R^T H), as (xx,xy,xz,yy,yz,zz).
+CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv) {
+  // Horn (1987) 4x4 matrix; its top eigenvector is the unit quaternion of the column-convention rotation R^T.
+  float a[4][4], v[4][4];
+  {
+    const float Sxx = (float)H[0], Sxy = (float)H[1], Sxz = (float)H[2];
+    const float Syx = (float)H[3], Syy = (float)H[4], Syz = (float)H[5];
+    const float Szx = (float)H[6], Szy = (float)H[7], Szz = (float)H[8];
+    // scale to O(1) so the Jacobi thresholds are meaningful for any unit system
+    float sc = fabsf(Sxx) + fabsf(Sxy) + fabsf(Sxz) + fabsf(Syx) + fabsf(Syy) + fabsf(Syz) + fabsf(Szx) + fabsf(Szy) + fabsf(Szz);
+    sc = sc > 0.0f ? 1.0f / sc : 1.0f;
+    a[0][0] = sc * (Sxx + Syy + Szz);
+    a[0][1] = a[1][0] = sc * (Syz - Szy);
+    a[0][2] = a[2][0] = sc * (Szx - Sxz);
+    a[0][3] = a[3][0] = sc * (Sxy - Syx);
+    a[1][1] = sc * (Sxx - Syy - Szz);
+    a[1][2] = a[2][1] = sc * (Sxy + Syx);
+    a[1][3] = a[3][1] = sc * (Szx + Sxz);
+    a[2][2] = sc * (-Sxx + Syy - Szz);
+    a[2][3] = a[3][2] = sc * (Syz + Szy);
+    a[3][3] = sc * (-Sxx - Syy + Szz);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0f : 0.0f;
+  for (int sweep = 0; sweep < 5; ++sweep) {
+    cvf_jacobi_rot<0, 1>(a, v);
+    cvf_jacobi_rot<0, 2>(a, v);
+    cvf_jacobi_rot<0, 3>(a, v);
+    cvf_jacobi_rot<1, 2>(a, v);
+    cvf_jacobi_rot<1, 3>(a, v);
+    cvf_jacobi_rot<2, 3>(a, v);
+  }
+  // column of the largest eigenvalue (branch-free select keeps v in registers)
+  float best = a[0][0], q0 = v[0][0], qx = v[1][0], qy = v[2][0], qz = v[3][0];
+#pragma unroll
+  for (int c = 1; c < 4; ++c) {
+    const bool take = a[c][c] > best;
+    best = take ? a[c][c] : best;
+    q0 = take ? v[0][c] : q0;
+    qx = take ? v[1][c] : qx;
+    qy = take ? v[2][c] : qy;
+    qz = take ? v[3][c] : qz;
+  }
+  double Rd[9];
+  {
+    const double n = 1.0 / sqrt((double)q0 * q0 + (double)qx * qx + (double)qy * qy + (double)qz * qz);
+    const double w = q0 * n, x = qx * n, y = qy * n, z = qz * n;
+    // R = (column-convention rotation of q)^T
+    Rd[0] = w * w + x * x - y * y - z * z;
+    Rd[3] = 2.0 * (x * y - w * z);
+    Rd[6] = 2.0 * (x * z + w * y);
+    Rd[1] = 2.0 * (y * x + w * z);
+    Rd[4] = w * w - x * x + y * y - z * z;
+    Rd[7] = 2.0 * (y * z - w * x);
+    Rd[2] = 2.0 * (z * x - w * y);
+    Rd[5] = 2.0 * (z * y + w * x);
+    Rd[8] = w * w - x * x - y * y + z * z;
+  }
+  double Ki[6] = {0, 0, 0, 0, 0, 0};
+  // Newton on the rotation: R <- R exp([d]x),  K d = axial(M - M^T),  M = R^T H.  Error e -> O(e^2).
+  for (int it = 0; it < 3; ++it) {
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M[3 * i + j] = Rd[i] * H[j] + Rd[3 + i] * H[3 + j] + Rd[6 + i] * H[6 + j];
+    const double sxy = 0.5 * (M[1] + M[3]), sxz = 0.5 * (M[2] + M[6]), syz = 0.5 * (M[5] + M[7]);
+    const double tr = M[0] + M[4] + M[8];
+    const double kxx = tr - M[0], kyy = tr - M[4], kzz = tr - M[8], kxy = -sxy, kxz = -sxz, kyz = -syz;
+    const double c00 = kyy * kzz - kyz * kyz, c01 = kxz * kyz - kxy * kzz, c02 = kxy * kyz - kxz * kyy;
+    const double c11 = kxx * kzz - kxz * kxz, c12 = kxy * kxz - kxx * kyz, c22 = kxx * kyy - kxy * kxy;
+    const double det = kxx * c00 + kxy * c01 + kxz * c02;
+    const double idet = det != 0.0 ? 1.0 / det : 0.0;
+    Ki[0] = c00 * idet, Ki[1] = c01 * idet, Ki[2] = c02 * idet, Ki[3] = c11 * idet, Ki[4] = c12 * idet, Ki[5] = c22 * idet;
+    if (it == 2) break;   // K^-1 of the polished rotation is what the Jacobian uses
+    const double t0 = M[7] - M[5], t1 = M[2] - M[6], t2 = M[3] - M[1];
+    double d0 = Ki[0] * t0 + Ki[1] * t1 + Ki[2] * t2;
+    double d1 = Ki[1] * t0 + Ki[3] * t1 + Ki[4] * t2;
+    double d2 = Ki[2] * t0 + Ki[4] * t1 + Ki[5] * t2;
+    const double th2 = d0 * d0 + d1 * d1 + d2 * d2;
+    if (!(th2 < 0.01)) break;   // degenerate frame (K singular): keep the Jacobi rotation
+    const double A = 1.0 - th2 / 6.0 + th2 * th2 / 120.0;        // sin(th)/th
+    const double Bc = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;      // (1-cos th)/th^2
+    // E = I + A [d]x + B [d]x^2
+    double E[9];
+    E[0] = 1.0 - Bc * (d1 * d1 + d2 * d2);
+    E[4] = 1.0 - Bc * (d0 * d0 + d2 * d2);
+    E[8] = 1.0 - Bc * (d0 * d0 + d1 * d1);
+    E[1] = -A * d2 + Bc * d0 * d1;
+    E[3] = A * d2 + Bc * d0 * d1;
+    E[2] = A * d1 + Bc * d0 * d2;
+    E[6] = -A * d1 + Bc * d0 * d2;
+    E[5] = -A * d0 + Bc * d1 * d2;
+    E[7] = A * d0 + Bc * d1 * d2;
+    double Rn[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Rn[3 * i + j] = Rd[3 * i] * E[j] + Rd[3 * i + 1] * E[3 + j] + Rd[3 * i + 2] * E[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rd[i] = Rn[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+  if (Kinv) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) Kinv[i] = (float)Ki[i];
+  }
+}
+
+// ---- feature stencils (values + gradient w.r.t. the atoms of the feature) -------------------------
+// bond |b-a|: gradient w.r.t. b is g, w.r.t. a is -g
+CVF_HD float cvf_bond(cvf_v3 a, cvf_v3 b, cvf_v3& g) {
+  const cvf_v3 d = b - a;
+  const float n = sqrtf(dot(d, d));
+  g = (1.0f / n) * d;
+  return n;
+}
+// cos of the angle at m between (a-m) and (c-m); gradients ga (atom a), gc (atom c); atom m gets -(ga+gc)
+CVF_HD float cvf_angle(cvf_v3 a, cvf_v3 m, cvf_v3 c, cvf_v3& ga, cvf_v3& gc) {
+  const cvf_v3 u = a - m, w = c - m;
+  const float inu = 1.0f / sqrtf(dot(u, u)), inw = 1.0f / sqrtf(dot(w, w));
+  const cvf_v3 uh = inu * u, wh = inw * w;
+  const float cs = dot(uh, wh);
+  ga = inu * (wh - cs * uh);
+  gc = inw * (uh - cs * wh);
+  return cs;
+}
+// dihedral of atoms (p0,p1,p2,p3): returns cos, sin and the gradient of the ANGLE phi w.r.t. each atom;
+// d cos = -sin * dphi, d sin = cos * dphi.
+CVF_HD void cvf_dihedral(cvf_v3 p0, cvf_v3 p1, cvf_v3 p2, cvf_v3 p3, float& cs, float& sn, cvf_v3 (&g)[4]) {
+  const cvf_v3 r12 = p1 - p0, r23 = p2 - p1, r34 = p3 - p2;
+  const cvf_v3 n1 = cross(r12, r23), n2 = cross(r23, r34);
+  const float n1s = dot(n1, n1), n2s = dot(n2, n2), l23s = dot(r23, r23);
+  const float l23 = sqrtf(l23s);
+  const float iden = 1.0f / sqrtf(n1s * n2s);
+  cs = dot(n1, n2) * iden;
+  sn = dot(n1, r34) * l23 * iden;
+  g[0] = (-l23 / n1s) * n1;
+  g[3] = (l23 / n2s) * n2;
+  const float p = dot(r12, r23) / l23s, q = dot(r34, r23) / l23s;
+  g[1] = (-1.0f - p) * g[0] + q * g[3];
+  g[2] = p * g[0] + (-1.0f - q) * g[3];
+}

@@ -1,0 +1,121 @@
+/*
+ * cvf.h -- C ABI of libcvf_sm100.so: the colvars-finder training step on B200 (sm_100a).
+ *
+ * The reference (zwpku/colvars-finder) has no native layer and no FFI; its boundary for this path is
+ * the Python class API (colvarsfinder/core.py, nn.py).  This header is the thin C boundary that the
+ * Python drop-in (colvars-finder_b200/colvarsfinder) binds with ctypes.  Each entry point names the
+ * reference code it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller (PyTorch's caching allocator); the
+ *     library allocates nothing on the device and keeps no state between calls;
+ *   - the descriptor structs (cvf_preproc, cvf_mlp) are HOST structs passed by pointer; the index /
+ *     coefficient arrays they point to live on the device;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no hidden sync;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = argument error (CVF_E_*); never throws.
+ *     cvf_last_error_string() describes the last non-zero return of the calling thread;
+ *   - fp32 frames / parameters; batch sums and gradient sums are accumulated and returned in fp64.
+ */
+#ifndef CVF_H
+#define CVF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVF_VERSION 100
+#define CVF_MAX_LAYERS 8   /* linear layers per network chain (AutoEncoder: encoder + decoder) */
+#define CVF_MAX_K 8        /* eigenfunctions per model */
+
+#define CVF_E_ARG (-1)        /* null pointer / negative size / inconsistent descriptor */
+#define CVF_E_UNSUPPORTED (-2) /* outside the supported envelope (depth, width, shared memory) */
+#define CVF_E_WORKSPACE (-3)  /* workspace too small */
+
+/* feature record types (molann-style features used by examples/dipeptide/main.ipynb:335-337) */
+#define CVF_FEAT_POSITION 0   /* 1 atom  -> 3 outputs (aligned x,y,z) */
+#define CVF_FEAT_BOND 1       /* 2 atoms -> |y_b - y_a| */
+#define CVF_FEAT_ANGLE 2      /* 3 atoms -> cos of the angle at the middle atom */
+#define CVF_FEAT_DIHEDRAL 3   /* 4 atoms -> (cos phi, sin phi) */
+
+/* Pre-processing layer r(x): the caller-supplied `pp_layer` of core.py:65,122,403,635
+ * (torch.nn.Identity in examples/2d/2d.ipynb:485; alignment + features in examples/dipeptide/main.ipynb:335-348). */
+typedef struct cvf_preproc {
+  int32_t kind;               /* 0: identity on a flat [B,dim] input; 1: molecular [B,n_atoms,3] input */
+  int32_t dim;                /* kind 0: input dimension d (= d_r) */
+  int32_t n_atoms;            /* kind 1: atoms per frame */
+  int32_t n_used;             /* kind 1: atoms read by alignment or features */
+  const int32_t* used_atoms;  /* [n_used] atom index inside the frame */
+  int32_t n_align;            /* 0 = no alignment */
+  const int32_t* align_used;  /* [n_align] positions in used_atoms of the alignment atoms */
+  const float* ref;           /* [n_align,3] reference positions, centred */
+  int32_t n_feat;             /* feature records */
+  const int32_t* feat;        /* [n_feat,5]: type, then up to 4 positions in used_atoms */
+  int32_t d_r;                /* output dimension of r */
+  int32_t positions_only;     /* 1: feat is exactly POSITION of used atom 0,1,..,n_used-1 (d_r = 3 n_used), so
+                                 r is the aligned frame itself and the kernels skip the feature copy */
+  const float* diag;          /* diag_coeff (core.py:348-354) gathered to [n_used*3] (kind 1) or [dim] (kind 0); NULL = ones */
+} cvf_preproc;
+
+/* Linear+activation chain built by nn.create_sequential_nn (nn.py:29-59).  For nn.AutoEncoder the
+ * chain is encoder followed by decoder (nn.py:114). */
+typedef struct cvf_mlp {
+  int32_t n_layers;
+  int32_t dims[CVF_MAX_LAYERS + 1];
+  int32_t act[CVF_MAX_LAYERS];   /* 1: tanh after this layer, 0: none */
+} cvf_mlp;
+
+int cvf_version(void);
+const char* cvf_last_error_string(void);
+
+/* number of float parameters of one chain, in torch's parameters() order: W1[out,in], b1[out], W2, b2, ... */
+int64_t cvf_mlp_param_count(const cvf_mlp* net);
+
+/* Kabsch alignment of every frame onto the reference (the alignment half of pp_layer; no reference
+ * source -- molann.ann.AlignmentLayer, examples/dipeptide/main.ipynb:345).
+ * x [B,n_atoms,3] -> y [B,n_atoms,3];  optional R_out [B,9] (row-major, y=(x-c)R) and c_out [B,3]. */
+int cvf_align_fwd(const float* x, int64_t B, int32_t n_atoms, const int32_t* align_idx, int32_t n_align,
+                  const float* ref_centred, float* y_out, float* R_out, float* c_out, void* stream);
+
+/* Whole-trajectory pre-pass of AutoEncoderTask.__init__ (core.py:635): r_out[B,d_r] = pp(x). */
+int cvf_features_fwd(const float* x, int64_t B, const cvf_preproc* pp, float* r_out, void* stream);
+
+/* ---- EigenFunctionTask.loss_func, generator branch (core.py:387-457) split at its batch sums ---- */
+
+/* doubles in the stats vector: S0, S1[k], S2[k*k], SD[k] */
+int32_t cvf_eigen_num_stats(int32_t k);
+/* doubles in the combine vector: loss, obj, pen, eig[k] (sorted), cvec[k], mean[k], cD[k], C2[k*k] */
+int32_t cvf_eigen_num_combine(int32_t k);
+/* bytes of scratch needed by cvf_eigen_stats / cvf_eigen_grad (per-block partial sums) */
+size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k);
+
+/* Pass 1: y = model(pp(X)), grad_x y_i, Dirichlet densities; batch sums (core.py:403-410,424-426).
+ * params [k * cvf_mlp_param_count] fp32.  y_out [k,B] fp32 (kept for pass 2).  stats_out fp64. */
+int cvf_eigen_stats(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
+                    int32_t k, const float* params, float* y_out, double* stats_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* After the cross-GPU sum of stats: loss, eigenvalues, cvec, objective, penalty (core.py:426-455) and
+ * the per-frame seed coefficients of pass 2.  eig_w: HOST array [k]. */
+int cvf_eigen_combine(const double* stats, int32_t k, double alpha, const double* eig_w, double beta,
+                      int32_t sort, double* combine_out, void* stream);
+
+/* Pass 2: d loss / d params (replaces loss.backward(), core.py:517).  grad_out [k * param_count] fp64,
+ * summed over this rank's frames. */
+int cvf_eigen_grad(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
+                   int32_t k, const float* params, const float* y_in, const double* combine,
+                   double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- AutoEncoderTask.weighted_MSE_loss + backward (core.py:652-666,708) ---- */
+size_t cvf_ae_workspace_bytes(const cvf_mlp* net);
+/* sums_out[2] = { sum_f w_f |dec(enc(F_f)) - F_f|^2 , sum_f w_f };  grad_out [param_count] fp64 holds the
+ * gradient of the FIRST sum (not yet divided by sum w).  grad_out may be NULL (evaluation only). */
+int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
+                double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVF_H */

@@ -1,0 +1,332 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in classes) against the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import ref_torch
+from oracle.ref_import import FakeTrajectory
+from tests import _cases as C
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0) if torch.cuda.is_available() else None
+BASE = ref_torch.DIPEPTIDE_NM * 10.0
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def _pp_pair(c):
+    """(pp_layer for the drop-in, closed-form oracle pre-processing) of a golden case."""
+    from colvarsfinder import utils
+    if c["pp_kind"] == "identity":
+        return torch.nn.Identity(), cf.Preproc(identity=True)
+    al = utils.Align(c["ref"], c["align_idx"]) if c["align_idx"] is not None else None
+    fm = utils.FeatureMap(c["features"]) if c["features"] is not None else None
+    return utils.Preprocessing(al, fm), cf.Preproc(align_idx=c["align_idx"], ref=c["ref"], feats=c["features"])
+
+
+def _eigen_task(c, tmp, X=None, w=None, **kw):
+    from colvarsfinder import core, nn
+    model = nn.EigenFunctions(c["layer_dims"], c["k"])
+    with torch.no_grad():
+        for i in range(c["k"]):
+            for p, v in zip(model.eigen_funcs[i].parameters(), c["params"][i]):
+                p.copy_(torch.as_tensor(v))
+    X = c["X"] if X is None else X
+    w = c["w"] if w is None else w
+    traj = FakeTrajectory(X, w.astype(np.float64), dt=1.0)
+    pp, _ = _pp_pair(c)
+    diag = None if c["diag_coeff"] is None else torch.as_tensor(c["diag_coeff"])
+    task = core.EigenFunctionTask(traj, pp, model, str(tmp), c["alpha"], c["eig_w"], diag_coeff=diag, beta=c["beta"],
+                                  sort_eigvals_in_training=c["sort"], k=c["k"], device=DEV, verbose=False, debug_mode=False,
+                                  **kw)
+    return task, model
+
+
+# --------------------------------------------------------------------------------------------- alignment
+@pytest.mark.parametrize("B", [1, 5, 128, 1000, 4099])
+def test_align_fwd_matches_oracle(B):
+    from colvarsfinder import utils
+    X = ref_torch.synth_frames(BASE, B, seed=B)
+    al = utils.Align(BASE, list(range(22))).to(DEV)
+    y, R, c = al.rotation(torch.as_tensor(X, device=DEV))
+    yo, Ro, co, _, _ = cf.kabsch(X.astype(np.float64), list(range(22)), BASE)
+    assert np.abs(y.cpu().numpy() - yo).max() < 1e-6          # Angstrom (north_star: aligned coordinates to 1e-6 A)
+    assert np.abs(R.cpu().numpy() - Ro).max() < 2e-7
+    assert np.abs(c.cpu().numpy() - co[:, 0]).max() < 2e-6
+    np.testing.assert_allclose(torch.linalg.det(R.double()).cpu().numpy(), 1.0, atol=1e-6)
+    assert torch.equal(al(torch.as_tensor(X, device=DEV)), y)
+
+
+def test_align_subset_large_molecule_and_invariance():
+    from colvarsfinder import utils
+    heavy = [1, 4, 5, 6, 8, 10, 14, 15, 16, 18]
+    X = ref_torch.synth_frames(BASE, 777, seed=2)
+    y = utils.Align(BASE[heavy], heavy).to(DEV)(torch.as_tensor(X, device=DEV)).cpu().numpy()
+    yo = cf.kabsch(X.astype(np.float64), heavy, BASE[heavy])[0]
+    assert np.abs(y - yo).max() < 1e-6
+    # 300-atom chain: a tile does not fit, warp-per-frame kernel
+    chain = ref_torch.chain_structure(300, seed=4)
+    Xc = ref_torch.synth_frames(chain, 257, seed=9)
+    sel = list(range(0, 300, 7))
+    al = utils.Align(chain[sel], sel).to(DEV)
+    yc = al(torch.as_tensor(Xc, device=DEV)).cpu().numpy()
+    yco = cf.kabsch(Xc.astype(np.float64), sel, chain[sel])[0]
+    assert np.abs(yc - yco).max() < 5e-6                       # |y| up to ~40 A: float32 spacing is 4e-6 there
+    # a rigid motion of the input does not change the aligned frame
+    Q = np.linalg.qr(np.random.default_rng(0).normal(size=(3, 3)))[0]
+    Q *= np.sign(np.linalg.det(Q))
+    X2 = (X.astype(np.float64) @ Q + 3.0).astype(np.float32)
+    y2 = utils.Align(BASE[heavy], heavy).to(DEV)(torch.as_tensor(X2, device=DEV)).cpu().numpy()
+    assert np.abs(y2 - y).max() < 2e-5
+
+
+def test_features_fwd_matches_oracle():
+    from colvarsfinder import utils
+    c = C.eigen_case("eigen_dipep_features")
+    pp, ppo = _pp_pair(c)
+    X = ref_torch.synth_frames(BASE, 1500, seed=12)
+    r = pp.to(DEV)(torch.as_tensor(X, device=DEV)).cpu().numpy()
+    ro = ppo.prepare(X.astype(np.float64))["r"]
+    assert r.shape == ro.shape
+    assert np.abs(r - ro).max() < 5e-6
+    c = C.eigen_case("eigen_dipep_invariant")
+    pp, ppo = _pp_pair(c)
+    r = pp.to(DEV)(torch.as_tensor(X, device=DEV)).cpu().numpy()
+    assert np.abs(r - ppo.prepare(X.astype(np.float64))["r"]).max() < 5e-6
+
+
+# --------------------------------------------------------------------------------------------- eigenfunction loss
+def _check_eigen(c, out, grads, gold, tag=""):
+    loss, eig, obj, pen, cvec = out
+    assert list(cvec.cpu().numpy()) == list(gold["cvec"])
+    assert abs(float(loss) - gold["loss"]) <= C.tol(gold["loss"], gold.get("loss32", gold["loss"])), (tag, float(loss), gold["loss"])
+    assert abs(float(obj) - gold["obj"]) <= C.tol(gold["obj"], gold.get("obj32", gold["obj"]))
+    assert abs(float(pen) - gold["pen"]) <= C.tol(gold["pen"], gold.get("pen32", gold["pen"]), rel=2e-5)
+    e32 = gold.get("eig32", gold["eig"])
+    for i in range(len(gold["eig"])):
+        assert abs(float(eig[i]) - gold["eig"][i]) <= C.tol(gold["eig"][i], e32[i]), (tag, i)
+    for i in range(len(grads)):
+        for j in range(len(grads[i])):
+            g64 = gold["grads"][i][j]
+            if np.abs(g64).max() < 1e-12:       # last-layer bias: exactly zero gradient in the generator loss
+                assert np.abs(grads[i][j]).max() < 1e-4 * max(1.0, abs(gold["loss"]))
+                continue
+            ref_err = C.rel_l2(gold["grads32"][i][j], g64) if "grads32" in gold else 0.0
+            assert C.rel_l2(grads[i][j], g64) <= max(2e-5, 2.0 * ref_err), (tag, i, j, C.rel_l2(grads[i][j], g64), ref_err)
+
+
+@pytest.mark.parametrize("name", C.EIGEN_GENERATOR_CASES)
+def test_eigen_loss_matches_reference_golden(name, tmp_path):
+    """loss, eigenvalues, objective, penalty, cvec and every parameter gradient vs the reference (fp64 gold; the
+    reference's own fp32 run sets the floor -- SURVEY 7.3-D)."""
+    c = C.eigen_case(name)
+    task, model = _eigen_task(c, tmp_path)
+    out = task.loss_func(task._traj, task._weights, None, None)
+    out[0].backward()
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    gold = dict(loss=float(c["g64_loss"]), obj=float(c["g64_obj"]), pen=float(c["g64_pen"]), eig=c["g64_eig"],
+                cvec=c["g64_cvec"], grads=c["g64"], loss32=float(c["r32_loss"]), obj32=float(c["r32_obj"]),
+                pen32=float(c["r32_pen"]), eig32=c["r32_eig"], grads32=c["g32"])
+    _check_eigen(c, out, grads, gold, name)
+
+
+@pytest.mark.parametrize("B", [1, 37, 128, 129, 1000, 20011])
+@pytest.mark.parametrize("name", ["eigen_dipep_k3", "eigen_dipep_features", "eigen_2d_k3_diag"])
+def test_eigen_loss_matches_oracle_ragged_sizes(name, B, tmp_path):
+    """Same inputs through the CUDA path and the fp64 closed-form oracle at batch sizes that exercise the tail
+    tile, a single frame, and many CTAs."""
+    c = C.eigen_case(name)
+    if c["pp_kind"] == "identity":
+        X = ref_torch.ring_2d(B, 100 + B) if hasattr(ref_torch, "ring_2d") else None
+        rng = np.random.default_rng(100 + B)
+        X = rng.normal(size=(B, 2)).astype(np.float32)
+    else:
+        X = ref_torch.synth_frames(BASE, B, seed=100 + B)
+    w = ref_torch.boltzmann_weights(B, seed=B)
+    if B == 1:
+        pytest.skip("variance of a single frame is zero: the reference loss is undefined (division by zero)")
+    task, model = _eigen_task(c, tmp_path, X, w)
+    out = task.loss_func(task._traj, task._weights, None, None)
+    out[0].backward()
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    _, ppo = _pp_pair(c)
+    comb, g64, _ = cf.eigen_loss_and_grads(X, w, c["params"], ppo, c["alpha"], c["eig_w"], c["diag_coeff"], c["beta"], c["sort"])
+    # fp32 floor of the reference formula var = E[y^2] - E[y]^2 is not available here: use a fixed 1e-4 envelope
+    loss, eig, obj, pen, cvec = out
+    assert list(cvec.cpu().numpy()) == list(comb["cvec"])
+    assert abs(float(loss) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
+    np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
+    for i in range(c["k"]):
+        for j in range(len(g64[i])):
+            if np.abs(g64[i][j]).max() < 1e-12:
+                continue
+            assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (i, j, C.rel_l2(grads[i][j], g64[i][j]))
+
+
+def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
+    """Size-independent property at BASELINE scale (2^20 frames of C3): the fp64 batch sums of a batch equal the sum over
+    its halves, and the gradient sums of pass 2 (at fixed coefficients) are additive too."""
+    c = C.eigen_case("eigen_dipep_k3")
+    n = 1 << 20
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    base = torch.as_tensor(BASE, dtype=torch.float32)
+    small = torch.as_tensor(ref_torch.synth_frames(BASE, 4096, seed=77))
+    X = (small[torch.randint(0, 4096, (n,), generator=gen)] + 0.05 * torch.randn(n, 22, 3, generator=gen)).numpy()
+    w = ref_torch.boltzmann_weights(n, seed=3)
+    task, model = _eigen_task(c, tmp_path, X, w)
+    ctx = task._ctx
+    Xd, wd = task._traj, task._weights
+    y, s_all = ctx.stats(Xd, wd)
+    h = n // 2 + 13
+    y1, s1 = ctx.stats(Xd[:h], wd[:h])
+    y2, s2 = ctx.stats(Xd[h:], wd[h:])
+    torch.testing.assert_close(s1 + s2, s_all, rtol=1e-12, atol=0)
+    assert torch.equal(torch.cat([y1, y2], 1), y)
+    comb = ctx.combine(s_all)
+    g_all = ctx.grads(Xd, wd, y, comb)
+    g_sum = ctx.grads(Xd[:h], wd[:h], y1.contiguous(), comb) + ctx.grads(Xd[h:], wd[h:], y2.contiguous(), comb)
+    scale = g_all.abs().max()
+    assert (g_all - g_sum).abs().max() <= 1e-9 * scale
+    # sample check against the oracle on a slice
+    comb_o, _, S = cf.eigen_loss_and_grads(X[:3000], w[:3000], c["params"], _pp_pair(c)[1], c["alpha"], c["eig_w"])
+    _, s_small = ctx.stats(Xd[:3000].contiguous(), wd[:3000].contiguous())
+    np.testing.assert_allclose(s_small.cpu().numpy()[0], S["S0"], rtol=1e-6)
+    np.testing.assert_allclose(s_small.cpu().numpy()[-3:], S["SD"], rtol=1e-4)
+
+
+def test_eigen_determinism(tmp_path):
+    c = C.eigen_case("eigen_dipep_k3")
+    X = ref_torch.synth_frames(BASE, 30000, seed=1)
+    w = ref_torch.boltzmann_weights(30000, seed=1)
+    task, model = _eigen_task(c, tmp_path, X, w)
+    outs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        out = task.loss_func(task._traj, task._weights)
+        out[0].backward()
+        outs.append((out[0].clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_eigen_train_matches_reference_run(tmp_path):
+    """Whole train(): same split (numpy global RNG drawn twice), same batches, Adam -- per-iteration losses and the final
+    parameters follow the reference run stored in tests/golden/train_eigen_2d.npz."""
+    from colvarsfinder import core, nn
+    d = C.load("train_eigen_2d")
+    torch.manual_seed(11)
+    model = nn.EigenFunctions([2, 20, 20, 20, 1], 2)
+    for j, p in enumerate(model.parameters()):
+        assert torch.equal(p.detach(), torch.as_tensor(d[f"init_{j}"]))      # same init stream as the reference
+    traj = FakeTrajectory(d["X"].astype(np.float64), d["w"].astype(np.float64), dt=0.1)
+    task = core.EigenFunctionTask(traj, torch.nn.Identity(), model, str(tmp_path), 20.0, [1.0, 0.7], beta=1.0, lag_tau=0,
+                                  learning_rate=0.005, k=2, batch_size=300, num_epochs=3, test_ratio=0.2,
+                                  save_model_every_step=0, device=DEV, verbose=False, debug_mode=False)
+    np.random.seed(77)
+    task.train()
+    tr = np.stack([l[0].numpy() for l in task.loss_list])
+    te = np.stack([l[1].numpy() for l in task.loss_list])
+    assert tr.shape == d["train_hist"].shape and te.shape == d["test_hist"].shape
+    np.testing.assert_allclose(tr, d["train_hist"], rtol=2e-3)
+    np.testing.assert_allclose(te, d["test_hist"], rtol=2e-3)
+    np.testing.assert_allclose(task.train_loss_df.to_numpy(), d["train_df"], rtol=2e-3)
+    assert list(task.train_loss_df.columns) == ['loss', 'eigen_non_penalty', 'eigen_penalty', 'eig_1', 'eig_2']
+    for j, p in enumerate(model.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), d[f"final_{j}"], atol=2e-4)
+
+
+# --------------------------------------------------------------------------------------------- autoencoder
+def _ae_task(c, tmp, F=None, w=None):
+    from colvarsfinder import core, nn
+    model = nn.AutoEncoder(c["e_dims"], c["d_dims"])
+    with torch.no_grad():
+        for p, v in zip(model.encoder.parameters(), c["enc"]):
+            p.copy_(torch.as_tensor(v))
+        for p, v in zip(model.decoder.parameters(), c["dec"]):
+            p.copy_(torch.as_tensor(v))
+    F = c["F"] if F is None else F
+    w = c["w"] if w is None else w
+    task = core.AutoEncoderTask(FakeTrajectory(F, w.astype(np.float64)), torch.nn.Identity(), model, str(tmp), device=DEV,
+                                verbose=False, debug_mode=False)
+    return task, model
+
+
+@pytest.mark.parametrize("name", C.AE_CASES)
+def test_ae_loss_matches_reference_golden(name, tmp_path):
+    c = C.ae_case(name)
+    task, model = _ae_task(c, tmp_path)
+    loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+    loss.backward()
+    assert abs(float(loss) - c["g64_loss"]) <= C.tol(c["g64_loss"], c["r32_loss"])
+    got = [p.grad.cpu().numpy() for p in model.encoder.parameters()] + [p.grad.cpu().numpy() for p in model.decoder.parameters()]
+    for g, g64, g32 in zip(got, c["g64_enc"] + c["g64_dec"], c["g32_enc"] + c["g32_dec"]):
+        assert C.rel_l2(g, g64) <= max(1e-5, 2 * C.rel_l2(g32, g64)), (C.rel_l2(g, g64), C.rel_l2(g32, g64))
+    with torch.no_grad():
+        l2 = task.weighted_MSE_loss(task._feature_traj, task._weights)
+    assert torch.equal(l2, loss.detach())
+
+
+@pytest.mark.parametrize("B", [1, 100, 128, 130, 5000, 40001])
+def test_ae_loss_matches_oracle_ragged_sizes(B, tmp_path):
+    c = C.ae_case("ae_dipep")
+    rng = np.random.default_rng(B)
+    F = (c["F"][rng.integers(0, len(c["F"]), B)] + rng.normal(scale=0.05, size=(B, 66))).astype(np.float32)
+    w = ref_torch.boltzmann_weights(B, seed=B)
+    task, model = _ae_task(c, tmp_path, F, w)
+    loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+    loss.backward()
+    lo, genc, gdec = cf.ae_loss_and_grads(F, w, c["enc"], c["dec"])
+    assert abs(float(loss) - lo) <= 1e-5 * abs(lo)
+    got = [p.grad.cpu().numpy() for p in model.encoder.parameters()] + [p.grad.cpu().numpy() for p in model.decoder.parameters()]
+    for g, go in zip(got, genc + gdec):
+        assert C.rel_l2(g, go) < 2e-5
+
+
+def test_ae_prepass_and_train_match_reference_run(tmp_path):
+    from colvarsfinder import core, nn, utils
+    d = C.load("train_ae_2d")
+    torch.manual_seed(12)
+    model = nn.AutoEncoder([2, 12, 12, 1], [1, 12, 2])
+    for j, p in enumerate(model.parameters()):
+        assert torch.equal(p.detach(), torch.as_tensor(d[f"init_{j}"]))
+    traj = FakeTrajectory(d["X"].astype(np.float64), d["w"].astype(np.float64), dt=0.1)
+    task = core.AutoEncoderTask(traj, torch.nn.Identity(), model, str(tmp_path), learning_rate=0.005, batch_size=200,
+                                num_epochs=3, test_ratio=0.2, save_model_every_step=0, device=DEV, verbose=False,
+                                debug_mode=False)
+    np.random.seed(78)
+    task.train()
+    tr = np.stack([l[0].numpy() for l in task.loss_list])
+    np.testing.assert_allclose(tr, d["train_hist"], rtol=1e-3)
+    np.testing.assert_allclose(np.stack([l[1].numpy() for l in task.loss_list]), d["test_hist"], rtol=1e-3)
+    for j, p in enumerate(model.parameters()):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), d[f"final_{j}"], atol=1e-4)
+    # molecular pre-pass (core.py:635): features of the whole trajectory = aligned coordinates
+    X = ref_torch.synth_frames(BASE, 3000, seed=4)
+    ae = nn.AutoEncoder([66, 20, 20, 20, 2], [2, 10, 10, 66])
+    t2 = core.AutoEncoderTask(FakeTrajectory(X, np.ones(3000)), utils.Align(BASE, list(range(22))), ae, str(tmp_path),
+                              device=DEV, verbose=False, debug_mode=False)
+    yo = cf.kabsch(X.astype(np.float64), list(range(22)), BASE)[0].reshape(3000, 66)
+    assert np.abs(t2._feature_traj.cpu().numpy() - yo).max() < 1e-6
+    assert t2.k == 2 and isinstance(t2.colvar_model(), torch.nn.Sequential)
+
+
+def test_save_model_and_unsupported(tmp_path):
+    from colvarsfinder import core, nn
+    c = C.eigen_case("eigen_2d_k2_nosort")
+    task, model = _eigen_task(c, tmp_path)
+    task.save_model(0)
+    import os
+    assert os.path.isfile(tmp_path / "latest" / "model.pt") and os.path.isfile(tmp_path / "latest" / "0_1_weight.txt")
+    sd = torch.load(tmp_path / "latest" / "model.pt")
+    assert "eigen_funcs.1.2.bias" in sd
+    traj = FakeTrajectory(c["X"], c["w"].astype(np.float64), dt=0.1)
+    with pytest.raises(NotImplementedError):
+        core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1), str(tmp_path), 1.0, [1.0],
+                               lag_tau=0.2, device=DEV, verbose=False)
+    with pytest.raises(RuntimeError, match="Tanh"):
+        core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1, torch.nn.ReLU()), str(tmp_path), 1.0,
+                               [1.0], device=DEV, verbose=False)
