@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""bench.py -- train-step throughput (frames/s) of the colvars-finder step on B200, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1|c4] [--impl reference]
+
+A step is the body of the reference's mini-batch loop (core.py:498-522 / 699-712): zero_grad, loss,
+backward, optimizer.step -- through the drop-in classes, on one batch of synthetic frames per GPU
+(SURVEY.md section 8d).  Default workload C3: alanine-dipeptide-sized frames (22 atoms, Kabsch on all atoms,
+position features d_r = 66), EigenFunctions([66,20,20,20,1], k=3), generator loss, Boltzmann weights.
+Weak scaling: every rank keeps `--frames` frames (default 2^22, 1.1 GB > L2) resident in its own HBM.
+
+`value`   : frames/s with the batch resident in HBM (CUDA events, max over ranks).
+`e2e`     : frames/s with the batch in pinned HOST memory, H2D copy + step + D2H of the loss inside the timed region.
+`roofline`: dominant kernel (pass 2, eigen_kernel<true>) timed alone with CUDA events; algorithmic bytes = 268 B/frame
+            against the measured HBM peak; `roofline_fp32` puts the same kernel against a measured fp32 FMA peak,
+            which is the roofline that actually binds this path.
+`cpu_baseline` / `--impl reference`: oracle/ref_torch.py (restatement of the reference's PyTorch path; /root/reference does
+            not exist on the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "colvars-finder_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, bytes/frame, flops/frame of one step) -- SURVEY.md section 8d
+    "c3": ("alanine-dipeptide EigenFunctionTask, generator loss, k=3, 22-atom Kabsch, position features (d_r=66), "
+           "nets [66,20,20,20,1]", 268, 97400),
+    "c2": ("alanine-dipeptide AutoEncoderTask step on aligned positions (d_r=66), enc [66,20,20,20,2], dec [2,10,10,66]",
+           268, 17640),
+    "c1": ("2-d EigenFunctionTask, generator loss, k=1, Identity pre-processing, net [2,20,20,20,1]", 12, 12040),
+    "c4": ("166-atom chain EigenFunctionTask, generator loss, k=3, 45 distances + 18 dihedrals (d_r=81), "
+           "nets [81,20,20,20,1]", 1996, 128500),
+}
+METRIC = "train-step frames/sec"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth_frames_device(base, n, dev, seed):
+    """frame = base Q + t + eps on the device: Haar rotation from a random unit quaternion,
+    t ~ N(0,5^2) A, eps ~ N(0,0.3^2) A."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    base_t = torch.as_tensor(base, dtype=torch.float32, device=dev)
+    out = torch.empty(n, base_t.shape[0], 3, dtype=torch.float32, device=dev)
+    chunk = 1 << 20
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        q = torch.randn(m, 4, generator=g, device=dev)
+        q = q / q.norm(dim=1, keepdim=True)
+        w, x, y, z = q.unbind(1)
+        Q = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+                         2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                         2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1).reshape(m, 3, 3)
+        fr = torch.einsum("ni,bij->bnj", base_t, Q)
+        fr += 5.0 * torch.randn(m, 1, 3, generator=g, device=dev)
+        fr += 0.3 * torch.randn(m, base_t.shape[0], 3, generator=g, device=dev)
+        out[s:s + m] = fr
+    return out
+
+
+def boltzmann_weights_device(n, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed + 1)
+    E = torch.randn(n, generator=g, device=dev)
+    w = torch.exp(-0.5 * (E - E.mean()))
+    return (w / w.mean()).contiguous()
+
+
+def c4_features():
+    """45 pair distances among 10 designated atoms + 18 backbone dihedrals of the 166-atom chain."""
+    sel = list(range(5, 166, 16))[:10]
+    feats = [("bond", [a, b]) for i, a in enumerate(sel) for b in sel[i + 1:]]
+    feats += [("dihedral", [s, s + 1, s + 2, s + 3]) for s in range(10, 10 + 18 * 8, 8)]
+    return feats, list(range(0, 160, 4))
+
+
+def build_workload(name, n_frames, dev, seed, lr=1e-3):
+    """Returns (step_fn(X, w) -> loss tensor, X, w, task, launches_per_step, dominant(X, w) -> None)."""
+    from colvarsfinder import core, nn, utils
+    from oracle import ref_torch
+    from oracle.ref_import import FakeTrajectory
+    torch.manual_seed(2026)
+    tmp = f"/tmp/cvf_bench_{os.getpid()}"
+    if name in ("c3", "c2"):
+        base = ref_torch.DIPEPTIDE_NM * 10.0
+        X = synth_frames_device(base, n_frames, dev, seed)
+        w = boltzmann_weights_device(n_frames, dev, seed) if name == "c3" else torch.ones(n_frames, device=dev)
+        small = FakeTrajectory(X[:1024].cpu().numpy(), np.ones(1024), dt=1.0)
+        align = utils.Align(base, list(range(22)))
+        if name == "c3":
+            model = nn.EigenFunctions([66, 20, 20, 20, 1], 3)
+            task = core.EigenFunctionTask(small, align, model, tmp, 20.0, [1.0, 0.6, 0.3], k=3, learning_rate=lr, device=dev,
+                                          verbose=False, debug_mode=False)
+        else:
+            model = nn.AutoEncoder([66, 20, 20, 20, 2], [2, 10, 10, 66])
+            task = core.AutoEncoderTask(small, align, model, tmp, learning_rate=lr, device=dev, verbose=False, debug_mode=False)
+            X = task.preprocessing_layer(X).reshape(n_frames, 66).contiguous()   # the pre-pass is outside the step (core.py:635)
+    elif name == "c1":
+        g = torch.Generator(device=dev).manual_seed(seed)
+        th = (torch.rand(n_frames, generator=g, device=dev) * 2 - 1) * np.pi
+        r = 1.0 + 0.25 * torch.randn(n_frames, generator=g, device=dev)
+        X = torch.stack([r * torch.cos(th), r * torch.sin(th)], 1).contiguous()
+        w = torch.ones(n_frames, device=dev)
+        small = FakeTrajectory(X[:1024].cpu().numpy(), np.ones(1024), dt=0.1)
+        model = nn.EigenFunctions([2, 20, 20, 20, 1], 1)
+        task = core.EigenFunctionTask(small, torch.nn.Identity(), model, tmp, 20.0, [1.0], k=1, learning_rate=lr, device=dev,
+                                      verbose=False, debug_mode=False)
+    elif name == "c4":
+        base = ref_torch.chain_structure(166, seed=2026)
+        X = synth_frames_device(base, n_frames, dev, seed)
+        w = boltzmann_weights_device(n_frames, dev, seed)
+        feats, align_idx = c4_features()
+        pp = utils.Preprocessing(utils.Align(base[align_idx], align_idx), utils.FeatureMap(feats))
+        small = FakeTrajectory(X[:1024].cpu().numpy(), np.ones(1024), dt=1.0)
+        model = nn.EigenFunctions([81, 20, 20, 20, 1], 3)
+        task = core.EigenFunctionTask(small, pp, model, tmp, 20.0, [1.0, 0.6, 0.3], k=3, learning_rate=lr, device=dev,
+                                      verbose=False, debug_mode=False)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+
+    if isinstance(task, core.EigenFunctionTask):
+        def step(Xb, wb):
+            task.optimizer.zero_grad(set_to_none=True)
+            loss = task.loss_func(Xb, wb, None, None)[0]
+            loss.backward()
+            task.optimizer.step()
+            return loss
+        launches = 5      # eigen_kernel<stats>, reduce, combine, eigen_kernel<grad>, reduce
+
+        def dominant(Xb, wb):
+            ctx = task._ctx
+            y, stats = ctx.stats(Xb, wb)
+            comb = ctx.combine(stats)
+            return lambda: ctx.grads(Xb, wb, y, comb)
+    else:
+        def step(Xb, wb):
+            task.optimizer.zero_grad(set_to_none=True)
+            loss = task.weighted_MSE_loss(Xb, wb)
+            loss.backward()
+            task.optimizer.step()
+            return loss
+        launches = 3      # ae_kernel, 2 x reduce
+
+        def dominant(Xb, wb):
+            return lambda: task._ctx.step(Xb, wb, True)
+    return step, X, w, task, launches, dominant
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
+    """The reference's PyTorch path (oracle/ref_torch.py restatement: autograd through torch.linalg.svd, double
+    backward, Adam) on the host cores.  Returns (frames/s, ms/step, cores)."""
+    from oracle import ref_torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(2026)
+    if name in ("c3", "c2"):
+        base = ref_torch.DIPEPTIDE_NM * 10.0
+        X = torch.as_tensor(ref_torch.synth_frames(base, n_frames, seed=seed))
+        w = torch.as_tensor(ref_torch.boltzmann_weights(n_frames, seed=seed)) if name == "c3" else torch.ones(n_frames)
+        pp = ref_torch.Preprocess(ref_torch.Align(base, list(range(22))), None)
+    elif name == "c1":
+        rng = np.random.default_rng(seed)
+        th, r = rng.uniform(-np.pi, np.pi, n_frames), rng.normal(1.0, 0.25, n_frames)
+        X = torch.as_tensor(np.stack([r * np.cos(th), r * np.sin(th)], 1).astype(np.float32))
+        w = torch.ones(n_frames)
+        pp = ref_torch.Preprocess()
+    else:
+        base = ref_torch.chain_structure(166, seed=2026)
+        X = torch.as_tensor(ref_torch.synth_frames(base, n_frames, seed=seed))
+        w = torch.as_tensor(ref_torch.boltzmann_weights(n_frames, seed=seed))
+        feats, align_idx = c4_features()
+        pp = ref_torch.Preprocess(ref_torch.Align(base[align_idx], align_idx), ref_torch.FeatureMap(feats))
+    if name == "c2":
+        enc = [p.requires_grad_() for p in ref_torch.init_mlp_params([66, 20, 20, 20, 2])]
+        dec = [p.requires_grad_() for p in ref_torch.init_mlp_params([2, 10, 10, 66])]
+        params = enc + dec
+        with torch.no_grad():
+            Fx = pp(X.double()).float()
+
+        def loss_fn():
+            return ref_torch.ae_loss(Fx, w, enc, dec)
+    else:
+        dims = {"c3": [66, 20, 20, 20, 1], "c1": [2, 20, 20, 20, 1], "c4": [81, 20, 20, 20, 1]}[name]
+        k = 1 if name == "c1" else 3
+        nets = [[p.requires_grad_() for p in ref_torch.init_mlp_params(dims)] for _ in range(k)]
+        params = [p for n in nets for p in n]
+        eig_w = [1.0, 0.6, 0.3][:k]
+
+        def loss_fn():
+            Xr = X.clone().requires_grad_()
+            return ref_torch.eigen_loss(Xr, w, nets, pp, 20.0, eig_w)[0]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn()
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return n_frames * steps / total, 1e3 * total / steps, cores
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=1 << 22, help="frames per GPU per step")
+    ap.add_argument("--cpu-frames", type=int, default=100000, help="frames per step of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    desc, bytes_per_frame, flops_per_frame = WORKLOADS[args.workload]
+    config = {"workload": f"{args.workload.upper()}: {desc}", "frames_per_gpu_per_step": args.frames,
+              "global_batch": args.frames * max(world, 1), "optimizer": "Adam", "parallelism": f"dp{max(world, 1)}",
+              "l2_policy": "inputs larger than L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w_ = max(args.warmup, 1)
+        fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, args.steps, w_)
+        sample = (f"{args.cpu_frames} frames/step x {args.steps} steps (+{w_} warm-up) of the same synthetic workload, "
+                  "oracle/ref_torch.py (PyTorch CPU autograd restatement of core.py:387-457,517 + Adam)")
+        config["frames_per_gpu_per_step"] = args.cpu_frames
+        config["global_batch"] = args.cpu_frames
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": w_, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    import __graft_entry__ as entry
+    if rank == 0:
+        entry.build()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    entry.build()
+    from colvarsfinder import _lib
+
+    step, X, w, task, launches, dominant = build_workload(args.workload, args.frames, dev, seed=2026 + rank)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-in-HBM throughput
+    for _ in range(W):
+        step(X, w)
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step(X, w)
+    e1.record()
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        torch.distributed.all_reduce(ms_total, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(ms_total)
+    value = args.frames * world * K / (ms_total * 1e-3)
+    final_loss = float(loss)
+
+    # ---- end to end: batch in pinned host memory, H2D + step + D2H(loss) per step, copy of step i+1 overlapped
+    hosts = [torch.empty(X.shape, dtype=X.dtype).pin_memory() for _ in range(2)]
+    hw = [torch.empty(w.shape, dtype=w.dtype).pin_memory() for _ in range(2)]
+    for hb, hwb in zip(hosts, hw):
+        hb.copy_(X)
+        hwb.copy_(w)
+    devb = [torch.empty_like(X) for _ in range(2)]
+    devw = [torch.empty_like(w) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = X.numel() * 4 + w.numel() * 4
+
+    def enqueue_copy(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            devb[b].copy_(hosts[b], non_blocking=True)
+            devw[b].copy_(hw[b], non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        for b in range(2):
+            freed[b].record(cur)
+        enqueue_copy(0)
+        for i in range(n):
+            b = i % 2
+            if i + 1 < n:
+                enqueue_copy(i + 1)
+            cur.wait_event(ready[b])
+            l = step(devb[b], devw[b])
+            freed[b].record(cur)
+            loss_host.copy_(l.detach(), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(2)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(K)
+    t1.record()
+    barrier()
+    ms_e2e = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(ms_e2e, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = args.frames * world * K / (float(ms_e2e) * 1e-3)
+    del hosts, hw, devb, devw
+
+    # ---- dominant kernel alone (pass 2 / AE step) with CUDA events on the launching stream
+    run = dominant(X, w)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(K):
+        run()
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / K
+    # ---- fp32 FMA peak probe
+    sink = torch.zeros(4, device=dev)
+    flops = C.c_double(0.0)
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        _lib.check(L.cvf_fma_probe(sink.data_ptr(), 20000, C.byref(flops), stream), "cvf_fma_probe")
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(3):
+        _lib.check(L.cvf_fma_probe(sink.data_ptr(), 20000, C.byref(flops), stream), "cvf_fma_probe")
+    p1.record()
+    torch.cuda.synchronize()
+    fma_peak = 3 * flops.value / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    hbm_peak, peak_src = measured_peaks()
+    achieved = bytes_per_frame * args.frames / (kern_ms * 1e-3) / 1e9
+    # flops of the dominant kernel per frame: C3/C4/C1 pass 2 ~ (step - pass 1); use the whole-step figure for the step
+    step_tflops = value / world * flops_per_frame / 1e12
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config, "clocks": clocks, "final_loss": final_loss,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                "ms_per_step": float(ms_e2e) / K},
+        "gpu_launches": launches * K * world,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "kernel": "eigen_kernel<GRAD>" if launches == 5 else "ae_kernel<GRAD>",
+                     "kernel_ms": kern_ms, "peak_source": peak_src,
+                     "note": "this step is fp32-FMA bound (SURVEY 8d), see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32_fma", "achieved": step_tflops, "peak": fma_peak, "unit": "TFLOP/s",
+                          "frac": step_tflops / fma_peak, "flops_per_frame": flops_per_frame,
+                          "peak_source": "cvf_fma_probe measured in this run"},
+    }
+    if not args.no_cpu_baseline:
+        fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, 5, 1)
+        out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": f"{args.cpu_frames} frames/step x 5 steps (+1 warm-up), oracle/ref_torch.py on the host"}
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

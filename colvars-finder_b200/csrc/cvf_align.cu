@@ -69,11 +69,12 @@ __device__ __forceinline__ void align_frame_inplace(float* fr, int n_atoms, cons
     H[6] += pz * rx, H[7] += pz * ry, H[8] += pz * rz;
   }
   float R[9];
-  cvf_rotation(H, R, nullptr);
+  double Rd[9];
+  cvf_rotation(H, R, nullptr, Rd);
   const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
   for (int a = 0; a < n_atoms; ++a) {
     float* p = fr + 3 * a;
-    const cvf_v3 y = mul_rowvec(v3(p[0] - fx, p[1] - fy, p[2] - fz), R);
+    const cvf_v3 y = cvf_transform(p[0], p[1], p[2], cx, cy, cz, Rd);
     p[0] = y.x, p[1] = y.y, p[2] = y.z;
   }
 #pragma unroll
@@ -177,14 +178,15 @@ align_warp_kernel(const float* __restrict__ x, long long B, int n_atoms, const i
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) H[i] += __shfl_xor_sync(0xffffffffu, H[i], o);
     float R[9];
-    cvf_rotation(H, R, nullptr);
+    double Rd[9];
+    cvf_rotation(H, R, nullptr, Rd);
     const float c[3] = {(float)cx, (float)cy, (float)cz};
     float* out = y + (size_t)f * fl;
     // coalesced: lane handles coordinate j of atom j/3; output coordinate b = sum_a (x_a - c_a) R[a][b]
     for (int j = lane; j < fl; j += 32) {
       const int a = j / 3, b = j - 3 * a;
       const float* p = fr + 3 * a;
-      out[j] = (p[0] - c[0]) * R[b] + (p[1] - c[1]) * R[3 + b] + (p[2] - c[2]) * R[6 + b];
+      out[j] = (float)((p[0] - cx) * Rd[b] + (p[1] - cy) * Rd[3 + b] + (p[2] - cz) * Rd[6 + b]);
     }
     if (lane < 9 && R_out) R_out[f * 9 + lane] = R[lane];
     if (lane < 3 && c_out) c_out[f * 3 + lane] = c[lane];
@@ -240,11 +242,11 @@ features_kernel(const FeatPlan P, const float* __restrict__ x, long long B, floa
           H[6] += pz * rx, H[7] += pz * ry, H[8] += pz * rz;
         }
         float R[9];
-        cvf_rotation(H, R, nullptr);
-        const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+        double Rd[9];
+        cvf_rotation(H, R, nullptr, Rd);
         for (int a = 0; a < P.n_used; ++a) {
           const cvf_v3 p = ld(a);
-          const cvf_v3 q = mul_rowvec(v3(p.x - fx, p.y - fy, p.z - fz), R);
+          const cvf_v3 q = cvf_transform(p.x, p.y, p.z, cx, cy, cz, Rd);
           Y[(3 * a) * S + f] = q.x, Y[(3 * a + 1) * S + f] = q.y, Y[(3 * a + 2) * S + f] = q.z;
         }
       }

@@ -47,3 +47,33 @@ extern "C" int64_t cvf_mlp_param_count(const cvf_mlp* net) {
   if (cvf::make_net_plan(net, &np)) return -1;
   return np.n_params;
 }
+
+// ---- fp32 FMA probe ------------------------------------------------------------------------------------
+namespace cvf {
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* sink, int iters) {
+  float a[16];
+  const float x = 1.0f + 1e-7f * threadIdx.x, y = 1e-9f * blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) sink[0] = s;   // never true: keeps the chains alive
+}
+}  // namespace cvf
+
+extern "C" int cvf_fma_probe(float* sink, int32_t iters, double* flops_out, void* stream) {
+  if (!sink || iters < 1 || !flops_out) {
+    cvf::set_error("cvf_fma_probe: bad argument");
+    return CVF_E_ARG;
+  }
+  const int grid = cvf::sm_count() * 8;
+  cvf::fma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+  *flops_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)grid;
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}

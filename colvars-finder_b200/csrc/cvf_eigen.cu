@@ -211,15 +211,15 @@ __device__ void preprocess_frame(const EigenPlan& P, float* rows, int f) {
       H[6] += pz * rx, H[7] += pz * ry, H[8] += pz * rz;
     }
     float R[9], Ki[6];
-    cvf_rotation(H, R, Ki);
+    double Rd[9];
+    cvf_rotation(H, R, Ki, Rd);
 #pragma unroll
     for (int i = 0; i < 9; ++i) rows[(P.row_R + i) * FS + f] = R[i];
 #pragma unroll
     for (int i = 0; i < 6; ++i) rows[(P.row_Kinv + i) * FS + f] = Ki[i];
-    const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
     for (int a = 0; a < P.n_used; ++a) {
       const cvf_v3 p = ldv(Y, FS, a, f);
-      stv(Y, FS, a, f, mul_rowvec(v3(p.x - fx, p.y - fy, p.z - fz), R));
+      stv(Y, FS, a, f, cvf_transform(p.x, p.y, p.z, cx, cy, cz, Rd));
     }
   }
   if (P.pos_alias) return;

@@ -76,7 +76,7 @@ CVF_HD void cvf_jacobi_rot(float (&a)[4][4], float (&v)[4][4]) {
 
 // H[9] row-major covariance (x_A-c)^T ref in double.  Outputs R[9] (row-major, y = (x-c) R) and,
 // if Kinv != nullptr, the inverse of K = tr(M) I - M, M = sym(R^T H), as (xx,xy,xz,yy,yz,zz).
-CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv) {
+CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out = nullptr) {
   // Horn (1987) 4x4 matrix; its top eigenvector is the unit quaternion of the column-convention rotation R^T.
   float a[4][4], v[4][4];
   {
@@ -181,10 +181,22 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv) {
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = (float)Rd[i];
+  if (Rd_out) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rd_out[i] = Rd[i];
+  }
   if (Kinv) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) Kinv[i] = (float)Ki[i];
   }
+}
+
+// y = (x - c) R evaluated in double and rounded once: keeps aligned coordinates within 1 ulp of the exact
+// value (the float32 rounding of a 15 A centroid alone would cost 5e-7 A).
+CVF_HD cvf_v3 cvf_transform(float px, float py, float pz, double cx, double cy, double cz, const double* Rd) {
+  const double dx = px - cx, dy = py - cy, dz = pz - cz;
+  return v3((float)(dx * Rd[0] + dy * Rd[3] + dz * Rd[6]), (float)(dx * Rd[1] + dy * Rd[4] + dz * Rd[7]),
+            (float)(dx * Rd[2] + dy * Rd[5] + dz * Rd[8]));
 }
 
 // ---- feature stencils (values + gradient w.r.t. the atoms of the feature) -------------------------

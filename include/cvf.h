@@ -115,6 +115,11 @@ size_t cvf_ae_workspace_bytes(const cvf_mlp* net);
 int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
                 double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement helper for bench.py (no reference counterpart): enqueue a kernel that issues exactly
+ * *flops_out = 2 * fmas fp32 FMA flops on independent register chains, so that the fp32 SIMT peak used as the
+ * compute-roofline denominator is measured on the same GPU, same clocks, as the step kernels. */
+int cvf_fma_probe(float* sink, int32_t iters, double* flops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,11 +93,11 @@ def test_features_fwd_matches_oracle():
     r = pp.to(DEV)(torch.as_tensor(X, device=DEV)).cpu().numpy()
     ro = ppo.prepare(X.astype(np.float64))["r"]
     assert r.shape == ro.shape
-    assert np.abs(r - ro).max() < 5e-6
+    assert np.abs(r - ro).max() < 2e-5        # fp32 feature arithmetic on values up to ~10 (float32 eps * 10 * a few ops)
     c = C.eigen_case("eigen_dipep_invariant")
     pp, ppo = _pp_pair(c)
     r = pp.to(DEV)(torch.as_tensor(X, device=DEV)).cpu().numpy()
-    assert np.abs(r - ppo.prepare(X.astype(np.float64))["r"]).max() < 5e-6
+    assert np.abs(r - ppo.prepare(X.astype(np.float64))["r"]).max() < 2e-5
 
 
 # --------------------------------------------------------------------------------------------- eigenfunction loss
@@ -163,7 +163,8 @@ def test_eigen_loss_matches_oracle_ragged_sizes(name, B, tmp_path):
     np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
     for i in range(c["k"]):
         for j in range(len(g64[i])):
-            if np.abs(g64[i][j]).max() < 1e-12:
+            if np.abs(g64[i][j]).max() < 1e-9 * abs(comb["loss"]):     # last-layer bias: zero up to rounding
+                assert np.abs(grads[i][j]).max() < 1e-4 * abs(comb["loss"])
                 continue
             assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (i, j, C.rel_l2(grads[i][j], g64[i][j]))
 
@@ -191,7 +192,7 @@ def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
     g_all = ctx.grads(Xd, wd, y, comb)
     g_sum = ctx.grads(Xd[:h], wd[:h], y1.contiguous(), comb) + ctx.grads(Xd[h:], wd[h:], y2.contiguous(), comb)
     scale = g_all.abs().max()
-    assert (g_all - g_sum).abs().max() <= 1e-9 * scale
+    assert (g_all - g_sum).abs().max() <= 2e-6 * scale      # fp32 within-tile sums regroup when the tile boundaries move
     # sample check against the oracle on a slice
     comb_o, _, S = cf.eigen_loss_and_grads(X[:3000], w[:3000], c["params"], _pp_pair(c)[1], c["alpha"], c["eig_w"])
     _, s_small = ctx.stats(Xd[:3000].contiguous(), wd[:3000].contiguous())
@@ -235,7 +236,11 @@ def test_eigen_train_matches_reference_run(tmp_path):
     np.testing.assert_allclose(te, d["test_hist"], rtol=2e-3)
     np.testing.assert_allclose(task.train_loss_df.to_numpy(), d["train_df"], rtol=2e-3)
     assert list(task.train_loss_df.columns) == ['loss', 'eigen_non_penalty', 'eigen_penalty', 'eig_1', 'eig_2']
-    for j, p in enumerate(model.parameters()):
+    for j, (name, p) in enumerate(model.named_parameters()):
+        if name.endswith("4.bias"):
+            # the last-layer bias has an exactly-zero gradient in the generator loss (it cancels from var, cov and
+            # grad f); Adam turns the rounding noise of either implementation into +-lr steps, so it is not comparable
+            continue
         np.testing.assert_allclose(p.detach().cpu().numpy(), d[f"final_{j}"], atol=2e-4)
 
 
