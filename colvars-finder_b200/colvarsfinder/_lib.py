@@ -21,7 +21,7 @@ class Preproc(C.Structure):
     """struct cvf_preproc (include/cvf.h)."""
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_atoms", C.c_int32), ("n_used", C.c_int32),
                 ("used_atoms", C.c_void_p), ("n_align", C.c_int32), ("align_used", C.c_void_p), ("ref", C.c_void_p),
-                ("n_feat", C.c_int32), ("feat", C.c_void_p), ("d_r", C.c_int32), ("positions_only", C.c_int32),
+                ("n_feat", C.c_int32), ("feat", C.c_void_p), ("d_r", C.c_int32), ("positions_only", C.c_int32), ("used_identity", C.c_int32),
                 ("diag", C.c_void_p)]
 
 

@@ -116,6 +116,7 @@ class PreprocSpec:
             s.n_feat, s.d_r = len(records), d_r
             s.feat = self._dev(torch.tensor(table, dtype=torch.int32).reshape(-1))
             s.positions_only = 1 if positions_only else 0
+            s.used_identity = 1 if used == list(range(n_atoms)) else 0
             if diag is not None:
                 g = diag.reshape(n_atoms, 3)[torch.tensor(used, dtype=torch.long)].reshape(-1).contiguous()
                 s.diag = self._dev(g)

@@ -43,14 +43,16 @@ static size_t ae_layout(AePlan* P, int F) {
   return P->smem_bytes;
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(256, 1)
+template <bool GRAD, int FPL>
+__global__ void __launch_bounds__(384, 1)
 ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restrict__ w, long long B,
           const float* __restrict__ params, double* __restrict__ partial) {
   extern __shared__ __align__(16) float smem[];
   const NetPlan& np = P.net;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int FS = P.FS, F = P.F, FB = P.FB, L = np.L;
+  const int FS = P.FS, F = P.F, L = np.L;
+  const int FB = F / FPL;
+  typedef FVec<FPL> V;
   float* Wsm = smem + P.off_params;
   float* rows = smem + P.off_rows;
   double* red = reinterpret_cast<double*>(smem + P.off_red);
@@ -64,10 +66,37 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
   const long long n_tiles = (B + F - 1) / F;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long f_base = tile * F;
-    for (int idx = tid; idx < F * d0; idx += nt) {
-      const int f = idx / d0, j = idx - f * d0;
-      const long long fr = min(f_base + f, B - 1);
-      rows[(P.a_row[0] + j) * FS + f] = feat[fr * d0 + j];
+    {
+      // all loads of a thread are issued before its first store (8 in flight); next tile prefetched into L2
+      const int total = F * d0;
+      const long long last = B * (long long)d0 - 1;
+      for (int base = 0; base < total; base += 8 * nt) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = base + j * nt + tid;
+          if (idx < total) v[j] = __ldg(feat + min(f_base * d0 + idx, last));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = base + j * nt + tid;
+          if (idx < total) {
+            const int f = idx / d0, u = idx - f * d0;
+            rows[(P.a_row[0] + u) * FS + f] = v[j];
+          }
+        }
+      }
+      if (tid == 0) {
+        const long long nxt = tile + gridDim.x;
+        if (nxt < n_tiles) {
+          const long long nb = nxt * F;
+          const long long nf = min((long long)F, B - nb);
+          const float* pn = feat + (size_t)nb * d0;
+          const unsigned bytes = (unsigned)((nf * d0 * 4) & ~15LL);
+          if (((reinterpret_cast<uintptr_t>(pn) & 15) == 0) && bytes > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pn), "r"(bytes) : "memory");
+        }
+      }
     }
     for (int f = tid; f < F; f += nt) rows[P.row_w * FS + f] = f_base + f < B ? w[f_base + f] : 0.0f;
     __syncthreads();
@@ -80,16 +109,17 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
       const int items = ((nout + 3) >> 2) * FB;
       for (int it = tid; it < items; it += nt) {
         const int ob = it / FB, fb = it - ob * FB;
-        float acc[4][4];
-        tile_fwd(acc, Wsm + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, 4 * fb);
+        float acc[4][FPL];
+        tile_fwd<FPL>(acc, Wsm + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, FPL * fb);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int o = 4 * ob + j;
           if (o < nout) {
             const float b = Wsm[np.b_off[l] + o];
-            float4 v = make_float4(acc[j][0] + b, acc[j][1] + b, acc[j][2] + b, acc[j][3] + b);
-            if (act) v = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
-            st4(out + o * FS + 4 * fb, v);
+            V v;
+#pragma unroll
+            for (int f = 0; f < FPL; ++f) v.v[f] = act ? cvf_tanh(acc[j][f] + b) : acc[j][f] + b;
+            v.st(out + o * FS + FPL * fb);
           }
         }
       }
@@ -128,30 +158,29 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
         const int nin = np.dims[l], nout = np.dims[l + 1];
         const float* S = rows + P.s_row[l + 1] * FS;
         const float* Ain = rows + P.a_row[l] * FS;
-        const int n_outer = ((nout + 3) >> 2) * ((nin + 3) >> 2);
+        // both kinds of work only read s_l and A_{l-1}: outer products first, then the back-propagation items
+        outer_layer(0, tid, nt, nout, nin, S, Ain, nullptr, nullptr, FS, F, part + 2 + np.gw_off[l], part + 2 + np.gb_off[l]);
         const int n_back = l > 0 ? ((nin + 3) >> 2) * FB : 0;
-        // both kinds of work item only read s_l and A_{l-1}: run them in the same phase
-        for (int it = tid; it < n_outer + n_back; it += nt) {
-          if (it < n_outer) {
-            outer_item(it, nout, nin, S, Ain, nullptr, nullptr, FS, F, part + 2 + np.gw_off[l], part + 2 + np.gb_off[l]);
-          } else {
-            const int it2 = it - n_outer;
-            const int ib = it2 / FB, fb = it2 - ib * FB;
-            float acc[4][4];
-            tile_tr(acc, Wsm + np.w_off[l], np.ld[l], 4 * ib, nout, S, FS, 4 * fb);
-            float* Sout = rows + P.s_row[l] * FS;
-            const bool act = np.act[l - 1] != 0;
+        for (int it2 = tid; it2 < n_back; it2 += nt) {
+          const int ib = it2 / FB, fb = it2 - ib * FB;
+          float acc[4][FPL];
+          tile_tr<FPL>(acc, Wsm + np.w_off[l], np.ld[l], 4 * ib, nout, S, FS, FPL * fb);
+          float* Sout = rows + P.s_row[l] * FS;
+          const bool act = np.act[l - 1] != 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = 4 * ib + j;
-              if (i < nin) {
-                float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                if (act) {
-                  const float4 a = ld4(Ain + i * FS + 4 * fb);
-                  v = make_float4(v.x * (1.f - a.x * a.x), v.y * (1.f - a.y * a.y), v.z * (1.f - a.z * a.z), v.w * (1.f - a.w * a.w));
-                }
-                st4(Sout + i * FS + 4 * fb, v);
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * ib + j;
+            if (i < nin) {
+              V v;
+              if (act) {
+                const V a = V::ld(Ain + i * FS + FPL * fb);
+#pragma unroll
+                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f] * (1.f - a.v[f] * a.v[f]);
+              } else {
+#pragma unroll
+                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f];
               }
+              v.st(Sout + i * FS + FPL * fb);
             }
           }
         }
@@ -186,7 +215,7 @@ static int ae_plan(const cvf_mlp* net, AePlan* P) {
       return CVF_E_UNSUPPORTED;
     }
   }
-  P->nthreads = 256;
+  P->nthreads = 384;
   return 0;
 }
 
@@ -216,11 +245,11 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
     return CVF_E_WORKSPACE;
   }
   if (grad) {
-    CVF_CUDA(cudaFuncSetAttribute(ae_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    ae_kernel<true><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
+    CVF_CUDA(cudaFuncSetAttribute(ae_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    ae_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
   } else {
-    CVF_CUDA(cudaFuncSetAttribute(ae_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    ae_kernel<false><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
+    CVF_CUDA(cudaFuncSetAttribute(ae_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    ae_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
   }
   CVF_CUDA(cudaGetLastError());
   // partial layout per CTA: [sum w|e|^2, sum w, grad...]; two reductions keep the output buffers separate

@@ -98,87 +98,124 @@ __device__ inline void load_net_params(const NetPlan& np, const float* __restric
   }
 }
 
+// ---- vectors of FPL consecutive frames (FPL = 2: LDS.64, FPL = 4: LDS.128) ----------------------------
+template <int N> struct FVec;
+template <> struct FVec<2> {
+  float v[2];
+  __device__ __forceinline__ static FVec ld(const float* p) { const float2 t = *reinterpret_cast<const float2*>(p); return FVec{{t.x, t.y}}; }
+  __device__ __forceinline__ void st(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <> struct FVec<4> {
+  float v[4];
+  __device__ __forceinline__ static FVec ld(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); return FVec{{t.x, t.y, t.z, t.w}}; }
+  __device__ __forceinline__ void st(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+// tanh with <= ~3 ulp error and no divergent slow path: odd minimax polynomial below 0.55, 1 - 2/(e^{2|x|}+1)
+// with ex2.approx / rcp.approx above (tanh.approx's 2^-11 error would break the 1e-5 parity target).
+__device__ __forceinline__ float cvf_tanh(float x) {
+  const float ax = fabsf(x), s = x * x;
+  float p = fmaf(-0.00622109929f, s, 0.0210381374f);
+  p = fmaf(p, s, -0.0538453273f);
+  p = fmaf(p, s, 0.133325338f);
+  p = fmaf(p, s, -0.333333164f);
+  const float small = fmaf(x * s, p, x);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390082f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  const float big = copysignf(fmaf(-2.0f, r, 1.0f), x);
+  return ax < 0.55f ? small : big;
+}
+
 // acc[j][f] = sum_i W[o0+j][i] * in[i][f0+f]      (rows of W clamped to n_out-1 for the tail block)
-__device__ __forceinline__ void tile_fwd(float (&acc)[4][4], const float* __restrict__ W, int ld, int o0, int n_out,
+template <int FPL>
+__device__ __forceinline__ void tile_fwd(float (&acc)[4][FPL], const float* __restrict__ W, int ld, int o0, int n_out,
                                          int n_in, const float* __restrict__ in, int FS, int f0) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int f = 0; f < 4; ++f) acc[j][f] = 0.0f;
-  const float* w0 = W + min(o0 + 0, n_out - 1) * ld;
-  const float* w1 = W + min(o0 + 1, n_out - 1) * ld;
-  const float* w2 = W + min(o0 + 2, n_out - 1) * ld;
-  const float* w3 = W + min(o0 + 3, n_out - 1) * ld;
+    for (int f = 0; f < FPL; ++f) acc[j][f] = 0.0f;
+  const float* wr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wr[j] = W + min(o0 + j, n_out - 1) * ld;
   const float* a = in + f0;
   int i = 0;
 #pragma unroll 2
   for (; i + 4 <= n_in; i += 4) {
-    const float4 wv[4] = {ld4(w0 + i), ld4(w1 + i), ld4(w2 + i), ld4(w3 + i)};
-    const float4 a0 = ld4(a + (i + 0) * FS), a1 = ld4(a + (i + 1) * FS), a2 = ld4(a + (i + 2) * FS), a3 = ld4(a + (i + 3) * FS);
+    float4 wv[4];
+    FVec<FPL> av[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      acc[j][0] = fmaf(wv[j].x, a0.x, acc[j][0]); acc[j][1] = fmaf(wv[j].x, a0.y, acc[j][1]);
-      acc[j][2] = fmaf(wv[j].x, a0.z, acc[j][2]); acc[j][3] = fmaf(wv[j].x, a0.w, acc[j][3]);
-      acc[j][0] = fmaf(wv[j].y, a1.x, acc[j][0]); acc[j][1] = fmaf(wv[j].y, a1.y, acc[j][1]);
-      acc[j][2] = fmaf(wv[j].y, a1.z, acc[j][2]); acc[j][3] = fmaf(wv[j].y, a1.w, acc[j][3]);
-      acc[j][0] = fmaf(wv[j].z, a2.x, acc[j][0]); acc[j][1] = fmaf(wv[j].z, a2.y, acc[j][1]);
-      acc[j][2] = fmaf(wv[j].z, a2.z, acc[j][2]); acc[j][3] = fmaf(wv[j].z, a2.w, acc[j][3]);
-      acc[j][0] = fmaf(wv[j].w, a3.x, acc[j][0]); acc[j][1] = fmaf(wv[j].w, a3.y, acc[j][1]);
-      acc[j][2] = fmaf(wv[j].w, a3.z, acc[j][2]); acc[j][3] = fmaf(wv[j].w, a3.w, acc[j][3]);
-    }
+    for (int j = 0; j < 4; ++j) wv[j] = ld4(wr[j] + i);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) av[q] = FVec<FPL>::ld(a + (i + q) * FS);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int f = 0; f < FPL; ++f) {
+        acc[j][f] = fmaf(wv[j].x, av[0].v[f], acc[j][f]);
+        acc[j][f] = fmaf(wv[j].y, av[1].v[f], acc[j][f]);
+        acc[j][f] = fmaf(wv[j].z, av[2].v[f], acc[j][f]);
+        acc[j][f] = fmaf(wv[j].w, av[3].v[f], acc[j][f]);
+      }
   }
   for (; i < n_in; ++i) {
-    const float4 av = ld4(a + i * FS);
-    const float wj[4] = {w0[i], w1[i], w2[i], w3[i]};
+    const FVec<FPL> av = FVec<FPL>::ld(a + i * FS);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      acc[j][0] = fmaf(wj[j], av.x, acc[j][0]); acc[j][1] = fmaf(wj[j], av.y, acc[j][1]);
-      acc[j][2] = fmaf(wj[j], av.z, acc[j][2]); acc[j][3] = fmaf(wj[j], av.w, acc[j][3]);
+      const float wj = wr[j][i];
+#pragma unroll
+      for (int f = 0; f < FPL; ++f) acc[j][f] = fmaf(wj, av.v[f], acc[j][f]);
     }
   }
 }
 
 // acc[j][f] = sum_o W[o][i0+j] * in[o][f0+f]
-__device__ __forceinline__ void tile_tr(float (&acc)[4][4], const float* __restrict__ W, int ld, int i0, int n_out,
+template <int FPL>
+__device__ __forceinline__ void tile_tr(float (&acc)[4][FPL], const float* __restrict__ W, int ld, int i0, int n_out,
                                         const float* __restrict__ in, int FS, int f0) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int f = 0; f < 4; ++f) acc[j][f] = 0.0f;
+    for (int f = 0; f < FPL; ++f) acc[j][f] = 0.0f;
   const float* wp = W + i0;
   const float* a = in + f0;
 #pragma unroll 4
   for (int o = 0; o < n_out; ++o) {
     const float4 wv = ld4(wp + o * ld);
-    const float4 av = ld4(a + o * FS);
-    acc[0][0] = fmaf(wv.x, av.x, acc[0][0]); acc[0][1] = fmaf(wv.x, av.y, acc[0][1]);
-    acc[0][2] = fmaf(wv.x, av.z, acc[0][2]); acc[0][3] = fmaf(wv.x, av.w, acc[0][3]);
-    acc[1][0] = fmaf(wv.y, av.x, acc[1][0]); acc[1][1] = fmaf(wv.y, av.y, acc[1][1]);
-    acc[1][2] = fmaf(wv.y, av.z, acc[1][2]); acc[1][3] = fmaf(wv.y, av.w, acc[1][3]);
-    acc[2][0] = fmaf(wv.z, av.x, acc[2][0]); acc[2][1] = fmaf(wv.z, av.y, acc[2][1]);
-    acc[2][2] = fmaf(wv.z, av.z, acc[2][2]); acc[2][3] = fmaf(wv.z, av.w, acc[2][3]);
-    acc[3][0] = fmaf(wv.w, av.x, acc[3][0]); acc[3][1] = fmaf(wv.w, av.y, acc[3][1]);
-    acc[3][2] = fmaf(wv.w, av.z, acc[3][2]); acc[3][3] = fmaf(wv.w, av.w, acc[3][3]);
+    const FVec<FPL> av = FVec<FPL>::ld(a + o * FS);
+#pragma unroll
+    for (int f = 0; f < FPL; ++f) {
+      acc[0][f] = fmaf(wv.x, av.v[f], acc[0][f]);
+      acc[1][f] = fmaf(wv.y, av.v[f], acc[1][f]);
+      acc[2][f] = fmaf(wv.z, av.v[f], acc[2][f]);
+      acc[3][f] = fmaf(wv.w, av.v[f], acc[3][f]);
+    }
   }
 }
 
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
 
 // Outer-product accumulation for one layer:  dW[o][i] += sum_f X1[o][f] Z1[i][f] (+ X2[o][f] Z2[i][f]),
-// db[o] += sum_f X1[o][f].  Work item = 4 strided outputs x 4 strided inputs; results are added to the
-// CTA's fp64 partial vector `part` (torch parameter order).  Items [item0, item0+n_items) of this layer
-// are spread over the calling threads by the caller.
-__device__ __forceinline__ void outer_item(int item, int n_out, int n_in, const float* __restrict__ X1,
+// db[o] += sum_f X1[o][f].  A work item is a 4x4 block of weights (rows 4 ob .. 4 ob+3, columns 4 ib .. 4 ib+3)
+// handled by a QUAD of adjacent lanes: lane q of the quad takes the 16-byte frame chunks q, q+4, q+8, ... of every
+// row, the quad butterfly-reduces its 16 sums with shuffles, and each lane then adds one row of the block to the
+// CTA's fp64 partial vector `part_w` (torch parameter order) with a fire-and-forget reduction: every address has one
+// writer per phase and phases are ordered by CTA barriers, so the sum order -- and the result -- is deterministic.  `slot` = item * 4 + q; every lane of a warp must
+// call this together (slots past the end compute on clamped rows and write nothing).
+__device__ __forceinline__ void outer_quad(int slot, int n_items, int n_out, int n_in, const float* __restrict__ X1,
                                            const float* __restrict__ Z1, const float* __restrict__ X2,
                                            const float* __restrict__ Z2, int FS, int F, double* __restrict__ part_w,
                                            double* __restrict__ part_b) {
-  const int nob = (n_out + 3) >> 2, nib = (n_in + 3) >> 2;
+  const int q = slot & 3;
+  const int item = min(slot >> 2, n_items - 1);
+  const bool valid = (slot >> 2) < n_items;
+  const int nib = (n_in + 3) >> 2;
   const int ob = item / nib, ib = item - ob * nib;
   int orow[4], irow[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    orow[j] = min(ob + j * nob, n_out - 1);
-    irow[j] = min(ib + j * nib, n_in - 1);
+    orow[j] = min(4 * ob + j, n_out - 1);
+    irow[j] = min(4 * ib + j, n_in - 1);
   }
   float acc[4][4];
   float bacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -186,7 +223,8 @@ __device__ __forceinline__ void outer_item(int item, int n_out, int n_in, const 
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[j][i] = 0.0f;
-  for (int f = 0; f < F; f += 4) {
+#pragma unroll 2
+  for (int f = 4 * q; f < F; f += 16) {
     float4 x[4], z[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -213,16 +251,50 @@ __device__ __forceinline__ void outer_item(int item, int n_out, int n_in, const 
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int o = ob + j * nob;
-    if (o < n_out) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ii = ib + i * nib;
-        if (ii < n_in) part_w[o * n_in + ii] += (double)acc[j][i];
-      }
-      if (ib == 0 && part_b != nullptr) part_b[o] += (double)bacc[j];
+    for (int i = 0; i < 4; ++i) {
+      acc[j][i] += __shfl_xor_sync(0xffffffffu, acc[j][i], 1);
+      acc[j][i] += __shfl_xor_sync(0xffffffffu, acc[j][i], 2);
     }
+    bacc[j] += __shfl_xor_sync(0xffffffffu, bacc[j], 1);
+    bacc[j] += __shfl_xor_sync(0xffffffffu, bacc[j], 2);
   }
+  if (!valid) return;
+  // lane q of the quad owns row 4 ob + q of the block
+  float row[4] = {0.f, 0.f, 0.f, 0.f};
+  float brow = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j == q) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) row[i] = acc[j][i];
+      brow = bacc[j];
+    }
+  const int o = 4 * ob + q;
+  if (o < n_out) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int ii = 4 * ib + i;
+      if (ii < n_in) atomicAdd(&part_w[o * n_in + ii], (double)row[i]);   // result unused -> RED.ADD.F64, no stall
+    }
+    if (ib == 0 && part_b != nullptr) atomicAdd(&part_b[o], (double)brow);
+  }
+}
+
+// Run the outer-product items of one layer over the whole CTA.  `slot0` rotates the starting thread so that the
+// layers of one phase land on different warps; returns the next rotation.  Warp-uniform control flow.
+__device__ __forceinline__ int outer_layer(int slot0, int tid, int nt, int n_out, int n_in, const float* X1, const float* Z1,
+                                           const float* X2, const float* Z2, int FS, int F, double* part_w, double* part_b) {
+  const int n_items = ((n_out + 3) >> 2) * ((n_in + 3) >> 2);
+  const int n_slots = 4 * n_items;
+  // thread t handles slots (t - slot0) mod nt, + nt, ...; slot0 is kept a multiple of 32 so warps stay whole
+  const int rel = (tid - slot0 + nt) % nt;
+  for (int base = 0; base < n_slots; base += nt) {
+    const int warp_first = base + (rel & ~31);
+    if (warp_first >= n_slots) continue;
+    outer_quad(base + rel, n_items, n_out, n_in, X1, Z1, X2, Z2, FS, F, part_w, part_b);
+  }
+  return (slot0 + ((n_slots + 31) & ~31)) % nt;
 }
 
 // deterministic sum of per-CTA fp64 partial vectors: out[i] = sum_b part[b * stride + off + i], i < n

@@ -19,6 +19,31 @@
 
 namespace cvf {
 
+// Optional per-phase cycle counters (profiling builds only: -DCVF_PHASE_TIMERS, see profiles/phase_timing.py).
+#ifdef CVF_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[16];
+#define PT_DECL long long pt_last = clock64(); unsigned long long pt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+#define PT_MARK(slot)                          \
+  do {                                         \
+    if (threadIdx.x == 0) {                    \
+      const long long t_ = clock64();          \
+      pt_acc[slot] += t_ - pt_last;            \
+      pt_last = t_;                            \
+    }                                          \
+  } while (0)
+#define PT_FLUSH                                                                        \
+  do {                                                                                  \
+    if (threadIdx.x == 0)                                                               \
+      for (int i_ = 0; i_ < 12; ++i_) atomicAdd(&g_phase_cycles[i_], pt_acc[i_]);       \
+  } while (0)
+#else
+#define PT_DECL
+#define PT_MARK(slot)
+#define PT_FLUSH
+#endif
+// slots: 0 load, 1 preprocess, 2 forward, 3 reverse, 4 J phase, 5 tangent, 6 outer(tangent part), 7 second reverse,
+//        8 outer(all layers), 9 stats, 10 setup
+
 struct EigenPlan {
   NetPlan net;
   int k;
@@ -32,6 +57,7 @@ struct EigenPlan {
   const int32_t* feat;
   const float* diag;
   int pos_alias;   // features are exactly the positions of the used atoms in order: r rows alias the y rows
+  int used_identity;   // used_atoms = 0..n_atoms-1: a tile is one contiguous block of global memory
   // rows (units of FS floats from the row base)
   int row_w, row_one, row_seed, row_R, row_Kinv, row_y, row_D, row_Y, row_r, row_net;
   int a_row[kMaxLayers + 1], g_row[kMaxLayers + 1], t_row[kMaxLayers + 1], s_row[kMaxLayers + 1];  // relative to row_net
@@ -86,6 +112,7 @@ static int build_plan(const cvf_preproc* pp, const cvf_mlp* net, int k, EigenPla
     }
     P->n_atoms = pp->n_atoms, P->n_used = pp->n_used, P->n_align = pp->n_align, P->n_feat = pp->n_feat, P->d_r = pp->d_r;
     P->used_atoms = pp->used_atoms, P->align_used = pp->align_used, P->ref = pp->ref, P->feat = pp->feat;
+    P->used_identity = pp->used_identity ? 1 : 0;
     if (pp->positions_only && (pp->n_feat != pp->n_used || pp->d_r != 3 * pp->n_used)) {
       set_error("positions_only needs n_feat == n_used and d_r == 3 n_used");
       return CVF_E_ARG;
@@ -170,7 +197,7 @@ static int finish_plan(EigenPlan* P, bool pos_alias) {
       return CVF_E_UNSUPPORTED;
     }
   }
-  P->nthreads = 256;
+  P->nthreads = 384;
   return 0;
 }
 
@@ -394,15 +421,88 @@ __device__ float jphase_frame(const EigenPlan& P, float* rows, float* netrows, i
 }
 
 // ------------------------------------------------------------------------------------------------------
-template <bool GRAD>
-__global__ void __launch_bounds__(256, 1)
+// Bring one tile of frames into the [unit][frame] rows.  All loads of a thread are issued before the first store
+// (8 in flight per thread) and the NEXT tile of this CTA is prefetched into L2, so the HBM latency is paid once per
+// tile instead of once per element.
+__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ void load_tile(const EigenPlan& P, const float* __restrict__ x, long long B, long long f_base, float* rows,
+                          int tid, int nt) {
+  const int FS = P.FS, F = P.F;
+  const int fl = P.kind == 0 ? P.dim : 3 * P.n_atoms;        // floats per frame in global memory
+  const int row0 = P.kind == 0 ? P.row_r : P.row_Y;
+  const bool full = f_base + F <= B;
+  const float* src = x + (size_t)f_base * fl;
+  if ((P.kind == 0 || P.used_identity) && full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((F * fl) & 3) == 0) {
+    // contiguous tile: coalesced 16-byte loads, scattered into the transposed rows
+    const int nvec = (F * fl) >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(src);
+    for (int base = 0; base < nvec; base += 8 * nt) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = base + j * nt + tid;
+        if (idx < nvec) v[j] = __ldg(src4 + idx);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = base + j * nt + tid;
+        if (idx < nvec) {
+          const int e = 4 * idx;
+          int f = e / fl, u = e - f * fl;
+          const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            rows[(row0 + u) * FS + f] = vv[c];
+            if (++u == fl) u = 0, ++f;
+          }
+        }
+      }
+    }
+  } else {
+    const int nu = P.kind == 0 ? P.dim : 3 * P.n_used;
+    const int total = F * nu;
+    for (int base = 0; base < total; base += 8 * nt) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = base + j * nt + tid;
+        if (idx < total) {
+          const int f = idx / nu, u = idx - f * nu;
+          const long long fr = min(f_base + f, B - 1);
+          int col = u;
+          if (P.kind == 1) {
+            const int a = u / 3;
+            col = 3 * P.used_atoms[a] + (u - 3 * a);
+          }
+          v[j] = __ldg(x + (size_t)fr * fl + col);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = base + j * nt + tid;
+        if (idx < total) {
+          const int f = idx / nu, u = idx - f * nu;
+          rows[(row0 + u) * FS + f] = v[j];
+        }
+      }
+    }
+  }
+}
+
+template <bool GRAD, int FPL>
+__global__ void __launch_bounds__(384, 1)
 eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __restrict__ w, long long B,
              const float* __restrict__ params, float* __restrict__ y_io, const double* __restrict__ combine,
              double* __restrict__ partial) {
   extern __shared__ __align__(16) float smem[];
   const NetPlan& np = P.net;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int FS = P.FS, F = P.F, FB = P.FB, k = P.k;
+  const int FS = P.FS, F = P.F, k = P.k;
+  const int FB = F / FPL;      // lane-sized frame blocks per tile
+  typedef FVec<FPL> V;
   float* Wsm = smem + P.off_params;
   float* rows = smem + P.off_rows;
   double* comb = reinterpret_cast<double*>(smem + P.off_comb);
@@ -418,43 +518,42 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
     for (int i = tid; i < n_part; i += nt) part[i] = 0.0;
   }
   double stat_acc = 0.0;   // thread `tid` owns batch sum number `tid` (stats pass)
+  PT_DECL;
   __syncthreads();
+  PT_MARK(10);
   // combine vector layout: loss, obj, pen, eig[k], cvec[k], mean[k], cD[k], C2[k*k]
   const double* c_mean = comb + 3 + 2 * k;
   const double* c_cD = comb + 3 + 3 * k;
   const double* c_C2 = comb + 3 + 4 * k;
+  const int fl = P.kind == 0 ? P.dim : 3 * P.n_atoms;
 
   const long long n_tiles = (B + F - 1) / F;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long f_base = tile * F;
     // ---- load the tile: frames -> rows (transposed), weights, (pass 2) y of every network
-    if (P.kind == 0) {
-      const int d = P.dim;
-      for (int idx = tid; idx < F * d; idx += nt) {
-        const int f = idx / d, j = idx - f * d;
-        const long long fr = min(f_base + f, B - 1);
-        rows[(P.row_r + j) * FS + f] = x[fr * d + j];
-      }
-    } else {
-      const int nu3 = 3 * P.n_used;
-      const long long stride = 3LL * P.n_atoms;
-      for (int idx = tid; idx < F * nu3; idx += nt) {
-        const int f = idx / nu3, j = idx - f * nu3;
-        const int a = j / 3, c = j - 3 * a;
-        const long long fr = min(f_base + f, B - 1);
-        rows[(P.row_Y + j) * FS + f] = x[fr * stride + 3 * P.used_atoms[a] + c];
-      }
-    }
+    load_tile(P, x, B, f_base, rows, tid, nt);
     for (int f = tid; f < F; f += nt) {
       const long long fr = f_base + f;
       rows[P.row_w * FS + f] = fr < B ? w[fr] : 0.0f;
       if (GRAD)
         for (int i = 0; i < k; ++i) rows[(P.row_y + i) * FS + f] = y_io[(size_t)i * B + min(fr, B - 1)];
     }
+    if (tid == 0) {
+      const long long nxt = tile + gridDim.x;
+      if (nxt < n_tiles) {
+        const long long nb = nxt * F;
+        const long long nf = min((long long)F, B - nb);
+        const float* pn = x + (size_t)nb * fl;
+        const unsigned bytes = (unsigned)((nf * fl * 4) & ~15LL);
+        if (((reinterpret_cast<uintptr_t>(pn) & 15) == 0) && bytes > 0) prefetch_l2(pn, bytes);
+      }
+    }
     __syncthreads();
+    PT_MARK(0);
     if (P.kind == 1) {
       if (tid < F) preprocess_frame(P, rows, tid);
       __syncthreads();
+      PT_MARK(1);
     }
     float* netrows = rows + P.row_net * FS;
     const float* r_in = rows + P.row_r * FS;
@@ -470,21 +569,23 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
         const int items = ((nout + 3) >> 2) * FB;
         for (int it = tid; it < items; it += nt) {
           const int ob = it / FB, fb = it - ob * FB;
-          float acc[4][4];
-          tile_fwd(acc, Wn + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, 4 * fb);
+          float acc[4][FPL];
+          tile_fwd<FPL>(acc, Wn + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, FPL * fb);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int o = 4 * ob + j;
             if (o < nout) {
               const float b = Wn[np.b_off[l] + o];
-              float4 v = make_float4(acc[j][0] + b, acc[j][1] + b, acc[j][2] + b, acc[j][3] + b);
-              if (!last) v = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
-              st4(out + o * FS + 4 * fb, v);
+              V v;
+#pragma unroll
+              for (int f = 0; f < FPL; ++f) v.v[f] = last ? acc[j][f] + b : cvf_tanh(acc[j][f] + b);
+              v.st(out + o * FS + FPL * fb);
             }
           }
         }
         __syncthreads();
       }
+      PT_MARK(2);
       // ---- reverse: G_l = adjoint of z_l for the seed dy = 1;  u = dy/dr -> V rows
       for (int l = np.L - 1; l >= 0; --l) {
         const int nin = np.dims[l], nout = np.dims[l + 1];
@@ -494,23 +595,28 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
         const int items = ((nin + 3) >> 2) * FB;
         for (int it = tid; it < items; it += nt) {
           const int ib = it / FB, fb = it - ib * FB;
-          float acc[4][4];
-          tile_tr(acc, Wn + np.w_off[l], np.ld[l], 4 * ib, nout, in, FS, 4 * fb);
+          float acc[4][FPL];
+          tile_tr<FPL>(acc, Wn + np.w_off[l], np.ld[l], 4 * ib, nout, in, FS, FPL * fb);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = 4 * ib + j;
             if (i < nin) {
-              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+              V v;
               if (l > 0) {
-                const float4 a = ld4(A + i * FS + 4 * fb);
-                v = make_float4(v.x * (1.f - a.x * a.x), v.y * (1.f - a.y * a.y), v.z * (1.f - a.z * a.z), v.w * (1.f - a.w * a.w));
+                const V a = V::ld(A + i * FS + FPL * fb);
+#pragma unroll
+                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f] * (1.f - a.v[f] * a.v[f]);
+              } else {
+#pragma unroll
+                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f];
               }
-              st4(out + i * FS + 4 * fb, v);
+              v.st(out + i * FS + FPL * fb);
             }
           }
         }
         __syncthreads();
       }
+      PT_MARK(3);
       // ---- J phase (thread per frame): Dirichlet density; pass 2: tangent direction and output seed
       if (tid < F) {
         const int f = tid;
@@ -526,6 +632,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
         if (!GRAD) rows[(P.row_D + n) * FS + f] = D;
       }
       __syncthreads();
+      PT_MARK(4);
       if (GRAD) {
         double* pn = part + (size_t)n * np.n_params;
         // ---- tangent sweep along v:  T_l = (1-A_l^2) zdot_l,  S_l = -2 A_l G_l zdot_l   (zdot_l = W_l T_{l-1})
@@ -539,38 +646,37 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
           const int items = ((nout + 3) >> 2) * FB;
           for (int it = tid; it < items; it += nt) {
             const int ob = it / FB, fb = it - ob * FB;
-            float acc[4][4];
-            tile_fwd(acc, Wn + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, 4 * fb);
+            float acc[4][FPL];
+            tile_fwd<FPL>(acc, Wn + np.w_off[l], np.ld[l], 4 * ob, nout, nin, in, FS, FPL * fb);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int o = 4 * ob + j;
               if (o < nout) {
-                const float4 a = ld4(A + o * FS + 4 * fb), g = ld4(G + o * FS + 4 * fb);
-                st4(T + o * FS + 4 * fb, make_float4((1.f - a.x * a.x) * acc[j][0], (1.f - a.y * a.y) * acc[j][1],
-                                                     (1.f - a.z * a.z) * acc[j][2], (1.f - a.w * a.w) * acc[j][3]));
-                st4(S + o * FS + 4 * fb, make_float4(-2.f * a.x * g.x * acc[j][0], -2.f * a.y * g.y * acc[j][1],
-                                                     -2.f * a.z * g.z * acc[j][2], -2.f * a.w * g.w * acc[j][3]));
+                const V a = V::ld(A + o * FS + FPL * fb), g = V::ld(G + o * FS + FPL * fb);
+                V t, e;
+#pragma unroll
+                for (int f = 0; f < FPL; ++f) {
+                  t.v[f] = (1.f - a.v[f] * a.v[f]) * acc[j][f];
+                  e.v[f] = -2.f * a.v[f] * g.v[f] * acc[j][f];
+                }
+                t.st(T + o * FS + FPL * fb);
+                e.st(S + o * FS + FPL * fb);
               }
             }
           }
           if (l == 0) {
-            // tangent part of dW_1 while V is still alive: dW_1 += G_1 (x) v
-            __syncthreads();
-            const int n1 = ((np.dims[1] + 3) >> 2) * ((np.dims[0] + 3) >> 2);
-            const float* X = np.L > 1 ? netrows + P.g_row[1] * FS : rows + P.row_one * FS;
-            for (int it = tid; it < n1; it += nt)
-              outer_item(it, np.dims[1], np.dims[0], X, netrows + P.v_row * FS, nullptr, nullptr, FS, F, pn + np.gw_off[0], nullptr);
+            // tangent part of dW_1 while V is still alive: dW_1 += G_1 (x) v   (same inputs as the items above: no barrier)
+            outer_layer(0, tid, nt, np.dims[1], np.dims[0], netrows + P.g_row[1] * FS, netrows + P.v_row * FS, nullptr, nullptr,
+                        FS, F, pn + np.gw_off[0], nullptr);
           }
           __syncthreads();
         }
         if (np.L == 1) {
-          // single linear layer: only the tangent part exists besides the seed part below
-          const int n1 = ((np.dims[1] + 3) >> 2) * ((np.dims[0] + 3) >> 2);
-          for (int it = tid; it < n1; it += nt)
-            outer_item(it, np.dims[1], np.dims[0], rows + P.row_one * FS, netrows + P.v_row * FS, nullptr, nullptr, FS, F,
-                       pn + np.gw_off[0], nullptr);
+          outer_layer(0, tid, nt, np.dims[1], np.dims[0], rows + P.row_one * FS, netrows + P.v_row * FS, nullptr, nullptr, FS, F,
+                      pn + np.gw_off[0], nullptr);
           __syncthreads();
         }
+        PT_MARK(5);
         // ---- second reverse sweep: s_l (adjoint of z_l) in place of S_l;  s_L = seed
         for (int l = np.L - 1; l >= 1; --l) {
           const int nin = np.dims[l], nout = np.dims[l + 1];
@@ -580,40 +686,37 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
           const int items = ((nin + 3) >> 2) * FB;
           for (int it = tid; it < items; it += nt) {
             const int ib = it / FB, fb = it - ib * FB;
-            float acc[4][4];
-            tile_tr(acc, Wn + np.w_off[l], np.ld[l], 4 * ib, nout, in, FS, 4 * fb);
+            float acc[4][FPL];
+            tile_tr<FPL>(acc, Wn + np.w_off[l], np.ld[l], 4 * ib, nout, in, FS, FPL * fb);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int i = 4 * ib + j;
               if (i < nin) {
-                const float4 a = ld4(A + i * FS + 4 * fb);
-                const float4 e = ld4(S + i * FS + 4 * fb);
-                st4(S + i * FS + 4 * fb, make_float4(fmaf(acc[j][0], 1.f - a.x * a.x, e.x), fmaf(acc[j][1], 1.f - a.y * a.y, e.y),
-                                                     fmaf(acc[j][2], 1.f - a.z * a.z, e.z), fmaf(acc[j][3], 1.f - a.w * a.w, e.w)));
+                const V a = V::ld(A + i * FS + FPL * fb);
+                V e = V::ld(S + i * FS + FPL * fb);
+#pragma unroll
+                for (int f = 0; f < FPL; ++f) e.v[f] = fmaf(acc[j][f], 1.f - a.v[f] * a.v[f], e.v[f]);
+                e.st(S + i * FS + FPL * fb);
               }
             }
           }
           __syncthreads();
         }
+        PT_MARK(7);
         // ---- parameter gradients: dW_l += s_l (x) A_{l-1} + G_l (x) T_{l-1},  db_l += sum_f s_l
         {
-          int base = 0;
+          int rot = 0;
           for (int l = 0; l < np.L; ++l) {
-            const int nin = np.dims[l], nout = np.dims[l + 1];
-            const int n_it = ((nout + 3) >> 2) * ((nin + 3) >> 2);
             const bool last = l == np.L - 1;
             const float* X1 = last ? rows + P.row_seed * FS : netrows + P.s_row[l + 1] * FS;
             const float* Z1 = l == 0 ? r_in : netrows + P.a_row[l] * FS;
             const float* X2 = l == 0 ? nullptr : (last ? rows + P.row_one * FS : netrows + P.g_row[l + 1] * FS);
             const float* Z2 = l == 0 ? nullptr : netrows + P.t_row[l] * FS;
-            // spread the items of all layers over the CTA: item index space is the concatenation of the layers
-            for (int it = tid - base; it < n_it; it += nt) {
-              if (it >= 0) outer_item(it, nout, nin, X1, Z1, X2, Z2, FS, F, pn + np.gw_off[l], pn + np.gb_off[l]);
-            }
-            base = (base + n_it) % nt;
+            rot = outer_layer(rot, tid, nt, np.dims[l + 1], np.dims[l], X1, Z1, X2, Z2, FS, F, pn + np.gw_off[l], pn + np.gb_off[l]);
           }
         }
         __syncthreads();
+        PT_MARK(8);
       }
     }  // networks
 
@@ -626,10 +729,10 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
           for (int i = 0; i < k; ++i) y_io[(size_t)i * B + fr] = rows[(P.row_y + i) * FS + f];
       }
       const int lane = tid & 31, warp = tid >> 5, nwarp_f = F / 32;
-      for (int s = 0; s < ns; ++s) {
-        double v = 0.0;
-        if (tid < F) {
-          const double wf = rows[P.row_w * FS + tid];
+      if (tid < F) {
+        const double wf = rows[P.row_w * FS + tid];
+        for (int s = 0; s < ns; ++s) {
+          double v;
           if (s == 0) v = wf;
           else if (s < 1 + k) v = wf * rows[(P.row_y + s - 1) * FS + tid];
           else if (s < 1 + k + k * k) {
@@ -648,8 +751,10 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
         stat_acc += v;
       }
       __syncthreads();
+      PT_MARK(9);
     }
   }  // tiles
+  PT_FLUSH;
   if (!GRAD && tid < P.n_stats) part[tid] = stat_acc;
 }
 
@@ -733,11 +838,11 @@ static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, co
     return CVF_E_WORKSPACE;
   }
   if (grad) {
-    CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    eigen_kernel<true><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
+    CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    eigen_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
   } else {
-    CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    eigen_kernel<false><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
+    CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
+    eigen_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
   }
   CVF_CUDA(cudaGetLastError());
   reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 0, n_part, out);
@@ -748,6 +853,17 @@ static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, co
 }  // namespace cvf
 
 using namespace cvf;
+
+#ifdef CVF_PHASE_TIMERS
+extern "C" int cvf_debug_phase_cycles(unsigned long long* out16, int reset) {
+  cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int32_t cvf_eigen_num_stats(int32_t k) { return 1 + 2 * k + k * k; }
 extern "C" int32_t cvf_eigen_num_combine(int32_t k) { return 3 + 4 * k + k * k; }

@@ -56,6 +56,7 @@ typedef struct cvf_preproc {
   int32_t d_r;                /* output dimension of r */
   int32_t positions_only;     /* 1: feat is exactly POSITION of used atom 0,1,..,n_used-1 (d_r = 3 n_used), so
                                  r is the aligned frame itself and the kernels skip the feature copy */
+  int32_t used_identity;      /* 1: used_atoms is 0,1,..,n_atoms-1 (every atom is read, in order) */
   const float* diag;          /* diag_coeff (core.py:348-354) gathered to [n_used*3] (kind 1) or [dim] (kind 0); NULL = ones */
 } cvf_preproc;
 
