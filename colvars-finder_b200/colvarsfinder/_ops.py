@@ -213,18 +213,36 @@ class EigenContext:
         self.n_stats = L.cvf_eigen_num_stats(self.k)
         self.n_comb = L.cvf_eigen_num_combine(self.k)
         self.n_per_net = int(L.cvf_mlp_param_count(C.byref(self.mlp)))
-        self.ws_bytes = int(L.cvf_eigen_workspace_bytes(self.spec.struct_ptr(), C.byref(self.mlp), self.k))
-        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.fast_path = bool(L.cvf_eigen_path(self.spec.struct_ptr(), C.byref(self.mlp), self.k) == 1)
+        self.ws_bytes, self.ws_frames, self.workspace = 0, 0, None
+        self._scratch_key = None
+
+    def _workspace_for(self, B):
+        """Scratch of the step kernels, grown to the largest batch seen (PyTorch's caching allocator owns it)."""
+        if self.workspace is None or B > self.ws_frames:
+            need = int(_lib.lib().cvf_eigen_workspace_bytes(self.spec.struct_ptr(), C.byref(self.mlp), self.k, B))
+            if need <= 0:
+                raise RuntimeError("cvf_eigen_workspace_bytes: unsupported configuration")
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.ws_bytes, self.ws_frames = need, B
+            self._scratch_key = None
+        return self.workspace.data_ptr()
+
+    def _key(self, X, weight):
+        return (X.data_ptr(), X.shape[0], X._version, weight.data_ptr(), weight._version, self.flat.flat._version)
 
     def stats(self, X, weight):
         """Pass 1 on this rank's frames -> (y [k,B] fp32, stats fp64)."""
         L = _lib.lib()
         B = X.shape[0]
+        ws = self._workspace_for(B)
         y = torch.empty(self.k, B, dtype=torch.float32, device=self.device)
         stats = torch.empty(self.n_stats, dtype=torch.float64, device=self.device)
         _lib.check(L.cvf_eigen_stats(X.data_ptr(), weight.data_ptr(), B, self.spec.struct_ptr(), C.byref(self.mlp), self.k,
-                                     self.flat.flat.data_ptr(), y.data_ptr(), stats.data_ptr(), self.workspace.data_ptr(),
-                                     self.ws_bytes, _stream()), "cvf_eigen_stats")
+                                     self.flat.flat.data_ptr(), y.data_ptr(), stats.data_ptr(), ws, self.ws_bytes, _stream()),
+                   "cvf_eigen_stats")
+        self._scratch_key = self._key(X, weight)
         return y, stats
 
     def combine(self, stats):
@@ -236,10 +254,13 @@ class EigenContext:
     def grads(self, X, weight, y, comb):
         """Pass 2 on this rank's frames -> fp64 gradient sums [k * n_per_net]."""
         g = torch.empty(self.k * self.n_per_net, dtype=torch.float64, device=self.device)
+        ws = self._workspace_for(X.shape[0])
+        # the scratch still holds pass 1's intermediates iff the last stats() call saw these very tensors and parameters
+        valid = 1 if self._scratch_key is not None and self._scratch_key == self._key(X, weight) else 0
         _lib.check(_lib.lib().cvf_eigen_grad(X.data_ptr(), weight.data_ptr(), X.shape[0], self.spec.struct_ptr(),
                                              C.byref(self.mlp), self.k, self.flat.flat.data_ptr(), y.data_ptr(),
-                                             comb.data_ptr(), g.data_ptr(), self.workspace.data_ptr(), self.ws_bytes,
-                                             _stream()), "cvf_eigen_grad")
+                                             comb.data_ptr(), g.data_ptr(), ws, self.ws_bytes, valid, _stream()),
+                   "cvf_eigen_grad")
         return g
 
 

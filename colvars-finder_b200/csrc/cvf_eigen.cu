@@ -19,6 +19,16 @@
 
 namespace cvf {
 
+// cvf_eigen_fast.cu: thread-private / FFMA2 path for the common network shape
+bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k);
+size_t fast_eigen_workspace_bytes(const cvf_preproc* pp, const NetPlan& np, int k, long long B);
+int fast_eigen_stats(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
+                     const float* params, float* y_out, double* stats_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int fast_eigen_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
+                    const float* params, const double* combine, double* grad_out, void* workspace, size_t ws_bytes,
+                    int scratch_valid, cudaStream_t stream);
+static int g_eigen_path = 0;   // 0: fast path whenever it applies, 1: always the general row-engine kernels
+
 // Optional per-phase cycle counters (profiling builds only: -DCVF_PHASE_TIMERS, see profiles/phase_timing.py).
 #ifdef CVF_PHASE_TIMERS
 __device__ unsigned long long g_phase_cycles[16];
@@ -818,7 +828,7 @@ __global__ void eigen_combine_kernel(const double* __restrict__ S, int k, double
 
 static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
                         int k, const float* params, float* y_io, const double* combine, double* out, void* workspace,
-                        size_t ws_bytes, void* stream_) {
+                        size_t ws_bytes, int scratch_valid, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EigenPlan P;
   int e = build_plan(pp, net, k, &P);
@@ -826,6 +836,10 @@ static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, co
   if (!x || !w || !params || !y_io || !out || !workspace || B < 1 || (grad && !combine)) {
     set_error("null pointer or empty batch");
     return CVF_E_ARG;
+  }
+  if (g_eigen_path == 0 && fast_eigen_supported(pp, P.net, k)) {
+    if (grad) return fast_eigen_grad(pp, P.net, k, x, w, B, params, combine, out, workspace, ws_bytes, scratch_valid, stream);
+    return fast_eigen_stats(pp, P.net, k, x, w, B, params, y_io, out, workspace, ws_bytes, stream);
   }
   e = finish_plan(&P, pp->kind == 1 && pp->positions_only != 0);   // largest tile that fits
   if (e) return e;
@@ -868,20 +882,39 @@ extern "C" int cvf_debug_phase_cycles(unsigned long long* out16, int reset) {
 extern "C" int32_t cvf_eigen_num_stats(int32_t k) { return 1 + 2 * k + k * k; }
 extern "C" int32_t cvf_eigen_num_combine(int32_t k) { return 3 + 4 * k + k * k; }
 
-extern "C" size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k) {
+extern "C" size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k, int64_t B) {
   NetPlan np;
-  (void)pp;
-  if (make_net_plan(net, &np) || k < 1 || k > kMaxK) return 0;
+  if (!pp || make_net_plan(net, &np) || k < 1 || k > kMaxK || B < 1) return 0;
   size_t n = (size_t)k * np.n_params;
   const size_t ns = (size_t)cvf_eigen_num_stats(k);
   if (ns > n) n = ns;
-  return n * sizeof(double) * (size_t)sm_count();
+  size_t bytes = n * sizeof(double) * (size_t)sm_count();
+  if (fast_eigen_supported(pp, np, k)) {
+    const size_t fb = fast_eigen_workspace_bytes(pp, np, k, B);
+    if (fb > bytes) bytes = fb;
+  }
+  return bytes;
+}
+
+extern "C" int cvf_eigen_set_path(int32_t mode) {
+  if (mode != 0 && mode != 1) {
+    set_error("cvf_eigen_set_path: mode must be 0 (auto) or 1 (general kernels)");
+    return CVF_E_ARG;
+  }
+  g_eigen_path = mode;
+  return 0;
+}
+
+extern "C" int cvf_eigen_path(const cvf_preproc* pp, const cvf_mlp* net, int32_t k) {
+  NetPlan np;
+  if (!pp || make_net_plan(net, &np)) return CVF_E_ARG;
+  return g_eigen_path == 0 && fast_eigen_supported(pp, np, k) ? 1 : 0;
 }
 
 extern "C" int cvf_eigen_stats(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net, int32_t k,
                                const float* params, float* y_out, double* stats_out, void* workspace, size_t workspace_bytes,
                                void* stream) {
-  return eigen_launch(false, x, w, B, pp, net, k, params, y_out, nullptr, stats_out, workspace, workspace_bytes, stream);
+  return eigen_launch(false, x, w, B, pp, net, k, params, y_out, nullptr, stats_out, workspace, workspace_bytes, 0, stream);
 }
 
 extern "C" int cvf_eigen_combine(const double* stats, int32_t k, double alpha, const double* eig_w, double beta, int32_t sort,
@@ -900,7 +933,7 @@ extern "C" int cvf_eigen_combine(const double* stats, int32_t k, double alpha, c
 
 extern "C" int cvf_eigen_grad(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net, int32_t k,
                               const float* params, const float* y_in, const double* combine, double* grad_out, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+                              size_t workspace_bytes, int32_t scratch_valid, void* stream) {
   return eigen_launch(true, x, w, B, pp, net, k, params, const_cast<float*>(y_in), combine, grad_out, workspace, workspace_bytes,
-                      stream);
+                      scratch_valid, stream);
 }

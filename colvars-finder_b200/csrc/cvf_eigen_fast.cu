@@ -1,0 +1,1029 @@
+// cvf_eigen_fast.cu -- the EigenFunctionTask step for the common network shape (every hidden layer H wide, H % 4 == 0)
+// on Identity or aligned-position pre-processing, organised around what the B200 SM can sustain (profiles/micro/mv_probe.cu):
+//
+//   * a 128-bit shared-memory load costs two cycles of the SM's shared-memory pipe even when every lane reads the same
+//     address, so a weight has to be used at least twice per load; packed FFMA2 (fma.rn.f32x2) halves the issue slots
+//     of the FMAs so the loads ride along.  A thread that owns TWO input vectors (two frames, or the primal and the
+//     tangent of one frame) and all H outputs reaches ~100 of the 128 fp32 FMA/clk/SM; anything with less reuse is
+//     shared-memory bound at <= 64;
+//   * therefore every dense layer is evaluated THREAD-PRIVATELY (weights broadcast from shared memory, activations in
+//     registers, no barrier between layers), and the only cross-frame work -- the weight-gradient outer products --
+//     is a warp-level register-tiled product over the 32 frames the warp has just processed.
+//
+// Per mini-batch (reference file:line under colvarsfinder/):
+//   prep   : Kabsch alignment of every frame (pp_layer, core.py:403), written frame-minor ("SoA": row = coordinate,
+//            column = frame) with the 3x3 K^-1 of the alignment Jacobian;  Identity pp: a transpose
+//   pass 1 : y = model(r) (core.py:403), u = grad_r y (core.py:424) by a reverse sweep, Dirichlet density
+//            D = |J_r^T u|^2 (core.py:426) and the four 3-vectors of the alignment Jacobian applied to u;  2 frames / thread
+//   stats  : fp64 batch sums (core.py:406-410,426)
+//   pass 2 : d loss / d theta (core.py:517): primal + tangent forward sweep fused (the tangent direction is
+//            v = J_r J_r^T u), reverse sweep of (G, s) fused, outer products per layer;  1 frame / lane
+#include <math.h>
+#include <string.h>
+
+#include "cvf_common.cuh"
+#include "cvf_math.cuh"
+
+namespace cvf {
+namespace fast {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)), "l"(*reinterpret_cast<u64*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 dup(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register staging, any number in flight
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// warp prefetch of `nrows` row segments (one 128-byte line each: 32 frames of a frame-minor row)
+__device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long long Bp, int lane) {
+  for (int r = lane; r < nrows; r += 32) prefetch_l2_line(base + (size_t)r * Bp);
+}
+
+constexpr int kRowPad = 36;   // floats per 32-frame row of the pass-2 operand rows (16-byte aligned, bank-group skew 1 per row)
+constexpr int kP1Frames = 512, kP1Threads = 256;
+constexpr int kP2Threads = 128, kP2Warps = 4;
+
+// Shared-memory image of one network (floats; every block 16-byte aligned because H % 4 == 0 and d_rp % 12 == 0):
+//   W1T [d_rp][H] (k-major)  b1 [H]  { WlT [H][H]  bl [H] } l=2..NH   Wout [H]  bout [4]   { Wl [H][H] natural } l=2..NH
+//   -- pass 2 reads up to here --   W1 [H][d_rp] natural
+template <int H, int NH>
+struct Img {
+  __host__ __device__ static int b1(int drp) { return drp * H; }
+  __host__ __device__ static int wt(int drp, int l) { return drp * H + H + (l - 2) * (H * H + H); }   // l = 2..NH
+  __host__ __device__ static int bl(int drp, int l) { return wt(drp, l) + H * H; }
+  __host__ __device__ static int wout(int drp) { return drp * H + H + (NH - 1) * (H * H + H); }
+  __host__ __device__ static int bout(int drp) { return wout(drp) + H; }
+  __host__ __device__ static int wn(int drp, int l) { return bout(drp) + 4 + (l - 2) * H * H; }        // l = 2..NH
+  __host__ __device__ static int p2_floats(int drp) { return bout(drp) + 4 + (NH - 1) * H * H; }
+  __host__ __device__ static int w1n(int drp) { return p2_floats(drp); }
+  __host__ __device__ static int floats(int drp) { return p2_floats(drp) + H * drp; }
+};
+
+struct FastPlan {
+  int k, d_r, d_rp, kind;        // kind 0: identity on [B,d_r];  1: aligned positions of all n_atoms atoms (d_r = 3 n_atoms)
+  int n_atoms, n_align;
+  int img_floats, img2_floats, geo_floats, n_params;
+  int gw_off[kMaxLayers], gb_off[kMaxLayers];   // torch-order offsets inside one network's parameters
+  long long B, Bp;
+  const int32_t* align_idx;      // [n_align] atom index
+  const float* ref;              // [n_align][3] centred
+  const float* diag;             // kind 0: [d_r] or null
+  float* img;                    // [k][img_floats] followed by geo [geo_floats]
+  float* Y;                      // [d_rp][Bp]
+  float* Kinv;                   // [6][Bp]
+  float* U;                      // [k][d_rp][Bp]
+  float* JQ;                     // [k][12][Bp]   gm, q, dc, om
+  float* Dq;                     // [k][Bp]
+  float* Ys;                     // [k][Bp]
+  double* part;                  // per-CTA / per-warp partial sums
+};
+
+// geo block (floats): kind 1: refA [d_rp] (reference position of the atom a coordinate belongs to, 0 if not aligned),
+// inA [d_rp] (1 if aligned), Iref [6] (sum |ref|^2 I - ref ref^T), nA, 1/nA;   kind 0: diag [d_rp], unused [d_rp], ...
+__host__ __device__ inline int geo_floats_of(int drp) { return 2 * drp + 8; }
+
+// ------------------------------------------------------------------------------------------------ pack
+template <int H, int NH>
+__global__ void pack_kernel(const FastPlan P, const float* __restrict__ params) {
+  const int drp = P.d_rp, d_r = P.d_r;
+  typedef Img<H, NH> I;
+  if (blockIdx.x == (unsigned)P.k) {   // geometry block
+    float* g = P.img + (size_t)P.k * P.img_floats;
+    for (int i = threadIdx.x; i < P.geo_floats; i += blockDim.x) g[i] = 0.0f;
+    __syncthreads();
+    if (P.kind == 0) {
+      for (int i = threadIdx.x; i < d_r; i += blockDim.x) g[i] = P.diag ? P.diag[i] : 1.0f;
+    } else {
+      for (int j = threadIdx.x; j < P.n_align; j += blockDim.x) {
+        const int a = P.align_idx[j];
+        for (int c = 0; c < 3; ++c) g[3 * a + c] = P.ref[3 * j + c], g[drp + 3 * a + c] = 1.0f;
+      }
+      if (threadIdx.x == 0) {
+        double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+        for (int j = 0; j < P.n_align; ++j) {
+          const double x = P.ref[3 * j], y = P.ref[3 * j + 1], z = P.ref[3 * j + 2], n2 = x * x + y * y + z * z;
+          xx += n2 - x * x, yy += n2 - y * y, zz += n2 - z * z, xy -= x * y, xz -= x * z, yz -= y * z;
+        }
+        float* t = g + 2 * drp;
+        t[0] = (float)xx, t[1] = (float)xy, t[2] = (float)xz, t[3] = (float)yy, t[4] = (float)yz, t[5] = (float)zz;
+        t[6] = (float)P.n_align, t[7] = 1.0f / (float)P.n_align;
+      }
+    }
+    return;
+  }
+  const float* src = params + (size_t)blockIdx.x * P.n_params;
+  float* dst = P.img + (size_t)blockIdx.x * P.img_floats;
+  for (int i = threadIdx.x; i < P.img_floats; i += blockDim.x) {
+    float v = 0.0f;
+    if (i < I::b1(drp)) {
+      const int kk = i / H, o = i - kk * H;
+      if (kk < d_r) v = src[P.gw_off[0] + o * d_r + kk];
+    } else if (i < I::b1(drp) + H) {
+      v = src[P.gb_off[0] + i - I::b1(drp)];
+    } else if (i < I::wout(drp)) {
+      const int r = i - (I::b1(drp) + H), l = 2 + r / (H * H + H), q = r - (l - 2) * (H * H + H);
+      if (q < H * H) {
+        const int kk = q / H, o = q - kk * H;
+        v = src[P.gw_off[l - 1] + o * H + kk];
+      } else {
+        v = src[P.gb_off[l - 1] + q - H * H];
+      }
+    } else if (i < I::bout(drp)) {
+      v = src[P.gw_off[NH] + i - I::wout(drp)];
+    } else if (i < I::bout(drp) + 4) {
+      if (i == I::bout(drp)) v = src[P.gb_off[NH]];
+    } else if (i < I::p2_floats(drp)) {
+      const int r = i - (I::bout(drp) + 4), l = 2 + r / (H * H), q = r - (l - 2) * H * H;
+      v = src[P.gw_off[l - 1] + q];
+    } else {
+      const int r = i - I::w1n(drp), o = r / drp, kk = r - o * drp;
+      if (kk < d_r) v = src[P.gw_off[0] + o * d_r + kk];
+    }
+    dst[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ prep
+// kind 1: Kabsch per frame (thread per frame on a coalesced shared-memory tile), frame-minor output.
+__global__ void __launch_bounds__(128) prep_align_kernel(const FastPlan P, const float* __restrict__ x) {
+  extern __shared__ __align__(16) float st[];
+  const int tid = threadIdx.x;
+  const int fl = 3 * P.n_atoms, S = fl | 1;   // odd stride: conflict-free column access
+  float* kin = st + 128 * S;                  // [6][128]
+  const long long n_tiles = P.Bp / 128;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long f0 = tile * 128;
+    if (f0 + 128 <= P.B) {
+      const float* src = x + (size_t)f0 * fl;
+      for (int i = tid; i < 128 * fl; i += 128) {
+        const int f = i / fl;
+        st[f * S + (i - f * fl)] = __ldg(src + i);
+      }
+    } else {
+      for (int i = tid; i < 128 * fl; i += 128) {
+        const int f = i / fl;
+        const long long fr = min(f0 + f, P.B - 1);   // padding frames repeat the last frame (their weight is 0)
+        st[f * S + (i - f * fl)] = __ldg(x + (size_t)fr * fl + (i - f * fl));
+      }
+    }
+    __syncthreads();
+    {
+      float* fr = st + tid * S;
+      double cx = 0, cy = 0, cz = 0;
+      for (int a = 0; a < P.n_align; ++a) {
+        const float* p = fr + 3 * P.align_idx[a];
+        cx += p[0], cy += p[1], cz += p[2];
+      }
+      const double inv = 1.0 / P.n_align;
+      cx *= inv, cy *= inv, cz *= inv;
+      double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int a = 0; a < P.n_align; ++a) {
+        const float* p = fr + 3 * P.align_idx[a];
+        const double px = p[0] - cx, py = p[1] - cy, pz = p[2] - cz;
+        const double rx = P.ref[3 * a], ry = P.ref[3 * a + 1], rz = P.ref[3 * a + 2];
+        Hm[0] += px * rx, Hm[1] += px * ry, Hm[2] += px * rz;
+        Hm[3] += py * rx, Hm[4] += py * ry, Hm[5] += py * rz;
+        Hm[6] += pz * rx, Hm[7] += pz * ry, Hm[8] += pz * rz;
+      }
+      float R[9], Ki[6];
+      double Rd[9];
+      cvf_rotation(Hm, R, Ki, Rd);
+      for (int a = 0; a < P.n_atoms; ++a) {
+        float* p = fr + 3 * a;
+        const cvf_v3 q = cvf_transform(p[0], p[1], p[2], cx, cy, cz, Rd);
+        p[0] = q.x, p[1] = q.y, p[2] = q.z;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) kin[i * 128 + tid] = Ki[i];
+    }
+    __syncthreads();
+    for (int r = 0; r < P.d_rp; ++r) P.Y[(size_t)r * P.Bp + f0 + tid] = r < fl ? st[tid * S + r] : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) P.Kinv[(size_t)i * P.Bp + f0 + tid] = kin[i * 128 + tid];
+    __syncthreads();
+  }
+}
+
+// kind 0: [B][d] -> [d_rp][Bp]
+__global__ void __launch_bounds__(256) prep_transpose_kernel(const FastPlan P, const float* __restrict__ x) {
+  const long long n = P.Bp;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long long)gridDim.x * blockDim.x) {
+    const long long fr = min(f, P.B - 1);
+    for (int r = 0; r < P.d_rp; ++r) P.Y[(size_t)r * P.Bp + f] = r < P.d_r ? __ldg(x + (size_t)fr * P.d_r + r) : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 1
+// One CTA per SM, 256 threads, tiles of 512 frames; thread t owns frames 2t, 2t+1 of the tile.
+template <int H, int NH>
+__global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, float* __restrict__ y_out) {
+  extern __shared__ __align__(16) float sm[];
+  typedef Img<H, NH> I;
+  constexpr int F = kP1Frames, HP = H / 2;
+  const int tid = threadIdx.x, drp = P.d_rp, d_r = P.d_r, k = P.k;
+  float* wsm = sm;
+  float* geo = wsm + k * P.img_floats;
+  float* tile = geo + P.geo_floats;   // [drp][F]
+  for (int i = tid; i < k * P.img_floats + P.geo_floats; i += kP1Threads) sm[i] = P.img[i];
+  const long long n_tiles = P.Bp / F;
+  const int c0 = 2 * tid;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long f0 = t * F;
+    __syncthreads();
+    {
+      const int nv = drp * (F / 4);
+      for (int i = tid; i < nv; i += kP1Threads) {
+        const int r = i / (F / 4), c4 = i - r * (F / 4);
+        st4(tile + r * F + 4 * c4, __ldg(reinterpret_cast<const float4*>(P.Y + (size_t)r * P.Bp + f0) + c4));
+      }
+    }
+    __syncthreads();
+    for (int n = 0; n < k; ++n) {
+      const float* W = wsm + n * P.img_floats;
+      float om[NH][2][H];   // 1 - A_l^2
+      float a[2][H];        // current activations
+      // ---- layer 1: z = W1 r + b1 (nn.py:52-57), both frames share every weight load
+      {
+        float2 z[2][HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) z[0][j] = z[1][j] = lds2(W + I::b1(drp) + 2 * j);
+#pragma unroll 2
+        for (int kk = 0; kk < d_r; ++kk) {
+          const float2 x = lds2(tile + kk * F + c0);
+          const float2 x0 = dup(x.x), x1 = dup(x.y);
+          const float* wr = W + kk * H;
+#pragma unroll
+          for (int q = 0; q < H / 4; ++q) {
+            const float4 wv = ld4(wr + 4 * q);
+            z[0][2 * q] = ffma2(make_float2(wv.x, wv.y), x0, z[0][2 * q]);
+            z[0][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[0][2 * q + 1]);
+            z[1][2 * q] = ffma2(make_float2(wv.x, wv.y), x1, z[1][2 * q]);
+            z[1][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), x1, z[1][2 * q + 1]);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int j = 0; j < HP; ++j) {
+            a[f][2 * j] = cvf_tanh(z[f][j].x), a[f][2 * j + 1] = cvf_tanh(z[f][j].y);
+            om[0][f][2 * j] = fmaf(-a[f][2 * j], a[f][2 * j], 1.0f);
+            om[0][f][2 * j + 1] = fmaf(-a[f][2 * j + 1], a[f][2 * j + 1], 1.0f);
+          }
+      }
+      // ---- hidden layers 2..NH
+#pragma unroll
+      for (int l = 2; l <= NH; ++l) {
+        float2 z[2][HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) z[0][j] = z[1][j] = lds2(W + I::bl(drp, l) + 2 * j);
+        const float* wt = W + I::wt(drp, l);
+#pragma unroll
+        for (int kk = 0; kk < H; ++kk) {
+          const float2 x0 = dup(a[0][kk]), x1 = dup(a[1][kk]);
+#pragma unroll
+          for (int q = 0; q < H / 4; ++q) {
+            const float4 wv = ld4(wt + kk * H + 4 * q);
+            z[0][2 * q] = ffma2(make_float2(wv.x, wv.y), x0, z[0][2 * q]);
+            z[0][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[0][2 * q + 1]);
+            z[1][2 * q] = ffma2(make_float2(wv.x, wv.y), x1, z[1][2 * q]);
+            z[1][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), x1, z[1][2 * q + 1]);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int j = 0; j < HP; ++j) {
+            a[f][2 * j] = cvf_tanh(z[f][j].x), a[f][2 * j + 1] = cvf_tanh(z[f][j].y);
+            om[l - 1][f][2 * j] = fmaf(-a[f][2 * j], a[f][2 * j], 1.0f);
+            om[l - 1][f][2 * j + 1] = fmaf(-a[f][2 * j + 1], a[f][2 * j + 1], 1.0f);
+          }
+      }
+      // ---- output y and the reverse sweep G_l = (1 - A_l^2) .* (W_{l+1}^T G_{l+1}),  G_{NH} seed = Wout
+      float yv[2] = {W[I::bout(drp)], W[I::bout(drp)]};
+      float g[2][H];
+#pragma unroll
+      for (int q = 0; q < H / 4; ++q) {
+        const float4 wv = ld4(W + I::wout(drp) + 4 * q);
+        const float wo[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            yv[f] = fmaf(wo[e], a[f][4 * q + e], yv[f]);
+            g[f][4 * q + e] = wo[e] * om[NH - 1][f][4 * q + e];
+          }
+      }
+#pragma unroll
+      for (int l = NH; l >= 2; --l) {
+        float2 h[2][HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) h[0][j] = h[1][j] = make_float2(0.f, 0.f);
+        const float* wn = W + I::wn(drp, l);
+#pragma unroll
+        for (int o = 0; o < H; ++o) {
+          const float2 g0 = dup(g[0][o]), g1 = dup(g[1][o]);
+#pragma unroll
+          for (int q = 0; q < H / 4; ++q) {
+            const float4 wv = ld4(wn + o * H + 4 * q);
+            h[0][2 * q] = ffma2(make_float2(wv.x, wv.y), g0, h[0][2 * q]);
+            h[0][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), g0, h[0][2 * q + 1]);
+            h[1][2 * q] = ffma2(make_float2(wv.x, wv.y), g1, h[1][2 * q]);
+            h[1][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), g1, h[1][2 * q + 1]);
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int j = 0; j < HP; ++j) {
+            g[f][2 * j] = h[f][j].x * om[l - 2][f][2 * j];
+            g[f][2 * j + 1] = h[f][j].y * om[l - 2][f][2 * j + 1];
+          }
+      }
+      // ---- u = W1^T G_1 in chunks of 12 coordinates (4 atoms), streamed to global memory and into the J sums
+      float S2[2] = {0.f, 0.f};
+      cvf_v3 gs[2], gsA[2], tau[2], kap[2];
+#pragma unroll
+      for (int f = 0; f < 2; ++f) gs[f] = gsA[f] = tau[f] = kap[f] = v3(0.f, 0.f, 0.f);
+      float* Un = P.U + ((size_t)n * drp) * P.Bp + f0 + c0;
+      const float* w1n = W + I::w1n(drp);
+      float2 kiv[6];   // K^-1 of both frames, in flight while u is computed
+      if (P.kind == 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) kiv[i] = __ldg(reinterpret_cast<const float2*>(P.Kinv + (size_t)i * P.Bp + f0 + c0));
+      }
+      for (int c = 0; c < drp / 12; ++c) {
+        float2 acc[2][6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) acc[0][p] = acc[1][p] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int o = 0; o < H; ++o) {
+          const float2 g0 = dup(g[0][o]), g1 = dup(g[1][o]);
+          const float* wr = w1n + o * drp + 12 * c;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const float4 wv = ld4(wr + 4 * q);
+            acc[0][2 * q] = ffma2(make_float2(wv.x, wv.y), g0, acc[0][2 * q]);
+            acc[0][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), g0, acc[0][2 * q + 1]);
+            acc[1][2 * q] = ffma2(make_float2(wv.x, wv.y), g1, acc[1][2 * q]);
+            acc[1][2 * q + 1] = ffma2(make_float2(wv.z, wv.w), g1, acc[1][2 * q + 1]);
+          }
+        }
+        float uu[2][12];
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int p = 0; p < 6; ++p) uu[f][2 * p] = acc[f][p].x, uu[f][2 * p + 1] = acc[f][p].y;
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+          *reinterpret_cast<float2*>(Un + (size_t)(12 * c + j) * P.Bp) = make_float2(uu[0][j], uu[1][j]);
+        if (P.kind == 1) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int r = 12 * c + 3 * m;
+            const float2 yx = lds2(tile + r * F + c0), yy = lds2(tile + (r + 1) * F + c0), yz = lds2(tile + (r + 2) * F + c0);
+            const cvf_v3 rf = v3(geo[r], geo[r + 1], geo[r + 2]);
+            const float ina = geo[drp + r];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              const cvf_v3 gg = v3(uu[f][3 * m], uu[f][3 * m + 1], uu[f][3 * m + 2]);
+              const cvf_v3 yv3 = f == 0 ? v3(yx.x, yy.x, yz.x) : v3(yx.y, yy.y, yz.y);
+              S2[f] += dot(gg, gg);
+              gs[f] = gs[f] + gg;
+              gsA[f] = gsA[f] + ina * gg;
+              tau[f] = tau[f] + cross(gg, yv3);
+              kap[f] = kap[f] + cross(gg, rf);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) {
+            const float aj = geo[12 * c + j];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) S2[f] = fmaf(aj * uu[f][j], uu[f][j], S2[f]);
+          }
+        }
+      }
+      // ---- Dirichlet density and the alignment-Jacobian vectors (derivation in DESIGN.md)
+      float Dv[2];
+      if (P.kind == 1) {
+        const float* ir = geo + 2 * drp;
+        const float nA = ir[6], inA = ir[7];
+        float* jq = P.JQ + ((size_t)n * 12) * P.Bp + f0 + c0;
+        float out[2][12];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          float Ki[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) Ki[i] = f == 0 ? kiv[i].x : kiv[i].y;
+          const cvf_v3 gm = inA * gs[f];
+          const cvf_v3 q = mul_sym(Ki, tau[f]);
+          const cvf_v3 Iq = mul_sym(ir, q);
+          Dv[f] = S2[f] - 2.0f * dot(gsA[f], gm) - 2.0f * dot(q, kap[f]) + nA * dot(gm, gm) + dot(q, Iq);
+          const cvf_v3 dc = inA * gsA[f] - gm;
+          const cvf_v3 omv = mul_sym(Ki, kap[f] - Iq);
+          out[f][0] = gm.x, out[f][1] = gm.y, out[f][2] = gm.z, out[f][3] = q.x, out[f][4] = q.y, out[f][5] = q.z;
+          out[f][6] = dc.x, out[f][7] = dc.y, out[f][8] = dc.z, out[f][9] = omv.x, out[f][10] = omv.y, out[f][11] = omv.z;
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) *reinterpret_cast<float2*>(jq + (size_t)i * P.Bp) = make_float2(out[0][i], out[1][i]);
+      } else {
+        Dv[0] = S2[0], Dv[1] = S2[1];
+      }
+      *reinterpret_cast<float2*>(P.Dq + (size_t)n * P.Bp + f0 + c0) = make_float2(Dv[0], Dv[1]);
+      *reinterpret_cast<float2*>(P.Ys + (size_t)n * P.Bp + f0 + c0) = make_float2(yv[0], yv[1]);
+      if (y_out) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+          if (f0 + c0 + f < P.B) y_out[(size_t)n * P.B + f0 + c0 + f] = yv[f];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stats
+// fp64 batch sums S0, S1[i], S2[i][j], SD[i] (core.py:406-410,426) from w, y, D; deterministic two-stage reduction.
+__global__ void __launch_bounds__(256) stats_kernel(const FastPlan P, const float* __restrict__ w, double* __restrict__ part) {
+  __shared__ double red[8];
+  const int k = P.k, ns = 1 + 2 * k + k * k;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = 0; s < ns; ++s) {
+    double acc = 0.0;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < P.B; f += (long long)gridDim.x * blockDim.x) {
+      const double wf = w[f];
+      double v;
+      if (s == 0) v = wf;
+      else if (s < 1 + k) v = wf * P.Ys[(size_t)(s - 1) * P.Bp + f];
+      else if (s < 1 + k + k * k) {
+        const int i = (s - 1 - k) / k, j = (s - 1 - k) % k;
+        v = wf * (double)P.Ys[(size_t)i * P.Bp + f] * (double)P.Ys[(size_t)j * P.Bp + f];
+      } else v = wf * P.Dq[(size_t)(s - 1 - k - k * k) * P.Bp + f];
+      acc += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < 8; ++q) t += red[q];
+      part[(size_t)blockIdx.x * ns + s] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 2
+// lane L ends with sum over lanes of v[L] (v[i >= N] treated as 0); 31 shuffles for up to 32 values.
+template <int N>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = N; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const bool hi = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const float send = hi ? v[i] : v[i + m];
+      const float keep = hi ? v[i + m] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  return v[0];
+}
+
+// Warp-level outer product over the warp's 32 frames:  acc[j][i] += sum_f X[rowX(j)][f] * Z[rowZ(i)][f] for two operand
+// pairs (Xa,Za) and (Xb,Zb).  Rows are kRowPad floats; a lane reads 4 frames per 128-bit load and keeps the even/odd
+// frame partial sums packed in one FFMA2 accumulator.
+template <int TO, int TI>
+__device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* __restrict__ Xa, const float* __restrict__ Za,
+                                           const float* __restrict__ Xb, const float* __restrict__ Zb, int strideX, int strideZ,
+                                           int fbeg, int fend) {
+#pragma unroll 1
+  for (int f = fbeg; f < fend; f += 4) {
+    float4 x[TO], z[TI];
+#pragma unroll
+    for (int j = 0; j < TO; ++j) x[j] = ld4(Xa + j * strideX + f);
+#pragma unroll
+    for (int i = 0; i < TI; ++i) z[i] = ld4(Za + i * strideZ + f);
+#pragma unroll
+    for (int j = 0; j < TO; ++j)
+#pragma unroll
+      for (int i = 0; i < TI; ++i) {
+        acc[j][i] = ffma2(make_float2(x[j].x, x[j].y), make_float2(z[i].x, z[i].y), acc[j][i]);
+        acc[j][i] = ffma2(make_float2(x[j].z, x[j].w), make_float2(z[i].z, z[i].w), acc[j][i]);
+      }
+#pragma unroll
+    for (int j = 0; j < TO; ++j) x[j] = ld4(Xb + j * strideX + f);
+#pragma unroll
+    for (int i = 0; i < TI; ++i) z[i] = ld4(Zb + i * strideZ + f);
+#pragma unroll
+    for (int j = 0; j < TO; ++j)
+#pragma unroll
+      for (int i = 0; i < TI; ++i) {
+        acc[j][i] = ffma2(make_float2(x[j].x, x[j].y), make_float2(z[i].x, z[i].y), acc[j][i]);
+        acc[j][i] = ffma2(make_float2(x[j].z, x[j].w), make_float2(z[i].z, z[i].w), acc[j][i]);
+      }
+  }
+}
+
+// One CTA per SM, 4 independent warps; a warp owns tiles of 32 frames (lane = frame) and a private set of operand rows.
+template <int H, int NH>
+__global__ void __launch_bounds__(kP2Threads, 1)
+pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine) {
+  extern __shared__ __align__(16) float sm[];
+  typedef Img<H, NH> I;
+  constexpr int HP = H / 2, RP = kRowPad, TQ = H / 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int drp = P.d_rp, d_r = P.d_r, k = P.k;
+  float* wsm = sm;                                   // k * img2 (pass-2 prefix of every image)
+  float* geo = wsm + k * P.img2_floats;
+  double* comb = reinterpret_cast<double*>(geo + P.geo_floats);   // mean[k], cD[k], C2[k*k]
+  const int n_comb = 2 * k + k * k;
+  float* rows0 = reinterpret_cast<float*>(comb + n_comb + (n_comb & 1));
+  const int rows_per_warp = 2 * drp + 2 * NH * H + 2 * H;
+  float* Rr = rows0 + (size_t)warp * rows_per_warp * RP;   // [drp]   r (aligned coordinates)
+  float* Vr = Rr + drp * RP;                               // [drp]   tangent direction v
+  float* Zr = Vr + drp * RP;                               // [NH][2H] A_l | T_l
+  float* Xr = Zr + 2 * NH * H * RP;                        // [2H]    s_l | G_l of the layer being reduced; flush buffer
+  for (int n = 0; n < k; ++n)
+    for (int i = tid; i < P.img2_floats; i += kP2Threads) wsm[n * P.img2_floats + i] = P.img[(size_t)n * P.img_floats + i];
+  for (int i = tid; i < P.geo_floats; i += kP2Threads) geo[i] = P.img[(size_t)k * P.img_floats + i];
+  for (int i = tid; i < n_comb; i += kP2Threads) comb[i] = combine[3 + 2 * k + i];
+  for (int i = tid; i < kP2Warps * rows_per_warp * RP; i += kP2Threads) rows0[i] = 0.0f;
+  const int n_part = k * P.n_params;
+  double* part = P.part + ((size_t)blockIdx.x * kP2Warps + warp) * n_part;
+  for (int i = lane; i < n_part; i += 32) part[i] = 0.0;
+  __syncthreads();
+  const double* c_mean = comb;
+  const double* c_cD = comb + k;
+  const double* c_C2 = comb + 2 * k;
+
+  const long long n_tiles = P.Bp / 32;
+  for (long long t = (long long)blockIdx.x * kP2Warps + warp; t < n_tiles; t += (long long)gridDim.x * kP2Warps) {
+    const long long f = t * 32 + lane;
+    const float wf = f < P.B ? __ldg(w + f) : 0.0f;
+    const long long t_next = t + (long long)gridDim.x * kP2Warps;
+    __syncwarp();
+    // stage r rows (own column) and the first network's u rows
+#pragma unroll 6
+    for (int r = 0; r < d_r; ++r) cp_async4(Rr + r * RP + lane, P.Y + (size_t)r * P.Bp + f);
+    for (int n = 0; n < k; ++n) {
+      const float* W = wsm + n * P.img2_floats;
+      double* pn = part + (size_t)n * P.n_params;
+      const float* Un = P.U + ((size_t)n * drp) * P.Bp + f;
+      __syncwarp();   // the previous network's flush has finished reading the Z rows / V rows
+#pragma unroll 6
+      for (int r = 0; r < d_r; ++r) cp_async4(Vr + r * RP + lane, Un + (size_t)r * P.Bp);
+      // L2 prefetch of what is read next: the next network's u rows, or the next tile's r rows and first u rows
+      if (n + 1 < k) {
+        prefetch_rows(P.U + ((size_t)(n + 1) * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
+        if (P.kind == 1) prefetch_rows(P.JQ + ((size_t)(n + 1) * 12) * P.Bp + t * 32, 12, P.Bp, lane);
+      } else if (t_next < n_tiles) {
+        prefetch_rows(P.Y + t_next * 32, d_r, P.Bp, lane);
+        prefetch_rows(P.U + t_next * 32, d_r, P.Bp, lane);
+        if (P.kind == 1) prefetch_rows(P.JQ + t_next * 32, 12, P.Bp, lane);
+      }
+      float seed;
+      {
+        double s = 0.0;
+        for (int j = 0; j < k; ++j) s += c_C2[n * k + j] * ((double)P.Ys[(size_t)j * P.Bp + f] - c_mean[j]);
+        seed = (float)((double)wf * s);
+      }
+      const float scale = (float)(2.0 * (double)wf * c_cD[n]);
+      // ---- joint forward, layer 1: (z, zdot) = W1 (r, v) + (b1, 0); v = scale * J_r J_r^T u built on the fly
+      float2 z[HP], zd[HP];
+#pragma unroll
+      for (int j = 0; j < HP; ++j) z[j] = lds2(W + I::b1(drp) + 2 * j), zd[j] = make_float2(0.f, 0.f);
+      if (P.kind == 1) {
+        const float* jq = P.JQ + ((size_t)n * 12) * P.Bp + f;
+        const cvf_v3 gm = v3(__ldg(jq), __ldg(jq + P.Bp), __ldg(jq + 2 * P.Bp));
+        const cvf_v3 q = v3(__ldg(jq + 3 * P.Bp), __ldg(jq + 4 * P.Bp), __ldg(jq + 5 * P.Bp));
+        const cvf_v3 dc = v3(__ldg(jq + 6 * P.Bp), __ldg(jq + 7 * P.Bp), __ldg(jq + 8 * P.Bp));
+        const cvf_v3 omv = v3(__ldg(jq + 9 * P.Bp), __ldg(jq + 10 * P.Bp), __ldg(jq + 11 * P.Bp));
+        cp_async_wait_all();
+#pragma unroll 2
+        for (int a = 0; a < P.n_atoms; ++a) {
+          const int r = 3 * a;
+          const cvf_v3 uu = v3(Vr[r * RP + lane], Vr[(r + 1) * RP + lane], Vr[(r + 2) * RP + lane]);
+          const cvf_v3 yv3 = v3(Rr[r * RP + lane], Rr[(r + 1) * RP + lane], Rr[(r + 2) * RP + lane]);
+          const cvf_v3 rf = v3(geo[r], geo[r + 1], geo[r + 2]);
+          const float ina = geo[drp + r];
+          const cvf_v3 gp = uu - ina * (gm + cross(rf, q));
+          const cvf_v3 vv = scale * ((gp - dc) + cross(omv, yv3));
+          const float xin[3] = {yv3.x, yv3.y, yv3.z}, vin[3] = {vv.x, vv.y, vv.z};
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            Vr[(r + c) * RP + lane] = vin[c];
+            const float2 x0 = dup(xin[c]), x1 = dup(vin[c]);
+            const float* wr = W + (r + c) * H;
+#pragma unroll
+            for (int qq = 0; qq < TQ; ++qq) {
+              const float4 wv = ld4(wr + 4 * qq);
+              z[2 * qq] = ffma2(make_float2(wv.x, wv.y), x0, z[2 * qq]);
+              z[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[2 * qq + 1]);
+              zd[2 * qq] = ffma2(make_float2(wv.x, wv.y), x1, zd[2 * qq]);
+              zd[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x1, zd[2 * qq + 1]);
+            }
+          }
+        }
+      } else {
+        cp_async_wait_all();
+#pragma unroll 2
+        for (int r = 0; r < d_r; ++r) {
+          const float xin = Rr[r * RP + lane];
+          const float vin = scale * geo[r] * Vr[r * RP + lane];
+          Vr[r * RP + lane] = vin;
+          const float2 x0 = dup(xin), x1 = dup(vin);
+          const float* wr = W + r * H;
+#pragma unroll
+          for (int qq = 0; qq < TQ; ++qq) {
+            const float4 wv = ld4(wr + 4 * qq);
+            z[2 * qq] = ffma2(make_float2(wv.x, wv.y), x0, z[2 * qq]);
+            z[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[2 * qq + 1]);
+            zd[2 * qq] = ffma2(make_float2(wv.x, wv.y), x1, zd[2 * qq]);
+            zd[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x1, zd[2 * qq + 1]);
+          }
+        }
+      }
+      float a[H], tg[H];   // A_l, T_l = (1 - A_l^2) zdot_l of the current layer
+#pragma unroll
+      for (int j = 0; j < HP; ++j) {
+        a[2 * j] = cvf_tanh(z[j].x), a[2 * j + 1] = cvf_tanh(z[j].y);
+        tg[2 * j] = fmaf(-a[2 * j], a[2 * j], 1.0f) * zd[j].x;
+        tg[2 * j + 1] = fmaf(-a[2 * j + 1], a[2 * j + 1], 1.0f) * zd[j].y;
+      }
+#pragma unroll
+      for (int o = 0; o < H; ++o) Zr[o * RP + lane] = a[o], Zr[(H + o) * RP + lane] = tg[o];
+#pragma unroll
+      for (int l = 2; l <= NH; ++l) {
+#pragma unroll
+        for (int j = 0; j < HP; ++j) z[j] = lds2(W + I::bl(drp, l) + 2 * j), zd[j] = make_float2(0.f, 0.f);
+        const float* wt = W + I::wt(drp, l);
+#pragma unroll
+        for (int kk = 0; kk < H; ++kk) {
+          const float2 x0 = dup(a[kk]), x1 = dup(tg[kk]);
+#pragma unroll
+          for (int qq = 0; qq < TQ; ++qq) {
+            const float4 wv = ld4(wt + kk * H + 4 * qq);
+            z[2 * qq] = ffma2(make_float2(wv.x, wv.y), x0, z[2 * qq]);
+            z[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[2 * qq + 1]);
+            zd[2 * qq] = ffma2(make_float2(wv.x, wv.y), x1, zd[2 * qq]);
+            zd[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x1, zd[2 * qq + 1]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+          a[2 * j] = cvf_tanh(z[j].x), a[2 * j + 1] = cvf_tanh(z[j].y);
+          tg[2 * j] = fmaf(-a[2 * j], a[2 * j], 1.0f) * zd[j].x;
+          tg[2 * j + 1] = fmaf(-a[2 * j + 1], a[2 * j + 1], 1.0f) * zd[j].y;
+        }
+#pragma unroll
+        for (int o = 0; o < H; ++o) Zr[((l - 1) * 2 * H + o) * RP + lane] = a[o], Zr[((l - 1) * 2 * H + H + o) * RP + lane] = tg[o];
+      }
+      // ---- output layer: dWout = sum_f seed A_NH + T_NH, dbout = sum_f seed;  G_NH, s_NH
+      float gl[H], sl[H];
+      {
+        float red[32];
+#pragma unroll
+        for (int o = 0; o < H; ++o) red[o] = fmaf(seed, a[o], tg[o]);
+        red[H] = seed;
+        const float tot = warp_reduce_scatter<H + 1>(red, lane);
+        if (lane < H) atomicAdd(pn + P.gw_off[NH] + lane, (double)tot);
+        else if (lane == H) atomicAdd(pn + P.gb_off[NH], (double)tot);
+#pragma unroll
+        for (int qq = 0; qq < TQ; ++qq) {
+          const float4 wv = ld4(W + I::wout(drp) + 4 * qq);
+          const float wo[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int o = 4 * qq + e;
+            const float omo = fmaf(-a[o], a[o], 1.0f);
+            gl[o] = omo * wo[e];
+            sl[o] = fmaf(-2.0f * a[o] * wo[e], tg[o], omo * seed * wo[e]);
+          }
+        }
+      }
+      // ---- reverse sweep over the hidden layers with the outer products of each layer as soon as (s_l, G_l) exist
+#pragma unroll
+      for (int l = NH; l >= 1; --l) {
+        __syncwarp();
+#pragma unroll
+        for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = gl[o];
+        // db_l = sum_f s_l
+        {
+          float red[32];
+#pragma unroll
+          for (int o = 0; o < H; ++o) red[o] = sl[o];
+          const float tot = warp_reduce_scatter<H>(red, lane);
+          if (lane < H) atomicAdd(pn + P.gb_off[l - 1] + lane, (double)tot);
+        }
+        __syncwarp();
+        if (l >= 2) {
+          // dW_l [H][H] += s_l (x) A_{l-1} + G_l (x) T_{l-1}: half-warps split the frames, 16 lanes x (TQ x TQ) entries
+          const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
+          float2 acc[TQ][TQ];
+#pragma unroll
+          for (int j = 0; j < TQ; ++j)
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) acc[j][i] = make_float2(0.f, 0.f);
+          const float* Zl = Zr + (size_t)(l - 2) * 2 * H * RP;
+          outer_tile<TQ, TQ>(acc, Xr + og * RP, Zl + ig * RP, Xr + (H + og) * RP, Zl + (H + ig) * RP, 4 * RP, 4 * RP, 16 * half,
+                             16 * half + 16);
+          float r2[TQ][TQ];
+#pragma unroll
+          for (int j = 0; j < TQ; ++j)
+#pragma unroll
+            for (int i = 0; i < TQ; ++i) {
+              r2[j][i] = acc[j][i].x + acc[j][i].y;
+              r2[j][i] += __shfl_xor_sync(0xffffffffu, r2[j][i], 16);
+            }
+          __syncwarp();
+          if (half == 0) {
+#pragma unroll
+            for (int j = 0; j < TQ; ++j)
+#pragma unroll
+              for (int i = 0; i < TQ; ++i) Xr[(4 * j + og) * H + 4 * i + ig] = r2[j][i];
+          }
+          __syncwarp();
+          for (int e = lane; e < H * H; e += 32) atomicAdd(pn + P.gw_off[l - 1] + e, (double)Xr[e]);
+          // next (G, s): h = W_l^T (G_l, s_l);  G_{l-1} = om h_G,  s_{l-1} = -2 A h_G T + om h_s
+          float2 hg[HP], hs[HP];
+#pragma unroll
+          for (int j = 0; j < HP; ++j) hg[j] = hs[j] = make_float2(0.f, 0.f);
+          const float* wn = W + I::wn(drp, l);
+#pragma unroll
+          for (int o = 0; o < H; ++o) {
+            const float2 g0 = dup(gl[o]), s0 = dup(sl[o]);
+#pragma unroll
+            for (int qq = 0; qq < TQ; ++qq) {
+              const float4 wv = ld4(wn + o * H + 4 * qq);
+              hg[2 * qq] = ffma2(make_float2(wv.x, wv.y), g0, hg[2 * qq]);
+              hg[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), g0, hg[2 * qq + 1]);
+              hs[2 * qq] = ffma2(make_float2(wv.x, wv.y), s0, hs[2 * qq]);
+              hs[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), s0, hs[2 * qq + 1]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < HP; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int o = 2 * j + e;
+              const float ao = Zl[o * RP + lane], to = Zl[(H + o) * RP + lane];
+              const float omo = fmaf(-ao, ao, 1.0f);
+              const float hgo = e == 0 ? hg[j].x : hg[j].y, hso = e == 0 ? hs[j].x : hs[j].y;
+              gl[o] = omo * hgo;
+              sl[o] = fmaf(-2.0f * ao * hgo, to, omo * hso);
+            }
+          }
+        } else {
+          // dW_1 [H][d_r] += s_1 (x) r + G_1 (x) v: lanes (og, ig) with 4 x 12 entries, interleaved rows (bank skew)
+          constexpr int LPO = 32 / TQ;   // lanes per output group
+          const int og = lane / LPO, ig0 = lane - og * LPO;
+          const int nig = drp / 12;
+          for (int ig = ig0; ig < nig && og < TQ; ig += LPO) {
+            float2 acc[4][12];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 12; ++i) acc[j][i] = make_float2(0.f, 0.f);
+            outer_tile<4, 12>(acc, Xr + og * RP, Rr + ig * RP, Xr + (H + og) * RP, Vr + ig * RP, TQ * RP, nig * RP, 0, 32);
+            // transpose through the (now dead) Z rows so that the fp64 reductions below are coalesced
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < 12; ++i) {
+                const int o = j * TQ + og, col = i * nig + ig;
+                if (col < d_r) Zr[o * d_r + col] = acc[j][i].x + acc[j][i].y;
+              }
+          }
+          __syncwarp();
+          for (int e = lane; e < H * d_r; e += 32) atomicAdd(pn + P.gw_off[0] + e, (double)Zr[e]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Shape {
+  int H, NH;
+};
+
+static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int drp) {
+  return ((size_t)k * img_floats + geo_floats + (size_t)drp * kP1Frames) * sizeof(float);
+}
+static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH) {
+  const int n_comb = 2 * k + k * k;
+  const int rows_per_warp = 2 * drp + 2 * NH * H + 2 * H;
+  return ((size_t)k * img2_floats + geo_floats) * sizeof(float) + (size_t)(n_comb + (n_comb & 1)) * sizeof(double) +
+         (size_t)kP2Warps * rows_per_warp * kRowPad * sizeof(float);
+}
+// image sizes without the template (same arithmetic as Img<H, NH>)
+static int img2_floats_of(int H, int NH, int drp) { return drp * H + H + (NH - 1) * (H * H + H) + H + 4 + (NH - 1) * H * H; }
+static int img_floats_of(int H, int NH, int drp) { return img2_floats_of(H, NH, drp) + H * drp; }
+
+static bool supported_shape(const NetPlan& np, Shape* s) {
+  if (np.L < 2) return false;
+  const int H = np.dims[1];
+  for (int l = 1; l < np.L; ++l)
+    if (np.dims[l] != H) return false;
+  if (np.dims[np.L] != 1) return false;
+  s->H = H, s->NH = np.L - 1;
+  return (H == 20 && (s->NH == 3 || s->NH == 2)) || (H == 32 && s->NH == 3) || (H == 16 && s->NH == 3);
+}
+
+}  // namespace fast
+
+// Whether the fast path covers this task; fills the byte count of its scratch (0 otherwise).
+bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k) {
+  fast::Shape s;
+  if (!fast::supported_shape(np, &s)) return false;
+  if (k < 1 || k > kMaxK) return false;
+  int d_r;
+  if (pp->kind == 0) {
+    d_r = pp->dim;
+  } else if (pp->kind == 1) {
+    if (!pp->positions_only || !pp->used_identity || pp->n_align < 3 || pp->diag != nullptr || pp->n_used != pp->n_atoms) return false;
+    d_r = 3 * pp->n_atoms;
+  } else {
+    return false;
+  }
+  if (d_r < 1) return false;
+  const int drp = (d_r + 11) / 12 * 12, geo = fast::geo_floats_of(drp);
+  const size_t cap = (size_t)max_smem_optin();
+  return fast::pass1_smem_bytes(k, fast::img_floats_of(s.H, s.NH, drp), geo, drp) <= cap &&
+         fast::pass2_smem_bytes(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) <= cap;
+}
+
+namespace fast {
+
+static inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+template <int H, int NH>
+static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np, int k, long long B, void* workspace) {
+  typedef Img<H, NH> I;
+  P->k = k;
+  P->kind = pp->kind;
+  P->d_r = pp->kind == 0 ? pp->dim : 3 * pp->n_atoms;
+  P->d_rp = (int)round_up(P->d_r, 12);
+  P->n_atoms = pp->kind == 1 ? pp->n_atoms : 0;
+  P->n_align = pp->kind == 1 ? pp->n_align : 0;
+  P->img_floats = I::floats(P->d_rp);
+  P->img2_floats = I::p2_floats(P->d_rp);
+  P->geo_floats = geo_floats_of(P->d_rp);
+  P->n_params = np.n_params;
+  for (int l = 0; l < np.L; ++l) P->gw_off[l] = np.gw_off[l], P->gb_off[l] = np.gb_off[l];
+  P->B = B;
+  P->Bp = round_up(B, kP1Frames);
+  P->align_idx = pp->kind == 1 ? pp->align_used : nullptr;   // used_identity: positions in used_atoms are atom indices
+  P->ref = pp->ref;
+  P->diag = pp->diag;
+  char* base = (char*)workspace;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const int n_part = k * np.n_params > 1 + 2 * k + k * k ? k * np.n_params : 1 + 2 * k + k * k;
+  P->part = (double*)take((size_t)sm_count() * kP2Warps * n_part * sizeof(double));
+  P->img = (float*)take(((size_t)k * P->img_floats + P->geo_floats) * sizeof(float));
+  P->Y = (float*)take((size_t)P->d_rp * P->Bp * sizeof(float));
+  P->Kinv = (float*)take((size_t)6 * P->Bp * sizeof(float));
+  P->U = (float*)take((size_t)k * P->d_rp * P->Bp * sizeof(float));
+  P->JQ = (float*)take((size_t)k * 12 * P->Bp * sizeof(float));
+  P->Dq = (float*)take((size_t)k * P->Bp * sizeof(float));
+  P->Ys = (float*)take((size_t)k * P->Bp * sizeof(float));
+  return off;
+}
+
+template <int H, int NH>
+static int run_forward(const FastPlan& P, const float* x, const float* params, float* y_out, cudaStream_t stream) {
+  pack_kernel<H, NH><<<P.k + 1, 256, 0, stream>>>(P, params);
+  CVF_CUDA(cudaGetLastError());
+  if (P.kind == 1) {
+    const size_t smem = (size_t)(128 * ((3 * P.n_atoms) | 1) + 6 * 128) * sizeof(float);
+    CVF_CUDA(cudaFuncSetAttribute(prep_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = (long long)sm_count() * 4;
+    if (P.Bp / 128 < grid) grid = P.Bp / 128;
+    prep_align_kernel<<<(int)grid, 128, smem, stream>>>(P, x);
+  } else {
+    long long grid = (long long)sm_count() * 8;
+    if ((P.Bp + 255) / 256 < grid) grid = (P.Bp + 255) / 256;
+    prep_transpose_kernel<<<(int)grid, 256, 0, stream>>>(P, x);
+  }
+  CVF_CUDA(cudaGetLastError());
+  const size_t smem1 = pass1_smem_bytes(P.k, P.img_floats, P.geo_floats, P.d_rp);
+  if (smem1 > (size_t)max_smem_optin()) {
+    set_error("fast eigen path: pass 1 needs %zu B of shared memory", smem1);
+    return CVF_E_UNSUPPORTED;
+  }
+  CVF_CUDA(cudaFuncSetAttribute(pass1_kernel<H, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  long long grid = sm_count();
+  if (P.Bp / kP1Frames < grid) grid = P.Bp / kP1Frames;
+  pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out);
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int H, int NH>
+static int run_stats(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
+                     const float* params, float* y_out, double* stats_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  FastPlan P;
+  const size_t need = plan_scratch<H, NH>(&P, pp, np, k, B, workspace);
+  if (need > ws_bytes) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, need);
+    return CVF_E_WORKSPACE;
+  }
+  int e = run_forward<H, NH>(P, x, params, y_out, stream);
+  if (e) return e;
+  const int ns = 1 + 2 * k + k * k;
+  long long grid = (long long)sm_count() * 2;
+  if ((B + 255) / 256 < grid) grid = (B + 255) / 256;
+  stats_kernel<<<(int)grid, 256, 0, stream>>>(P, w, P.part);
+  CVF_CUDA(cudaGetLastError());
+  reduce_partials_kernel<<<(ns + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, ns, 0, ns, stats_out);
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int H, int NH>
+static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
+                    const float* params, const double* combine, double* grad_out, void* workspace, size_t ws_bytes,
+                    int scratch_valid, cudaStream_t stream) {
+  FastPlan P;
+  const size_t need = plan_scratch<H, NH>(&P, pp, np, k, B, workspace);
+  if (need > ws_bytes) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, need);
+    return CVF_E_WORKSPACE;
+  }
+  if (!scratch_valid) {
+    int e = run_forward<H, NH>(P, x, params, nullptr, stream);
+    if (e) return e;
+  }
+  const size_t smem2 = pass2_smem_bytes(k, P.img2_floats, P.geo_floats, P.d_rp, H, NH);
+  if (smem2 > (size_t)max_smem_optin()) {
+    set_error("fast eigen path: pass 2 needs %zu B of shared memory", smem2);
+    return CVF_E_UNSUPPORTED;
+  }
+  CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  long long grid = sm_count();
+  const long long n_tiles = P.Bp / 32;
+  if ((n_tiles + kP2Warps - 1) / kP2Warps < grid) grid = (n_tiles + kP2Warps - 1) / kP2Warps;
+  pass2_kernel<H, NH><<<(int)grid, kP2Threads, smem2, stream>>>(P, w, combine);
+  CVF_CUDA(cudaGetLastError());
+  const int n_part = k * np.n_params;
+  reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid * kP2Warps, n_part, 0, n_part, grad_out);
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fast
+
+#define CVF_FAST_DISPATCH(CALL, ...)                                   \
+  do {                                                                 \
+    fast::Shape s_;                                                    \
+    fast::supported_shape(np, &s_);                                    \
+    if (s_.H == 20 && s_.NH == 3) return fast::CALL<20, 3>(__VA_ARGS__); \
+    if (s_.H == 20 && s_.NH == 2) return fast::CALL<20, 2>(__VA_ARGS__); \
+    if (s_.H == 32 && s_.NH == 3) return fast::CALL<32, 3>(__VA_ARGS__); \
+    if (s_.H == 16 && s_.NH == 3) return fast::CALL<16, 3>(__VA_ARGS__); \
+  } while (0)
+
+size_t fast_eigen_workspace_bytes(const cvf_preproc* pp, const NetPlan& np, int k, long long B) {
+  fast::FastPlan P;
+  fast::Shape s_;
+  fast::supported_shape(np, &s_);
+  if (s_.H == 20 && s_.NH == 3) return fast::plan_scratch<20, 3>(&P, pp, np, k, B, nullptr);
+  if (s_.H == 20 && s_.NH == 2) return fast::plan_scratch<20, 2>(&P, pp, np, k, B, nullptr);
+  if (s_.H == 32 && s_.NH == 3) return fast::plan_scratch<32, 3>(&P, pp, np, k, B, nullptr);
+  if (s_.H == 16 && s_.NH == 3) return fast::plan_scratch<16, 3>(&P, pp, np, k, B, nullptr);
+  return 0;
+}
+
+int fast_eigen_stats(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
+                     const float* params, float* y_out, double* stats_out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  CVF_FAST_DISPATCH(run_stats, pp, np, k, x, w, B, params, y_out, stats_out, workspace, ws_bytes, stream);
+  set_error("fast eigen path: shape not instantiated");
+  return CVF_E_UNSUPPORTED;
+}
+
+int fast_eigen_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
+                    const float* params, const double* combine, double* grad_out, void* workspace, size_t ws_bytes,
+                    int scratch_valid, cudaStream_t stream) {
+  CVF_FAST_DISPATCH(run_grad, pp, np, k, x, w, B, params, combine, grad_out, workspace, ws_bytes, scratch_valid, stream);
+  set_error("fast eigen path: shape not instantiated");
+  return CVF_E_UNSUPPORTED;
+}
+
+}  // namespace cvf

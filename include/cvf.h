@@ -89,8 +89,13 @@ int cvf_features_fwd(const float* x, int64_t B, const cvf_preproc* pp, float* r_
 int32_t cvf_eigen_num_stats(int32_t k);
 /* doubles in the combine vector: loss, obj, pen, eig[k] (sorted), cvec[k], mean[k], cD[k], C2[k*k] */
 int32_t cvf_eigen_num_combine(int32_t k);
-/* bytes of scratch needed by cvf_eigen_stats / cvf_eigen_grad (per-block partial sums) */
-size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k);
+/* bytes of scratch needed by cvf_eigen_stats / cvf_eigen_grad on a batch of B frames: per-CTA partial sums and, on the
+ * fast path, the frame-minor intermediates pass 1 leaves for pass 2 (aligned frames, grad_r y, Jacobian vectors). */
+size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k, int64_t B);
+/* 1 if (pp, net, k) runs on the thread-private FFMA2 kernels (cvf_eigen_fast.cu), 0 if on the general row-engine kernels */
+int cvf_eigen_path(const cvf_preproc* pp, const cvf_mlp* net, int32_t k);
+/* testing / profiling switch: 0 = choose automatically (default), 1 = always the general kernels */
+int cvf_eigen_set_path(int32_t mode);
 
 /* Pass 1: y = model(pp(X)), grad_x y_i, Dirichlet densities; batch sums (core.py:403-410,424-426).
  * params [k * cvf_mlp_param_count] fp32.  y_out [k,B] fp32 (kept for pass 2).  stats_out fp64. */
@@ -104,10 +109,11 @@ int cvf_eigen_combine(const double* stats, int32_t k, double alpha, const double
                       int32_t sort, double* combine_out, void* stream);
 
 /* Pass 2: d loss / d params (replaces loss.backward(), core.py:517).  grad_out [k * param_count] fp64,
- * summed over this rank's frames. */
+ * summed over this rank's frames.  scratch_valid = 1 promises that `workspace` still holds what the cvf_eigen_stats
+ * call on the SAME x, w, params left there (the normal loss -> backward sequence); 0 recomputes it. */
 int cvf_eigen_grad(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
                    int32_t k, const float* params, const float* y_in, const double* combine,
-                   double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
+                   double* grad_out, void* workspace, size_t workspace_bytes, int32_t scratch_valid, void* stream);
 
 /* ---- AutoEncoderTask.weighted_MSE_loss + backward (core.py:652-666,708) ---- */
 size_t cvf_ae_workspace_bytes(const cvf_mlp* net);

@@ -169,6 +169,96 @@ def test_eigen_loss_matches_oracle_ragged_sizes(name, B, tmp_path):
             assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (i, j, C.rel_l2(grads[i][j], g64[i][j]))
 
 
+def _random_nets(dims, k, seed):
+    torch.manual_seed(seed)
+    return [[p.numpy() for p in ref_torch.init_mlp_params(dims)] for _ in range(k)]
+
+
+FAST_CASES = {
+    # name: (layer dims, k, pre-processing, diag)
+    "c3_all_atoms": ([66, 20, 20, 20, 1], 3, "align_all", False),
+    "align_subset_k2": ([66, 20, 20, 20, 1], 2, "align_subset", False),
+    "two_hidden_k4": ([66, 20, 20, 1], 4, "align_all", False),
+    "width16_k1": ([66, 16, 16, 16, 1], 1, "align_all", False),
+    "width32_k2": ([5, 32, 32, 32, 1], 2, "identity", True),
+    "identity_2d_k1": ([2, 20, 20, 20, 1], 1, "identity", False),
+    "identity_5d_diag_k3": ([5, 20, 20, 20, 1], 3, "identity", True),
+}
+
+
+@pytest.mark.parametrize("B", [2, 37, 512, 1500])
+@pytest.mark.parametrize("name", sorted(FAST_CASES))
+def test_eigen_fast_path_matches_oracle(name, B, tmp_path):
+    """The thread-private FFMA2 kernels (cvf_eigen_fast.cu) against the fp64 closed-form oracle: every network shape they are
+    instantiated for, alignment on all atoms and on a subset, Identity pre-processing with and without diag_coeff, batch
+    sizes below / at / above their 512-frame tile."""
+    from colvarsfinder import core, nn, utils
+    dims, k, ppk, use_diag = FAST_CASES[name]
+    nets = _random_nets(dims, k, seed=len(name) + B)
+    rng = np.random.default_rng(B + k)
+    heavy = [1, 4, 5, 6, 8, 10, 14, 15, 16, 18]
+    if ppk == "identity":
+        X = rng.normal(size=(B, dims[0])).astype(np.float32)
+        pp, ppo = torch.nn.Identity(), cf.Preproc(identity=True)
+    elif ppk == "align_all":
+        X = ref_torch.synth_frames(BASE, B, seed=B + 1)
+        pp, ppo = utils.Align(BASE, list(range(22))), cf.Preproc(align_idx=list(range(22)), ref=BASE)
+    else:
+        X = ref_torch.synth_frames(BASE, B, seed=B + 2)
+        pp, ppo = utils.Align(BASE[heavy], heavy), cf.Preproc(align_idx=heavy, ref=BASE[heavy])
+    w = ref_torch.boltzmann_weights(B, seed=B)
+    diag = (0.5 + rng.random(dims[0])).astype(np.float32) if use_diag else None
+    eig_w = [1.0, 0.6, 0.3, 0.2][:k]
+    model = nn.EigenFunctions(dims, k)
+    with torch.no_grad():
+        for i in range(k):
+            for p, v in zip(model.eigen_funcs[i].parameters(), nets[i]):
+                p.copy_(torch.as_tensor(v))
+    task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64), dt=1.0), pp, model, str(tmp_path), 20.0, eig_w,
+                                  diag_coeff=None if diag is None else torch.as_tensor(diag), k=k, device=DEV, verbose=False,
+                                  debug_mode=False)
+    assert task._ctx.fast_path
+    out = task.loss_func(task._traj, task._weights, None, None)
+    out[0].backward()
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, eig_w, diag)
+    loss, eig, obj, pen, cvec = out
+    assert list(cvec.cpu().numpy()) == list(comb["cvec"])
+    assert abs(float(loss) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
+    np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
+    for i in range(k):
+        for j in range(len(g64[i])):
+            if np.abs(g64[i][j]).max() < 1e-9 * abs(comb["loss"]):
+                assert np.abs(grads[i][j]).max() < 1e-4 * abs(comb["loss"])
+                continue
+            assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (i, j, C.rel_l2(grads[i][j], g64[i][j]))
+
+
+@pytest.mark.parametrize("name", ["eigen_2d_k1", "eigen_dipep_k3"])
+def test_eigen_general_kernels_on_fast_shapes(name, tmp_path):
+    """cvf_eigen_set_path(1) forces the general row-engine kernels on the shapes the fast path normally takes: both
+    implementations are held to the reference's golden vectors and to each other."""
+    from colvarsfinder import _lib
+    c = C.eigen_case(name)
+    res = {}
+    for mode in (1, 0):
+        _lib.check(_lib.lib().cvf_eigen_set_path(mode), "cvf_eigen_set_path")
+        try:
+            task, model = _eigen_task(c, tmp_path)
+            assert task._ctx.fast_path == (mode == 0)
+            out = task.loss_func(task._traj, task._weights, None, None)
+            out[0].backward()
+            grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+        finally:
+            _lib.lib().cvf_eigen_set_path(0)
+        gold = dict(loss=float(c["g64_loss"]), obj=float(c["g64_obj"]), pen=float(c["g64_pen"]), eig=c["g64_eig"],
+                    cvec=c["g64_cvec"], grads=c["g64"], loss32=float(c["r32_loss"]), obj32=float(c["r32_obj"]),
+                    pen32=float(c["r32_pen"]), eig32=c["r32_eig"], grads32=c["g32"])
+        _check_eigen(c, out, grads, gold, f"{name}/mode{mode}")
+        res[mode] = (float(out[0]), grads)
+    assert abs(res[0][0] - res[1][0]) <= 2e-5 * abs(res[1][0])
+
+
 def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
     """Size-independent property at BASELINE scale (2^20 frames of C3): the fp64 batch sums of a batch equal the sum over
     its halves, and the gradient sums of pass 2 (at fixed coefficients) are additive too."""
