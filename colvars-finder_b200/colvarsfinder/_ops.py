@@ -261,6 +261,8 @@ class EigenContext:
                                              C.byref(self.mlp), self.k, self.flat.flat.data_ptr(), y.data_ptr(),
                                              comb.data_ptr(), g.data_ptr(), ws, self.ws_bytes, valid, _stream()),
                    "cvf_eigen_grad")
+        if not valid:
+            self._scratch_key = self._key(X, weight)   # pass 2 refreshed the scratch for these tensors
         return g
 
 
