@@ -51,7 +51,7 @@ __device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long
 
 constexpr int kRowPad = 36;   // floats per 32-frame row of the pass-2 operand rows (16-byte aligned, bank-group skew 1 per row)
 constexpr int kP1Frames = 512, kP1Threads = 256;
-constexpr int kP2Threads = 128, kP2Warps = 4;
+constexpr int kP2MaxWarps = 8, kP2MinWarps = 4;
 
 // Shared-memory image of one network (floats; every block 16-byte aligned because H % 4 == 0 and d_rp % 12 == 0):
 //   W1T [d_rp][H] (k-major)  b1 [H]  { WlT [H][H]  bl [H] } l=2..NH   Wout [H]  bout [4]   { Wl [H][H] natural } l=2..NH
@@ -85,7 +85,9 @@ struct FastPlan {
   float* JQ;                     // [k][12][Bp]   gm, q, dc, om
   float* Dq;                     // [k][Bp]
   float* Ys;                     // [k][Bp]
+  float* SG;                     // [k][2H][Bp]   s_1 | scale G_1 (pass 2a -> pass 2b)
   double* part;                  // per-CTA / per-warp partial sums
+  double* part2;                 // pass 2b: per-warp partial [H][d_r] blocks
 };
 
 // geo block (floats): kind 1: refA [d_rp] (reference position of the atom a coordinate belongs to, 0 if not aligned),
@@ -536,32 +538,34 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
   }
 }
 
-// One CTA per SM, 4 independent warps; a warp owns tiles of 32 frames (lane = frame) and a private set of operand rows.
+// Pass 2a.  One CTA per SM, up to 8 independent warps; a warp owns tiles of 32 frames (lane = frame) and a private set of
+// operand rows: Z rows (A_l | T_l of every hidden layer; during layer 1 they stage r and u) and X rows (s_l | G_l of the
+// layer being reduced, then the flush buffer).  The first layer's weight gradient needs r and v of every frame as operand
+// rows, which would halve the number of resident warps: (s_1, scale G_1) go to global memory and pass 2b does that product.
 template <int H, int NH>
-__global__ void __launch_bounds__(kP2Threads, 1)
-pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine) {
+__global__ void __launch_bounds__(256, 1)
+pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp) {
   extern __shared__ __align__(16) float sm[];
   typedef Img<H, NH> I;
   constexpr int HP = H / 2, RP = kRowPad, TQ = H / 4;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
   const int drp = P.d_rp, d_r = P.d_r, k = P.k;
   float* wsm = sm;                                   // k * img2 (pass-2 prefix of every image)
   float* geo = wsm + k * P.img2_floats;
   double* comb = reinterpret_cast<double*>(geo + P.geo_floats);   // mean[k], cD[k], C2[k*k]
   const int n_comb = 2 * k + k * k;
   float* rows0 = reinterpret_cast<float*>(comb + n_comb + (n_comb & 1));
-  const int rows_per_warp = 2 * drp + 2 * NH * H + 2 * H;
-  float* Rr = rows0 + (size_t)warp * rows_per_warp * RP;   // [drp]   r (aligned coordinates)
-  float* Vr = Rr + drp * RP;                               // [drp]   tangent direction v
-  float* Zr = Vr + drp * RP;                               // [NH][2H] A_l | T_l
-  float* Xr = Zr + 2 * NH * H * RP;                        // [2H]    s_l | G_l of the layer being reduced; flush buffer
+  float* Zr = rows0 + (size_t)warp * rows_per_warp * RP;   // [NH][2H] A_l | T_l
+  float* Xr = Zr + 2 * NH * H * RP;                        // [2H]     s_l | G_l; flush buffer
+  float* Sr = Zr;                                          // [drp]    r staged for layer 1
+  float* Su = Zr + drp * RP;                               // [drp]    u staged for layer 1
   for (int n = 0; n < k; ++n)
-    for (int i = tid; i < P.img2_floats; i += kP2Threads) wsm[n * P.img2_floats + i] = P.img[(size_t)n * P.img_floats + i];
-  for (int i = tid; i < P.geo_floats; i += kP2Threads) geo[i] = P.img[(size_t)k * P.img_floats + i];
-  for (int i = tid; i < n_comb; i += kP2Threads) comb[i] = combine[3 + 2 * k + i];
-  for (int i = tid; i < kP2Warps * rows_per_warp * RP; i += kP2Threads) rows0[i] = 0.0f;
+    for (int i = tid; i < P.img2_floats; i += nt) wsm[n * P.img2_floats + i] = P.img[(size_t)n * P.img_floats + i];
+  for (int i = tid; i < P.geo_floats; i += nt) geo[i] = P.img[(size_t)k * P.img_floats + i];
+  for (int i = tid; i < n_comb; i += nt) comb[i] = combine[3 + 2 * k + i];
+  for (int i = tid; i < nw * rows_per_warp * RP; i += nt) rows0[i] = 0.0f;
   const int n_part = k * P.n_params;
-  double* part = P.part + ((size_t)blockIdx.x * kP2Warps + warp) * n_part;
+  double* part = P.part + ((size_t)blockIdx.x * nw + warp) * n_part;
   for (int i = lane; i < n_part; i += 32) part[i] = 0.0;
   __syncthreads();
   const double* c_mean = comb;
@@ -569,21 +573,22 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   const double* c_C2 = comb + 2 * k;
 
   const long long n_tiles = P.Bp / 32;
-  for (long long t = (long long)blockIdx.x * kP2Warps + warp; t < n_tiles; t += (long long)gridDim.x * kP2Warps) {
+  for (long long t = (long long)blockIdx.x * nw + warp; t < n_tiles; t += (long long)gridDim.x * nw) {
     const long long f = t * 32 + lane;
     const float wf = f < P.B ? __ldg(w + f) : 0.0f;
-    const long long t_next = t + (long long)gridDim.x * kP2Warps;
-    __syncwarp();
-    // stage r rows (own column) and the first network's u rows
-#pragma unroll 6
-    for (int r = 0; r < d_r; ++r) cp_async4(Rr + r * RP + lane, P.Y + (size_t)r * P.Bp + f);
+    const long long t_next = t + (long long)gridDim.x * nw;
+    float ysv[kMaxK];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) ysv[j] = j < k ? __ldg(P.Ys + (size_t)j * P.Bp + f) : 0.0f;
     for (int n = 0; n < k; ++n) {
       const float* W = wsm + n * P.img2_floats;
       double* pn = part + (size_t)n * P.n_params;
       const float* Un = P.U + ((size_t)n * drp) * P.Bp + f;
-      __syncwarp();   // the previous network's flush has finished reading the Z rows / V rows
+      __syncwarp();   // the previous network's flush has finished reading the X rows
 #pragma unroll 6
-      for (int r = 0; r < d_r; ++r) cp_async4(Vr + r * RP + lane, Un + (size_t)r * P.Bp);
+      for (int r = 0; r < d_r; ++r) cp_async4(Sr + r * RP + lane, P.Y + (size_t)r * P.Bp + f);
+#pragma unroll 6
+      for (int r = 0; r < d_r; ++r) cp_async4(Su + r * RP + lane, Un + (size_t)r * P.Bp);
       // L2 prefetch of what is read next: the next network's u rows, or the next tile's r rows and first u rows
       if (n + 1 < k) {
         prefetch_rows(P.U + ((size_t)(n + 1) * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
@@ -596,7 +601,9 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       float seed;
       {
         double s = 0.0;
-        for (int j = 0; j < k; ++j) s += c_C2[n * k + j] * ((double)P.Ys[(size_t)j * P.Bp + f] - c_mean[j]);
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j)
+          if (j < k) s += c_C2[n * k + j] * ((double)ysv[j] - c_mean[j]);
         seed = (float)((double)wf * s);
       }
       const float scale = (float)(2.0 * (double)wf * c_cD[n]);
@@ -614,8 +621,8 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll 2
         for (int a = 0; a < P.n_atoms; ++a) {
           const int r = 3 * a;
-          const cvf_v3 uu = v3(Vr[r * RP + lane], Vr[(r + 1) * RP + lane], Vr[(r + 2) * RP + lane]);
-          const cvf_v3 yv3 = v3(Rr[r * RP + lane], Rr[(r + 1) * RP + lane], Rr[(r + 2) * RP + lane]);
+          const cvf_v3 uu = v3(Su[r * RP + lane], Su[(r + 1) * RP + lane], Su[(r + 2) * RP + lane]);
+          const cvf_v3 yv3 = v3(Sr[r * RP + lane], Sr[(r + 1) * RP + lane], Sr[(r + 2) * RP + lane]);
           const cvf_v3 rf = v3(geo[r], geo[r + 1], geo[r + 2]);
           const float ina = geo[drp + r];
           const cvf_v3 gp = uu - ina * (gm + cross(rf, q));
@@ -623,7 +630,6 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           const float xin[3] = {yv3.x, yv3.y, yv3.z}, vin[3] = {vv.x, vv.y, vv.z};
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            Vr[(r + c) * RP + lane] = vin[c];
             const float2 x0 = dup(xin[c]), x1 = dup(vin[c]);
             const float* wr = W + (r + c) * H;
 #pragma unroll
@@ -640,9 +646,8 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         cp_async_wait_all();
 #pragma unroll 2
         for (int r = 0; r < d_r; ++r) {
-          const float xin = Rr[r * RP + lane];
-          const float vin = scale * geo[r] * Vr[r * RP + lane];
-          Vr[r * RP + lane] = vin;
+          const float xin = Sr[r * RP + lane];
+          const float vin = scale * geo[r] * Su[r * RP + lane];
           const float2 x0 = dup(xin), x1 = dup(vin);
           const float* wr = W + r * H;
 #pragma unroll
@@ -716,9 +721,6 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       // ---- reverse sweep over the hidden layers with the outer products of each layer as soon as (s_l, G_l) exist
 #pragma unroll
       for (int l = NH; l >= 1; --l) {
-        __syncwarp();
-#pragma unroll
-        for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = gl[o];
         // db_l = sum_f s_l
         {
           float red[32];
@@ -727,8 +729,11 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           const float tot = warp_reduce_scatter<H>(red, lane);
           if (lane < H) atomicAdd(pn + P.gb_off[l - 1] + lane, (double)tot);
         }
-        __syncwarp();
         if (l >= 2) {
+          __syncwarp();
+#pragma unroll
+          for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = gl[o];
+          __syncwarp();
           // dW_l [H][H] += s_l (x) A_{l-1} + G_l (x) T_{l-1}: half-warps split the frames, 16 lanes x (TQ x TQ) entries
           const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
           float2 acc[TQ][TQ];
@@ -786,32 +791,126 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
             }
           }
         } else {
-          // dW_1 [H][d_r] += s_1 (x) r + G_1 (x) v: lanes (og, ig) with 4 x 12 entries, interleaved rows (bank skew)
-          constexpr int LPO = 32 / TQ;   // lanes per output group
-          const int og = lane / LPO, ig0 = lane - og * LPO;
-          const int nig = drp / 12;
-          for (int ig = ig0; ig < nig && og < TQ; ig += LPO) {
-            float2 acc[4][12];
+          // (s_1, scale G_1) of this frame for pass 2b:  dW_1 = sum_f s_1 (x) r + (scale G_1) (x) (v / scale)
+          float* sg = P.SG + ((size_t)n * 2 * H) * P.Bp + f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int i = 0; i < 12; ++i) acc[j][i] = make_float2(0.f, 0.f);
-            outer_tile<4, 12>(acc, Xr + og * RP, Rr + ig * RP, Xr + (H + og) * RP, Vr + ig * RP, TQ * RP, nig * RP, 0, 32);
-            // transpose through the (now dead) Z rows so that the fp64 reductions below are coalesced
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int i = 0; i < 12; ++i) {
-                const int o = j * TQ + og, col = i * nig + ig;
-                if (col < d_r) Zr[o * d_r + col] = acc[j][i].x + acc[j][i].y;
-              }
+          for (int o = 0; o < H; ++o) {
+            sg[(size_t)o * P.Bp] = sl[o];
+            sg[(size_t)(H + o) * P.Bp] = scale * gl[o];
           }
-          __syncwarp();
-          for (int e = lane; e < H * d_r; e += 32) atomicAdd(pn + P.gw_off[0] + e, (double)Zr[e]);
         }
       }
     }
   }
+}
+
+// Pass 2b:  dW_1[n] = sum_f s_1 (x) r + (scale G_1) (x) vhat,  vhat = J_r J_r^T u  -- a product over the frames with the
+// accumulators of one network's [H][d_r] block held in the registers of a warp for a run of tiles.  A warp owns one network
+// and every (warps-per-network)-th tile of the CTA; operand rows are staged in warp-private shared memory.
+template <int H>
+__global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, int wpn, double* __restrict__ part2) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ, FLUSH = 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int drp = P.d_rp, d_r = P.d_r, nig = drp / 12;
+  float* geo = sm;
+  const int rows_per_warp = 2 * drp + 2 * H;
+  float* Rr = geo + P.geo_floats + (size_t)warp * rows_per_warp * RP;
+  float* Vr = Rr + drp * RP;
+  float* Xr = Vr + drp * RP;
+  for (int i = tid; i < P.geo_floats; i += nt) geo[i] = P.img[(size_t)P.k * P.img_floats + i];
+  for (int i = tid; i < (nt >> 5) * rows_per_warp * RP; i += nt) geo[P.geo_floats + i] = 0.0f;
+  const int n = warp / wpn, slot = warp - n * wpn;
+  double* part = part2 + ((size_t)blockIdx.x * (nt >> 5) + warp) * (size_t)(H * d_r);
+  for (int i = lane; i < H * d_r; i += 32) part[i] = 0.0;
+  __syncthreads();
+  const int og = lane / LPO, ig = lane - og * LPO;
+  const bool active = og < TQ && ig < nig;
+  float2 acc[4][12];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[j][i] = make_float2(0.f, 0.f);
+  const long long n_tiles = P.Bp / 32;
+  const long long step = (long long)gridDim.x * wpn;
+  int since_flush = 0;
+  for (long long t = (long long)blockIdx.x * wpn + slot; t < n_tiles; t += step) {
+    const long long f = t * 32 + lane;
+    const float* Un = P.U + ((size_t)n * drp) * P.Bp + f;
+    const float* sg = P.SG + ((size_t)n * 2 * H) * P.Bp + f;
+    __syncwarp();
+#pragma unroll 6
+    for (int r = 0; r < d_r; ++r) cp_async4(Rr + r * RP + lane, P.Y + (size_t)r * P.Bp + f);
+#pragma unroll 6
+    for (int r = 0; r < d_r; ++r) cp_async4(Vr + r * RP + lane, Un + (size_t)r * P.Bp);
+#pragma unroll 8
+    for (int r = 0; r < 2 * H; ++r) cp_async4(Xr + r * RP + lane, sg + (size_t)r * P.Bp);
+    if (t + step < n_tiles) {
+      const long long tn = (t + step) * 32;
+      prefetch_rows(P.Y + tn, d_r, P.Bp, lane);
+      prefetch_rows(P.U + ((size_t)n * drp) * P.Bp + tn, d_r, P.Bp, lane);
+      prefetch_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + tn, 2 * H, P.Bp, lane);
+      if (P.kind == 1) prefetch_rows(P.JQ + ((size_t)n * 12) * P.Bp + tn, 12, P.Bp, lane);
+    }
+    if (P.kind == 1) {
+      const float* jq = P.JQ + ((size_t)n * 12) * P.Bp + f;
+      const cvf_v3 gm = v3(__ldg(jq), __ldg(jq + P.Bp), __ldg(jq + 2 * P.Bp));
+      const cvf_v3 q = v3(__ldg(jq + 3 * P.Bp), __ldg(jq + 4 * P.Bp), __ldg(jq + 5 * P.Bp));
+      const cvf_v3 dc = v3(__ldg(jq + 6 * P.Bp), __ldg(jq + 7 * P.Bp), __ldg(jq + 8 * P.Bp));
+      const cvf_v3 omv = v3(__ldg(jq + 9 * P.Bp), __ldg(jq + 10 * P.Bp), __ldg(jq + 11 * P.Bp));
+      cp_async_wait_all();
+#pragma unroll 2
+      for (int a = 0; a < P.n_atoms; ++a) {
+        const int r = 3 * a;
+        const cvf_v3 uu = v3(Vr[r * RP + lane], Vr[(r + 1) * RP + lane], Vr[(r + 2) * RP + lane]);
+        const cvf_v3 yv3 = v3(Rr[r * RP + lane], Rr[(r + 1) * RP + lane], Rr[(r + 2) * RP + lane]);
+        const cvf_v3 rf = v3(geo[r], geo[r + 1], geo[r + 2]);
+        const float ina = geo[drp + r];
+        const cvf_v3 gp = uu - ina * (gm + cross(rf, q));
+        const cvf_v3 vv = (gp - dc) + cross(omv, yv3);
+        Vr[r * RP + lane] = vv.x, Vr[(r + 1) * RP + lane] = vv.y, Vr[(r + 2) * RP + lane] = vv.z;
+      }
+    } else {
+      cp_async_wait_all();
+      for (int r = 0; r < d_r; ++r) Vr[r * RP + lane] *= geo[r];
+    }
+    __syncwarp();
+    if (active)
+      outer_tile<4, 12>(acc, Xr + og * RP, Rr + ig * RP, Xr + (H + og) * RP, Vr + ig * RP, TQ * RP, nig * RP, 0, 32);
+    if (++since_flush == FLUSH || t + step >= n_tiles) {
+      // fp32 partial sums of FLUSH * 32 frames -> this warp's fp64 partial block, transposed through the r rows so that the
+      // additions are coalesced (one owner per address: deterministic)
+      since_flush = 0;
+      __syncwarp();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const int o = j * TQ + og, col = i * nig + ig;
+            if (col < d_r) Rr[o * d_r + col] = acc[j][i].x + acc[j][i].y;
+            acc[j][i] = make_float2(0.f, 0.f);
+          }
+      }
+      __syncwarp();
+      for (int e = lane; e < H * d_r; e += 32) part[e] += (double)Rr[e];
+      __syncwarp();
+      // the pad rows of r (and of v) must read as zero in the next product
+      for (int e = lane; e < (drp - d_r) * RP; e += 32) Rr[d_r * RP + e] = 0.0f;
+    }
+  }
+}
+
+// grad_out[n][W1 block] += sum over the per-warp partial blocks of network n
+__global__ void dw1_reduce_kernel(const double* __restrict__ part2, int n_ctas, int warps_per_cta, int wpn, int block, int n_params,
+                                  int w1_off, double* __restrict__ grad_out) {
+  const int n = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= block) return;
+  double s = 0.0;
+  for (int c = 0; c < n_ctas; ++c)
+    for (int q = 0; q < wpn; ++q) s += part2[((size_t)c * warps_per_cta + n * wpn + q) * block + e];
+  grad_out[(size_t)n * n_params + w1_off + e] += s;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -822,11 +921,24 @@ struct Shape {
 static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int drp) {
   return ((size_t)k * img_floats + geo_floats + (size_t)drp * kP1Frames) * sizeof(float);
 }
-static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH) {
+static int pass2_rows_per_warp(int drp, int H, int NH) {
+  const int need = 2 * NH * H + 2 * H, stage = 2 * drp;
+  return need > stage ? need : stage;
+}
+static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH, int warps) {
   const int n_comb = 2 * k + k * k;
-  const int rows_per_warp = 2 * drp + 2 * NH * H + 2 * H;
   return ((size_t)k * img2_floats + geo_floats) * sizeof(float) + (size_t)(n_comb + (n_comb & 1)) * sizeof(double) +
-         (size_t)kP2Warps * rows_per_warp * kRowPad * sizeof(float);
+         (size_t)warps * pass2_rows_per_warp(drp, H, NH) * kRowPad * sizeof(float);
+}
+// most warps (<= 8) whose operand rows fit next to the weights; 0 if fewer than kP2MinWarps fit
+static int pass2_warps(int k, int img2_floats, int geo_floats, int drp, int H, int NH) {
+  for (int wv = kP2MaxWarps; wv >= kP2MinWarps; --wv)
+    if (pass2_smem_bytes(k, img2_floats, geo_floats, drp, H, NH, wv) <= (size_t)max_smem_optin()) return wv;
+  return 0;
+}
+static int dw1_warps_per_net(int k) { return k >= kP2MaxWarps ? 1 : kP2MaxWarps / k; }
+static size_t dw1_smem_bytes(int k, int geo_floats, int drp, int H) {
+  return ((size_t)geo_floats + (size_t)k * dw1_warps_per_net(k) * (2 * drp + 2 * H) * kRowPad) * sizeof(float);
 }
 // image sizes without the template (same arithmetic as Img<H, NH>)
 static int img2_floats_of(int H, int NH, int drp) { return drp * H + H + (NH - 1) * (H * H + H) + H + 4 + (NH - 1) * H * H; }
@@ -861,8 +973,10 @@ bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k) {
   if (d_r < 1) return false;
   const int drp = (d_r + 11) / 12 * 12, geo = fast::geo_floats_of(drp);
   const size_t cap = (size_t)max_smem_optin();
+  if (drp / 12 > 32 / (s.H / 4)) return false;   // pass 2b: one 12-column group of dW_1 per lane
   return fast::pass1_smem_bytes(k, fast::img_floats_of(s.H, s.NH, drp), geo, drp) <= cap &&
-         fast::pass2_smem_bytes(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) <= cap;
+         fast::pass2_warps(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) > 0 &&
+         fast::dw1_smem_bytes(k, geo, drp, s.H) <= cap;
 }
 
 namespace fast {
@@ -896,7 +1010,8 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
     return p;
   };
   const int n_part = k * np.n_params > 1 + 2 * k + k * k ? k * np.n_params : 1 + 2 * k + k * k;
-  P->part = (double*)take((size_t)sm_count() * kP2Warps * n_part * sizeof(double));
+  P->part = (double*)take((size_t)sm_count() * kP2MaxWarps * n_part * sizeof(double));
+  P->part2 = (double*)take((size_t)sm_count() * k * dw1_warps_per_net(k) * H * P->d_r * sizeof(double));
   P->img = (float*)take(((size_t)k * P->img_floats + P->geo_floats) * sizeof(float));
   P->Y = (float*)take((size_t)P->d_rp * P->Bp * sizeof(float));
   P->Kinv = (float*)take((size_t)6 * P->Bp * sizeof(float));
@@ -904,6 +1019,7 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   P->JQ = (float*)take((size_t)k * 12 * P->Bp * sizeof(float));
   P->Dq = (float*)take((size_t)k * P->Bp * sizeof(float));
   P->Ys = (float*)take((size_t)k * P->Bp * sizeof(float));
+  P->SG = (float*)take((size_t)k * 2 * H * P->Bp * sizeof(float));
   return off;
 }
 
@@ -971,19 +1087,32 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
     int e = run_forward<H, NH>(P, x, params, nullptr, stream);
     if (e) return e;
   }
-  const size_t smem2 = pass2_smem_bytes(k, P.img2_floats, P.geo_floats, P.d_rp, H, NH);
-  if (smem2 > (size_t)max_smem_optin()) {
-    set_error("fast eigen path: pass 2 needs %zu B of shared memory", smem2);
+  const int nw = pass2_warps(k, P.img2_floats, P.geo_floats, P.d_rp, H, NH);
+  if (nw == 0) {
+    set_error("fast eigen path: pass 2 does not fit shared memory");
     return CVF_E_UNSUPPORTED;
   }
+  const size_t smem2 = pass2_smem_bytes(k, P.img2_floats, P.geo_floats, P.d_rp, H, NH, nw);
   CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  long long grid = sm_count();
   const long long n_tiles = P.Bp / 32;
-  if ((n_tiles + kP2Warps - 1) / kP2Warps < grid) grid = (n_tiles + kP2Warps - 1) / kP2Warps;
-  pass2_kernel<H, NH><<<(int)grid, kP2Threads, smem2, stream>>>(P, w, combine);
+  long long grid = sm_count();
+  if ((n_tiles + nw - 1) / nw < grid) grid = (n_tiles + nw - 1) / nw;
+  pass2_kernel<H, NH><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH));
   CVF_CUDA(cudaGetLastError());
   const int n_part = k * np.n_params;
-  reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid * kP2Warps, n_part, 0, n_part, grad_out);
+  reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid * nw, n_part, 0, n_part, grad_out);
+  CVF_CUDA(cudaGetLastError());
+  // pass 2b: the first layer's weight gradient
+  const int wpn = dw1_warps_per_net(k), warps_b = k * wpn;
+  const size_t smem3 = dw1_smem_bytes(k, P.geo_floats, P.d_rp, H);
+  CVF_CUDA(cudaFuncSetAttribute(dw1_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+  long long grid_b = sm_count();
+  if ((n_tiles + wpn - 1) / wpn < grid_b) grid_b = (n_tiles + wpn - 1) / wpn;
+  dw1_kernel<H><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, wpn, P.part2);
+  CVF_CUDA(cudaGetLastError());
+  const int block = H * P.d_r;
+  dw1_reduce_kernel<<<dim3((block + 127) / 128, k), 128, 0, stream>>>(P.part2, (int)grid_b, warps_b, wpn, block, np.n_params,
+                                                                      np.gw_off[0], grad_out);
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
