@@ -49,6 +49,10 @@ SYMBOLS = {
     "cvf_ae_workspace_bytes": (_SZ, [C.POINTER(Mlp)]),
     "cvf_ae_step": (C.c_int, [_P, _P, _I64, C.POINTER(Mlp), _P, _P, _P, _P, _SZ, _P]),
     "cvf_fma_probe": (C.c_int, [_P, _I32, C.POINTER(_D), _P]),
+    "cvf_profile_enable": (C.c_int, [_I32]),
+    "cvf_profile_num_kernels": (_I32, []),
+    "cvf_profile_kernel_name": (C.c_char_p, [_I32]),
+    "cvf_profile_read": (C.c_int, [C.POINTER(_D), C.POINTER(_I64), C.POINTER(_I64), _I32]),
 }
 
 _lib = None
@@ -74,6 +78,15 @@ def check(code: int, what: str):
     if code != 0:
         msg = lib().cvf_last_error_string().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {code}): {msg}")
+
+
+def profile_read(reset=True):
+    """{kernel name: (summed ms of timed launches, timed launches, launches since last reset)} from the library's accounting."""
+    L = lib()
+    n = L.cvf_profile_num_kernels()
+    ms, timed, launches = (_D * n)(), (_I64 * n)(), (_I64 * n)()
+    check(L.cvf_profile_read(ms, timed, launches, 1 if reset else 0), "cvf_profile_read")
+    return {L.cvf_profile_kernel_name(i).decode(): (ms[i], int(timed[i]), int(launches[i])) for i in range(n)}
 
 
 def make_mlp(dims, acts) -> Mlp:

@@ -261,8 +261,8 @@ class EigenContext:
                                              C.byref(self.mlp), self.k, self.flat.flat.data_ptr(), y.data_ptr(),
                                              comb.data_ptr(), g.data_ptr(), ws, self.ws_bytes, valid, _stream()),
                    "cvf_eigen_grad")
-        if not valid:
-            self._scratch_key = self._key(X, weight)   # pass 2 refreshed the scratch for these tensors
+        # pass 2 consumes the scratch (it leaves v = J J^T u where pass 1 left u): a second backward recomputes it
+        self._scratch_key = None
         return g
 
 

@@ -246,17 +246,17 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
   }
   if (grad) {
     CVF_CUDA(cudaFuncSetAttribute(ae_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    ae_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
+    CVF_LAUNCH(K_AE_STEP, stream, ae_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace));
   } else {
     CVF_CUDA(cudaFuncSetAttribute(ae_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    ae_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace);
+    CVF_LAUNCH(K_AE_STEP, stream, ae_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace));
   }
   CVF_CUDA(cudaGetLastError());
   // partial layout per CTA: [sum w|e|^2, sum w, grad...]; two reductions keep the output buffers separate
-  reduce_partials_kernel<<<1, 32, 0, stream>>>((const double*)workspace, grid, n_part, 0, 2, sums_out);
+  CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<1, 32, 0, stream>>>((const double*)workspace, grid, n_part, 0, 2, sums_out));
   if (grad)
-    reduce_partials_kernel<<<(P.net.n_params + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 2,
-                                                                             P.net.n_params, grad_out);
+    CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(P.net.n_params + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 2,
+                                                                             P.net.n_params, grad_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -311,13 +311,13 @@ extern "C" int cvf_align_fwd(const float* x, int64_t B, int32_t n_atoms, const i
     if (n_tiles < grid) grid = n_tiles;
     // frames are 16-byte aligned in global memory iff the base is and tile_f * 12 N is a multiple of 16 (tile_f % 4 == 0)
     const int use_tma = (((uintptr_t)x | (uintptr_t)y_out) & 15) == 0 ? 1 : 0;
-    align_tile_kernel<<<(int)grid, tile_f, smem, stream>>>(x, B, n_atoms, align_idx, n_align, ref_centred, y_out, R_out, c_out,
-                                                          tile_f, use_tma);
+    CVF_LAUNCH(K_ALIGN, stream, align_tile_kernel<<<(int)grid, tile_f, smem, stream>>>(x, B, n_atoms, align_idx, n_align, ref_centred, y_out, R_out, c_out,
+                                                          tile_f, use_tma));
   } else {
     long long grid = (long long)sm_count() * 8;
     const long long need = (B + 7) / 8;
     if (need < grid) grid = need;
-    align_warp_kernel<<<(int)grid, 256, 0, stream>>>(x, B, n_atoms, align_idx, n_align, ref_centred, y_out, R_out, c_out);
+    CVF_LAUNCH(K_ALIGN, stream, align_warp_kernel<<<(int)grid, 256, 0, stream>>>(x, B, n_atoms, align_idx, n_align, ref_centred, y_out, R_out, c_out));
   }
   CVF_CUDA(cudaGetLastError());
   return 0;
@@ -352,7 +352,7 @@ extern "C" int cvf_features_fwd(const float* x, int64_t B, const cvf_preproc* pp
   const int per_sm = (int)((size_t)max_smem_optin() / (smem + 1024));
   long long grid = (long long)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
   if (n_tiles < grid) grid = n_tiles;
-  features_kernel<<<(int)grid, nt, smem, stream>>>(P, x, B, r_out);
+  CVF_LAUNCH(K_FEATURES, stream, features_kernel<<<(int)grid, nt, smem, stream>>>(P, x, B, r_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -34,12 +34,67 @@ static int device_attr(int* cache, cudaDeviceAttr attr, int fallback) {
   return cache[dev];
 }
 
+// ---- launch accounting -------------------------------------------------------------------------------------
+static const char* const g_kernel_names[K_COUNT] = {
+    "align_fwd", "features_fwd", "eigen_stats(general)", "eigen_grad(general)", "eigen_combine", "reduce_partials", "ae_step",
+    "fast_pack", "fast_prep", "fast_pass1", "fast_stats", "fast_pass2a", "fast_pass2b(dW1)", "fma_probe"};
+static long long g_launches[K_COUNT];
+static int g_prof_on = 0;
+struct ProfRec {
+  int id;
+  cudaEvent_t e0, e1;
+};
+static ProfRec g_recs[4096];
+static int g_n_recs = 0;
+
+void prof_begin(int id, cudaStream_t stream) {
+  ++g_launches[id];
+  if (!g_prof_on || g_n_recs >= 4096) return;
+  ProfRec& r = g_recs[g_n_recs];
+  r.id = id;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, stream);
+}
+void prof_end(int id, cudaStream_t stream) {
+  if (!g_prof_on || g_n_recs >= 4096 || g_recs[g_n_recs].id != id) return;
+  cudaEventRecord(g_recs[g_n_recs].e1, stream);
+  ++g_n_recs;
+}
+
 int sm_count() { return device_attr(g_sms, cudaDevAttrMultiProcessorCount, 148); }
 int max_smem_optin() { return device_attr(g_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, 232448); }
 
 }  // namespace cvf
 
 extern "C" int cvf_version(void) { return CVF_VERSION; }
+
+extern "C" int cvf_profile_enable(int32_t on) {
+  cvf::g_prof_on = on ? 1 : 0;
+  return 0;
+}
+extern "C" int32_t cvf_profile_num_kernels(void) { return cvf::K_COUNT; }
+extern "C" const char* cvf_profile_kernel_name(int32_t id) { return id >= 0 && id < cvf::K_COUNT ? cvf::g_kernel_names[id] : ""; }
+extern "C" int cvf_profile_read(double* ms_out, int64_t* timed_out, int64_t* launches_out, int32_t reset) {
+  using namespace cvf;
+  if (!ms_out || !timed_out || !launches_out) {
+    set_error("cvf_profile_read: null pointer");
+    return CVF_E_ARG;
+  }
+  for (int i = 0; i < K_COUNT; ++i) ms_out[i] = 0.0, timed_out[i] = 0, launches_out[i] = g_launches[i];
+  for (int i = 0; i < g_n_recs; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_recs[i].e1) == cudaSuccess && cudaEventElapsedTime(&ms, g_recs[i].e0, g_recs[i].e1) == cudaSuccess) {
+      ms_out[g_recs[i].id] += ms;
+      ++timed_out[g_recs[i].id];
+    }
+    cudaEventDestroy(g_recs[i].e0);
+    cudaEventDestroy(g_recs[i].e1);
+  }
+  g_n_recs = 0;
+  if (reset)
+    for (int i = 0; i < K_COUNT; ++i) g_launches[i] = 0;
+  return 0;
+}
 extern "C" const char* cvf_last_error_string(void) { return cvf::g_err; }
 
 extern "C" int64_t cvf_mlp_param_count(const cvf_mlp* net) {
@@ -72,7 +127,7 @@ extern "C" int cvf_fma_probe(float* sink, int32_t iters, double* flops_out, void
     return CVF_E_ARG;
   }
   const int grid = cvf::sm_count() * 8;
-  cvf::fma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+  CVF_LAUNCH(cvf::K_FMA_PROBE, (cudaStream_t)stream, cvf::fma_probe_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sink, iters));
   *flops_out = 2.0 * 16.0 * (double)iters * 256.0 * (double)grid;
   CVF_CUDA(cudaGetLastError());
   return 0;

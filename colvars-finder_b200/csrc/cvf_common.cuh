@@ -31,6 +31,21 @@ int max_smem_optin();
     if (_e) return _e;                                   \
   } while (0)
 
+// Launch accounting (cvf_api.cu): every kernel launch of the library goes through CVF_LAUNCH, which counts it and, while
+// profiling is switched on with cvf_profile_enable(1), brackets it with CUDA events on the launching stream.
+enum KernelId {
+  K_ALIGN = 0, K_FEATURES, K_EIGEN_STATS, K_EIGEN_GRAD, K_EIGEN_COMBINE, K_REDUCE, K_AE_STEP, K_FAST_PACK, K_FAST_PREP,
+  K_FAST_PASS1, K_FAST_STATS, K_FAST_PASS2A, K_FAST_PASS2B, K_FMA_PROBE, K_COUNT
+};
+void prof_begin(int id, cudaStream_t stream);
+void prof_end(int id, cudaStream_t stream);
+#define CVF_LAUNCH(id, stream, ...)   \
+  do {                                \
+    cvf::prof_begin((id), (stream));  \
+    __VA_ARGS__;                      \
+    cvf::prof_end((id), (stream));    \
+  } while (0)
+
 constexpr int kMaxLayers = CVF_MAX_LAYERS;
 constexpr int kMaxK = CVF_MAX_K;
 

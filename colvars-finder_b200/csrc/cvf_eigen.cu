@@ -853,13 +853,13 @@ static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, co
   }
   if (grad) {
     CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    eigen_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
+    CVF_LAUNCH(K_EIGEN_GRAD, stream, eigen_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace));
   } else {
     CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    eigen_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace);
+    CVF_LAUNCH(K_EIGEN_STATS, stream, eigen_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace));
   }
   CVF_CUDA(cudaGetLastError());
-  reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 0, n_part, out);
+  CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 0, n_part, out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -926,7 +926,7 @@ extern "C" int cvf_eigen_combine(const double* stats, int32_t k, double alpha, c
   }
   EigW ew;   // eig_w is a HOST array: it travels by value as a kernel parameter
   for (int i = 0; i < kMaxK; ++i) ew.v[i] = i < k ? eig_w[i] : 0.0;
-  eigen_combine_kernel<<<1, 32, 0, stream>>>(stats, k, alpha, beta, sort, ew, combine_out);
+  CVF_LAUNCH(K_EIGEN_COMBINE, stream, eigen_combine_kernel<<<1, 32, 0, stream>>>(stats, k, alpha, beta, sort, ew, combine_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }

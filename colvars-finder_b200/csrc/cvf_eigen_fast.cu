@@ -28,6 +28,7 @@ namespace cvf {
 namespace fast {
 
 typedef unsigned long long u64;
+constexpr int kRowPad = 36;   // floats per 32-frame row of the pass-2 operand rows (16-byte aligned, bank-group skew 1 per row)
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   u64 d;
@@ -42,14 +43,31 @@ __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cas
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+// 16-byte variant (bypasses L1): a 4-byte LDGSTS costs as much issue / shared-memory time as a 16-byte one
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// warp-cooperative staging of `nrows` frame-minor row segments (32 frames = 128 B each) into padded shared-memory rows:
+// lane -> (row mod 4, 16-byte chunk); `src` points at the first frame of the tile in row 0
+__device__ __forceinline__ void stage_rows(float* dst, const float* src, int nrows, long long Bp, int lane) {
+  const int c4 = 4 * (lane & 7);
+#pragma unroll 4
+  for (int r = lane >> 3; r < nrows; r += 4) cp_async16(dst + r * kRowPad + c4, src + (size_t)r * Bp + c4);
+}
+// the reverse: padded shared-memory rows -> frame-minor global rows, 16 bytes per lane
+__device__ __forceinline__ void store_rows(float* dst, const float* src, int nrows, long long Bp, int lane) {
+  const int c4 = 4 * (lane & 7);
+#pragma unroll 4
+  for (int r = lane >> 3; r < nrows; r += 4)
+    *reinterpret_cast<float4*>(dst + (size_t)r * Bp + c4) = *reinterpret_cast<const float4*>(src + r * kRowPad + c4);
+}
 __device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // warp prefetch of `nrows` row segments (one 128-byte line each: 32 frames of a frame-minor row)
 __device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long long Bp, int lane) {
   for (int r = lane; r < nrows; r += 32) prefetch_l2_line(base + (size_t)r * Bp);
 }
 
-constexpr int kRowPad = 36;   // floats per 32-frame row of the pass-2 operand rows (16-byte aligned, bank-group skew 1 per row)
 constexpr int kP1Frames = 512, kP1Threads = 256;
 constexpr int kP2MaxWarps = 8, kP2MinWarps = 4;
 
@@ -517,24 +535,28 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
     for (int j = 0; j < TO; ++j) x[j] = ld4(Xa + j * strideX + f);
 #pragma unroll
     for (int i = 0; i < TI; ++i) z[i] = ld4(Za + i * strideZ + f);
+    // every accumulator is touched once per sweep: dependent FFMA2s are TO * TI instructions apart
 #pragma unroll
     for (int j = 0; j < TO; ++j)
 #pragma unroll
-      for (int i = 0; i < TI; ++i) {
-        acc[j][i] = ffma2(make_float2(x[j].x, x[j].y), make_float2(z[i].x, z[i].y), acc[j][i]);
-        acc[j][i] = ffma2(make_float2(x[j].z, x[j].w), make_float2(z[i].z, z[i].w), acc[j][i]);
-      }
+      for (int i = 0; i < TI; ++i) acc[j][i] = ffma2(make_float2(x[j].x, x[j].y), make_float2(z[i].x, z[i].y), acc[j][i]);
+#pragma unroll
+    for (int j = 0; j < TO; ++j)
+#pragma unroll
+      for (int i = 0; i < TI; ++i) acc[j][i] = ffma2(make_float2(x[j].z, x[j].w), make_float2(z[i].z, z[i].w), acc[j][i]);
 #pragma unroll
     for (int j = 0; j < TO; ++j) x[j] = ld4(Xb + j * strideX + f);
 #pragma unroll
     for (int i = 0; i < TI; ++i) z[i] = ld4(Zb + i * strideZ + f);
+    // every accumulator is touched once per sweep: dependent FFMA2s are TO * TI instructions apart
 #pragma unroll
     for (int j = 0; j < TO; ++j)
 #pragma unroll
-      for (int i = 0; i < TI; ++i) {
-        acc[j][i] = ffma2(make_float2(x[j].x, x[j].y), make_float2(z[i].x, z[i].y), acc[j][i]);
-        acc[j][i] = ffma2(make_float2(x[j].z, x[j].w), make_float2(z[i].z, z[i].w), acc[j][i]);
-      }
+      for (int i = 0; i < TI; ++i) acc[j][i] = ffma2(make_float2(x[j].x, x[j].y), make_float2(z[i].x, z[i].y), acc[j][i]);
+#pragma unroll
+    for (int j = 0; j < TO; ++j)
+#pragma unroll
+      for (int i = 0; i < TI; ++i) acc[j][i] = ffma2(make_float2(x[j].z, x[j].w), make_float2(z[i].z, z[i].w), acc[j][i]);
   }
 }
 
@@ -583,12 +605,10 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
     for (int n = 0; n < k; ++n) {
       const float* W = wsm + n * P.img2_floats;
       double* pn = part + (size_t)n * P.n_params;
-      const float* Un = P.U + ((size_t)n * drp) * P.Bp + f;
+      float* Ut = P.U + ((size_t)n * drp) * P.Bp + t * 32;
       __syncwarp();   // the previous network's flush has finished reading the X rows
-#pragma unroll 6
-      for (int r = 0; r < d_r; ++r) cp_async4(Sr + r * RP + lane, P.Y + (size_t)r * P.Bp + f);
-#pragma unroll 6
-      for (int r = 0; r < d_r; ++r) cp_async4(Su + r * RP + lane, Un + (size_t)r * P.Bp);
+      stage_rows(Sr, P.Y + t * 32, d_r, P.Bp, lane);
+      stage_rows(Su, Ut, d_r, P.Bp, lane);
       // L2 prefetch of what is read next: the next network's u rows, or the next tile's r rows and first u rows
       if (n + 1 < k) {
         prefetch_rows(P.U + ((size_t)(n + 1) * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
@@ -618,6 +638,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         const cvf_v3 dc = v3(__ldg(jq + 6 * P.Bp), __ldg(jq + 7 * P.Bp), __ldg(jq + 8 * P.Bp));
         const cvf_v3 omv = v3(__ldg(jq + 9 * P.Bp), __ldg(jq + 10 * P.Bp), __ldg(jq + 11 * P.Bp));
         cp_async_wait_all();
+        __syncwarp();
 #pragma unroll 2
         for (int a = 0; a < P.n_atoms; ++a) {
           const int r = 3 * a;
@@ -626,7 +647,9 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           const cvf_v3 rf = v3(geo[r], geo[r + 1], geo[r + 2]);
           const float ina = geo[drp + r];
           const cvf_v3 gp = uu - ina * (gm + cross(rf, q));
-          const cvf_v3 vv = scale * ((gp - dc) + cross(omv, yv3));
+          const cvf_v3 vh = (gp - dc) + cross(omv, yv3);   // vhat = J_r J_r^T u, kept for pass 2b in place of u
+          Su[r * RP + lane] = vh.x, Su[(r + 1) * RP + lane] = vh.y, Su[(r + 2) * RP + lane] = vh.z;
+          const cvf_v3 vv = scale * vh;
           const float xin[3] = {yv3.x, yv3.y, yv3.z}, vin[3] = {vv.x, vv.y, vv.z};
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
@@ -644,10 +667,13 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         }
       } else {
         cp_async_wait_all();
+        __syncwarp();
 #pragma unroll 2
         for (int r = 0; r < d_r; ++r) {
           const float xin = Sr[r * RP + lane];
-          const float vin = scale * geo[r] * Su[r * RP + lane];
+          const float vh = geo[r] * Su[r * RP + lane];
+          Su[r * RP + lane] = vh;
+          const float vin = scale * vh;
           const float2 x0 = dup(xin), x1 = dup(vin);
           const float* wr = W + r * H;
 #pragma unroll
@@ -660,6 +686,9 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           }
         }
       }
+      // vhat rows -> global memory (in place of u), 16 bytes per lane, before the Z rows take over the staging area
+      __syncwarp();
+      store_rows(Ut, Su, d_r, P.Bp, lane);
       float a[H], tg[H];   // A_l, T_l = (1 - A_l^2) zdot_l of the current layer
 #pragma unroll
       for (int j = 0; j < HP; ++j) {
@@ -667,6 +696,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         tg[2 * j] = fmaf(-a[2 * j], a[2 * j], 1.0f) * zd[j].x;
         tg[2 * j + 1] = fmaf(-a[2 * j + 1], a[2 * j + 1], 1.0f) * zd[j].y;
       }
+      __syncwarp();
 #pragma unroll
       for (int o = 0; o < H; ++o) Zr[o * RP + lane] = a[o], Zr[(H + o) * RP + lane] = tg[o];
 #pragma unroll
@@ -792,35 +822,53 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           }
         } else {
           // (s_1, scale G_1) of this frame for pass 2b:  dW_1 = sum_f s_1 (x) r + (scale G_1) (x) (v / scale)
-          float* sg = P.SG + ((size_t)n * 2 * H) * P.Bp + f;
+          __syncwarp();
 #pragma unroll
-          for (int o = 0; o < H; ++o) {
-            sg[(size_t)o * P.Bp] = sl[o];
-            sg[(size_t)(H + o) * P.Bp] = scale * gl[o];
-          }
+          for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = scale * gl[o];
+          __syncwarp();
+          store_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, Xr, 2 * H, P.Bp, lane);
         }
       }
     }
   }
+  // fold the warps' fp64 partial vectors into the first one (fixed order: deterministic), so that the final reduction
+  // reads one vector per CTA
+  __syncthreads();
+  double* cta_part = P.part + (size_t)blockIdx.x * nw * n_part;
+  for (int i = tid; i < n_part; i += nt) {
+    double sacc = 0.0;
+    for (int q = 0; q < nw; ++q) sacc += __ldcg(cta_part + (size_t)q * n_part + i);
+    cta_part[i] = sacc;
+  }
 }
 
-// Pass 2b:  dW_1[n] = sum_f s_1 (x) r + (scale G_1) (x) vhat,  vhat = J_r J_r^T u  -- a product over the frames with the
-// accumulators of one network's [H][d_r] block held in the registers of a warp for a run of tiles.  A warp owns one network
-// and every (warps-per-network)-th tile of the CTA; operand rows are staged in warp-private shared memory.
+// Pass 2b:  dW_1[n] = sum_f s_1 (x) r + (scale G_1) (x) vhat  -- a product over the frames with the accumulators of one
+// network's [H][d_r] block held in the registers of a warp for a run of tiles.  The CTA's warps are dealt out to the networks
+// (the first `rem` networks get base + 1 warps, the others base); a warp takes every wpn-th tile of its CTA and stages the
+// operand rows (r, vhat left by pass 2a in place of u, s_1 | scale G_1) in warp-private shared memory.
+__host__ __device__ inline void dw1_warp_role(int warp, int base, int rem, int* n, int* slot, int* wpn) {
+  const int cut = rem * (base + 1);
+  if (warp < cut) {
+    *n = warp / (base + 1), *slot = warp - *n * (base + 1), *wpn = base + 1;
+  } else {
+    const int w2 = warp - cut;
+    *n = rem + w2 / base, *slot = w2 - (w2 / base) * base, *wpn = base;
+  }
+}
+
 template <int H>
-__global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, int wpn, double* __restrict__ part2) {
+__global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, int base, int rem, double* __restrict__ part2) {
   extern __shared__ __align__(16) float sm[];
   constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ, FLUSH = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
   const int drp = P.d_rp, d_r = P.d_r, nig = drp / 12;
-  float* geo = sm;
   const int rows_per_warp = 2 * drp + 2 * H;
-  float* Rr = geo + P.geo_floats + (size_t)warp * rows_per_warp * RP;
+  float* Rr = sm + (size_t)warp * rows_per_warp * RP;
   float* Vr = Rr + drp * RP;
   float* Xr = Vr + drp * RP;
-  for (int i = tid; i < P.geo_floats; i += nt) geo[i] = P.img[(size_t)P.k * P.img_floats + i];
-  for (int i = tid; i < (nt >> 5) * rows_per_warp * RP; i += nt) geo[P.geo_floats + i] = 0.0f;
-  const int n = warp / wpn, slot = warp - n * wpn;
+  for (int i = tid; i < (nt >> 5) * rows_per_warp * RP; i += nt) sm[i] = 0.0f;
+  int n, slot, wpn;
+  dw1_warp_role(warp, base, rem, &n, &slot, &wpn);
   double* part = part2 + ((size_t)blockIdx.x * (nt >> 5) + warp) * (size_t)(H * d_r);
   for (int i = lane; i < H * d_r; i += 32) part[i] = 0.0;
   __syncthreads();
@@ -835,45 +883,17 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, int wpn, 
   const long long step = (long long)gridDim.x * wpn;
   int since_flush = 0;
   for (long long t = (long long)blockIdx.x * wpn + slot; t < n_tiles; t += step) {
-    const long long f = t * 32 + lane;
-    const float* Un = P.U + ((size_t)n * drp) * P.Bp + f;
-    const float* sg = P.SG + ((size_t)n * 2 * H) * P.Bp + f;
     __syncwarp();
-#pragma unroll 6
-    for (int r = 0; r < d_r; ++r) cp_async4(Rr + r * RP + lane, P.Y + (size_t)r * P.Bp + f);
-#pragma unroll 6
-    for (int r = 0; r < d_r; ++r) cp_async4(Vr + r * RP + lane, Un + (size_t)r * P.Bp);
-#pragma unroll 8
-    for (int r = 0; r < 2 * H; ++r) cp_async4(Xr + r * RP + lane, sg + (size_t)r * P.Bp);
+    stage_rows(Rr, P.Y + t * 32, d_r, P.Bp, lane);
+    stage_rows(Vr, P.U + ((size_t)n * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
+    stage_rows(Xr, P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, 2 * H, P.Bp, lane);
     if (t + step < n_tiles) {
       const long long tn = (t + step) * 32;
       prefetch_rows(P.Y + tn, d_r, P.Bp, lane);
       prefetch_rows(P.U + ((size_t)n * drp) * P.Bp + tn, d_r, P.Bp, lane);
       prefetch_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + tn, 2 * H, P.Bp, lane);
-      if (P.kind == 1) prefetch_rows(P.JQ + ((size_t)n * 12) * P.Bp + tn, 12, P.Bp, lane);
     }
-    if (P.kind == 1) {
-      const float* jq = P.JQ + ((size_t)n * 12) * P.Bp + f;
-      const cvf_v3 gm = v3(__ldg(jq), __ldg(jq + P.Bp), __ldg(jq + 2 * P.Bp));
-      const cvf_v3 q = v3(__ldg(jq + 3 * P.Bp), __ldg(jq + 4 * P.Bp), __ldg(jq + 5 * P.Bp));
-      const cvf_v3 dc = v3(__ldg(jq + 6 * P.Bp), __ldg(jq + 7 * P.Bp), __ldg(jq + 8 * P.Bp));
-      const cvf_v3 omv = v3(__ldg(jq + 9 * P.Bp), __ldg(jq + 10 * P.Bp), __ldg(jq + 11 * P.Bp));
-      cp_async_wait_all();
-#pragma unroll 2
-      for (int a = 0; a < P.n_atoms; ++a) {
-        const int r = 3 * a;
-        const cvf_v3 uu = v3(Vr[r * RP + lane], Vr[(r + 1) * RP + lane], Vr[(r + 2) * RP + lane]);
-        const cvf_v3 yv3 = v3(Rr[r * RP + lane], Rr[(r + 1) * RP + lane], Rr[(r + 2) * RP + lane]);
-        const cvf_v3 rf = v3(geo[r], geo[r + 1], geo[r + 2]);
-        const float ina = geo[drp + r];
-        const cvf_v3 gp = uu - ina * (gm + cross(rf, q));
-        const cvf_v3 vv = (gp - dc) + cross(omv, yv3);
-        Vr[r * RP + lane] = vv.x, Vr[(r + 1) * RP + lane] = vv.y, Vr[(r + 2) * RP + lane] = vv.z;
-      }
-    } else {
-      cp_async_wait_all();
-      for (int r = 0; r < d_r; ++r) Vr[r * RP + lane] *= geo[r];
-    }
+    cp_async_wait_all();
     __syncwarp();
     if (active)
       outer_tile<4, 12>(acc, Xr + og * RP, Rr + ig * RP, Xr + (H + og) * RP, Vr + ig * RP, TQ * RP, nig * RP, 0, 32);
@@ -894,22 +914,34 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, int wpn, 
       }
       __syncwarp();
       for (int e = lane; e < H * d_r; e += 32) part[e] += (double)Rr[e];
-      __syncwarp();
-      // the pad rows of r (and of v) must read as zero in the next product
-      for (int e = lane; e < (drp - d_r) * RP; e += 32) Rr[d_r * RP + e] = 0.0f;
+    }
+  }
+  // fold the blocks of the warps that share a network into the first of them
+  __syncthreads();
+  {
+    const int nwarps = nt >> 5, blk = H * d_r;
+    double* cta = part2 + (size_t)blockIdx.x * nwarps * blk;
+    for (int net = 0; net < P.k; ++net) {
+      const int cnt = net < rem ? base + 1 : base;
+      const int w0 = net < rem ? net * (base + 1) : rem * (base + 1) + (net - rem) * base;
+      for (int e = tid; e < blk; e += nt) {
+        double sacc = 0.0;
+        for (int q = 0; q < cnt; ++q) sacc += __ldcg(cta + (size_t)(w0 + q) * blk + e);
+        cta[(size_t)w0 * blk + e] = sacc;
+      }
     }
   }
 }
 
 // grad_out[n][W1 block] += sum over the per-warp partial blocks of network n
-__global__ void dw1_reduce_kernel(const double* __restrict__ part2, int n_ctas, int warps_per_cta, int wpn, int block, int n_params,
-                                  int w1_off, double* __restrict__ grad_out) {
+__global__ void dw1_reduce_kernel(const double* __restrict__ part2, int n_ctas, int warps_per_cta, int base, int rem, int block,
+                                  int n_params, int w1_off, double* __restrict__ grad_out) {
   const int n = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= block) return;
+  const int w0 = n < rem ? n * (base + 1) : rem * (base + 1) + (n - rem) * base;
   double s = 0.0;
-  for (int c = 0; c < n_ctas; ++c)
-    for (int q = 0; q < wpn; ++q) s += part2[((size_t)c * warps_per_cta + n * wpn + q) * block + e];
+  for (int c = 0; c < n_ctas; ++c) s += part2[((size_t)c * warps_per_cta + w0) * block + e];   // folded per CTA by dw1_kernel
   grad_out[(size_t)n * n_params + w1_off + e] += s;
 }
 
@@ -936,9 +968,12 @@ static int pass2_warps(int k, int img2_floats, int geo_floats, int drp, int H, i
     if (pass2_smem_bytes(k, img2_floats, geo_floats, drp, H, NH, wv) <= (size_t)max_smem_optin()) return wv;
   return 0;
 }
-static int dw1_warps_per_net(int k) { return k >= kP2MaxWarps ? 1 : kP2MaxWarps / k; }
-static size_t dw1_smem_bytes(int k, int geo_floats, int drp, int H) {
-  return ((size_t)geo_floats + (size_t)k * dw1_warps_per_net(k) * (2 * drp + 2 * H) * kRowPad) * sizeof(float);
+static size_t dw1_smem_bytes(int warps, int drp, int H) { return (size_t)warps * (2 * drp + 2 * H) * kRowPad * sizeof(float); }
+// warps of a pass-2b CTA: as many as fit (<= 8), at least one per network; 0 if they do not fit
+static int dw1_warps(int k, int drp, int H) {
+  for (int wv = kP2MaxWarps; wv >= k; --wv)
+    if (dw1_smem_bytes(wv, drp, H) <= (size_t)max_smem_optin()) return wv;
+  return 0;
 }
 // image sizes without the template (same arithmetic as Img<H, NH>)
 static int img2_floats_of(int H, int NH, int drp) { return drp * H + H + (NH - 1) * (H * H + H) + H + 4 + (NH - 1) * H * H; }
@@ -976,7 +1011,7 @@ bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k) {
   if (drp / 12 > 32 / (s.H / 4)) return false;   // pass 2b: one 12-column group of dW_1 per lane
   return fast::pass1_smem_bytes(k, fast::img_floats_of(s.H, s.NH, drp), geo, drp) <= cap &&
          fast::pass2_warps(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) > 0 &&
-         fast::dw1_smem_bytes(k, geo, drp, s.H) <= cap;
+         fast::dw1_warps(k, drp, s.H) > 0;
 }
 
 namespace fast {
@@ -1011,7 +1046,7 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   };
   const int n_part = k * np.n_params > 1 + 2 * k + k * k ? k * np.n_params : 1 + 2 * k + k * k;
   P->part = (double*)take((size_t)sm_count() * kP2MaxWarps * n_part * sizeof(double));
-  P->part2 = (double*)take((size_t)sm_count() * k * dw1_warps_per_net(k) * H * P->d_r * sizeof(double));
+  P->part2 = (double*)take((size_t)sm_count() * kP2MaxWarps * H * P->d_r * sizeof(double));
   P->img = (float*)take(((size_t)k * P->img_floats + P->geo_floats) * sizeof(float));
   P->Y = (float*)take((size_t)P->d_rp * P->Bp * sizeof(float));
   P->Kinv = (float*)take((size_t)6 * P->Bp * sizeof(float));
@@ -1025,18 +1060,18 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
 
 template <int H, int NH>
 static int run_forward(const FastPlan& P, const float* x, const float* params, float* y_out, cudaStream_t stream) {
-  pack_kernel<H, NH><<<P.k + 1, 256, 0, stream>>>(P, params);
+  CVF_LAUNCH(K_FAST_PACK, stream, pack_kernel<H, NH><<<P.k + 1, 256, 0, stream>>>(P, params));
   CVF_CUDA(cudaGetLastError());
   if (P.kind == 1) {
     const size_t smem = (size_t)(128 * ((3 * P.n_atoms) | 1) + 6 * 128) * sizeof(float);
     CVF_CUDA(cudaFuncSetAttribute(prep_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)sm_count() * 4;
     if (P.Bp / 128 < grid) grid = P.Bp / 128;
-    prep_align_kernel<<<(int)grid, 128, smem, stream>>>(P, x);
+    CVF_LAUNCH(K_FAST_PREP, stream, prep_align_kernel<<<(int)grid, 128, smem, stream>>>(P, x));
   } else {
     long long grid = (long long)sm_count() * 8;
     if ((P.Bp + 255) / 256 < grid) grid = (P.Bp + 255) / 256;
-    prep_transpose_kernel<<<(int)grid, 256, 0, stream>>>(P, x);
+    CVF_LAUNCH(K_FAST_PREP, stream, prep_transpose_kernel<<<(int)grid, 256, 0, stream>>>(P, x));
   }
   CVF_CUDA(cudaGetLastError());
   const size_t smem1 = pass1_smem_bytes(P.k, P.img_floats, P.geo_floats, P.d_rp);
@@ -1047,7 +1082,7 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
   CVF_CUDA(cudaFuncSetAttribute(pass1_kernel<H, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   long long grid = sm_count();
   if (P.Bp / kP1Frames < grid) grid = P.Bp / kP1Frames;
-  pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out);
+  CVF_LAUNCH(K_FAST_PASS1, stream, pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1066,9 +1101,9 @@ static int run_stats(const cvf_preproc* pp, const NetPlan& np, int k, const floa
   const int ns = 1 + 2 * k + k * k;
   long long grid = (long long)sm_count() * 2;
   if ((B + 255) / 256 < grid) grid = (B + 255) / 256;
-  stats_kernel<<<(int)grid, 256, 0, stream>>>(P, w, P.part);
+  CVF_LAUNCH(K_FAST_STATS, stream, stats_kernel<<<(int)grid, 256, 0, stream>>>(P, w, P.part));
   CVF_CUDA(cudaGetLastError());
-  reduce_partials_kernel<<<(ns + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, ns, 0, ns, stats_out);
+  CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(ns + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, ns, 0, ns, stats_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1097,22 +1132,22 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   const long long n_tiles = P.Bp / 32;
   long long grid = sm_count();
   if ((n_tiles + nw - 1) / nw < grid) grid = (n_tiles + nw - 1) / nw;
-  pass2_kernel<H, NH><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH));
+  CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH)));
   CVF_CUDA(cudaGetLastError());
   const int n_part = k * np.n_params;
-  reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid * nw, n_part, 0, n_part, grad_out);
+  CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, nw * n_part, 0, n_part, grad_out));
   CVF_CUDA(cudaGetLastError());
   // pass 2b: the first layer's weight gradient
-  const int wpn = dw1_warps_per_net(k), warps_b = k * wpn;
-  const size_t smem3 = dw1_smem_bytes(k, P.geo_floats, P.d_rp, H);
+  const int warps_b = dw1_warps(k, P.d_rp, H), base = warps_b / k, rem = warps_b % k;
+  const size_t smem3 = dw1_smem_bytes(warps_b, P.d_rp, H);
   CVF_CUDA(cudaFuncSetAttribute(dw1_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
   long long grid_b = sm_count();
-  if ((n_tiles + wpn - 1) / wpn < grid_b) grid_b = (n_tiles + wpn - 1) / wpn;
-  dw1_kernel<H><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, wpn, P.part2);
+  if ((n_tiles + base - 1) / base < grid_b) grid_b = (n_tiles + base - 1) / base;
+  CVF_LAUNCH(K_FAST_PASS2B, stream, dw1_kernel<H><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, base, rem, P.part2));
   CVF_CUDA(cudaGetLastError());
   const int block = H * P.d_r;
-  dw1_reduce_kernel<<<dim3((block + 127) / 128, k), 128, 0, stream>>>(P.part2, (int)grid_b, warps_b, wpn, block, np.n_params,
-                                                                      np.gw_off[0], grad_out);
+  CVF_LAUNCH(K_REDUCE, stream, dw1_reduce_kernel<<<dim3((block + 127) / 128, k), 128, 0, stream>>>(P.part2, (int)grid_b, warps_b, base, rem, block, np.n_params,
+                                                                      np.gw_off[0], grad_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }

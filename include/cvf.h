@@ -122,6 +122,15 @@ size_t cvf_ae_workspace_bytes(const cvf_mlp* net);
 int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
                 double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Launch accounting for bench.py (no reference counterpart).  The library counts every kernel it launches; with
+ * cvf_profile_enable(1) each launch is also bracketed by CUDA events on the stream it was enqueued on.
+ * cvf_profile_read fills, per kernel id < cvf_profile_num_kernels(): summed milliseconds of the timed launches, how many were
+ * timed, and the launch count since the last reset; it synchronises on the recorded events. */
+int cvf_profile_enable(int32_t on);
+int32_t cvf_profile_num_kernels(void);
+const char* cvf_profile_kernel_name(int32_t id);
+int cvf_profile_read(double* ms_out, int64_t* timed_out, int64_t* launches_out, int32_t reset);
+
 /* Measurement helper for bench.py (no reference counterpart): enqueue a kernel that issues exactly
  * *flops_out = 2 * fmas fp32 FMA flops on independent register chains, so that the fp32 SIMT peak used as the
  * compute-roofline denominator is measured on the same GPU, same clocks, as the step kernels. */
