@@ -11,11 +11,14 @@ Weak scaling: every rank keeps `--frames` frames (default 2^22, 1.1 GB > L2) res
 
 `value`   : frames/s with the batch resident in HBM (CUDA events, max over ranks).
 `e2e`     : frames/s with the batch in pinned HOST memory, H2D copy + step + D2H of the loss inside the timed region.
-`roofline`: dominant kernel (pass 2, eigen_kernel<true>) timed alone with CUDA events; algorithmic bytes = 268 B/frame
-            against the measured HBM peak; `roofline_fp32` puts the same kernel against a measured fp32 FMA peak,
-            which is the roofline that actually binds this path.
+`roofline`: the dominant kernel (most device time per step in the library's own launch accounting, CUDA events around
+            every launch on the launching stream, measured in a separate profiled run of K steps): algorithmic bytes
+            = SURVEY 8d's per-frame figure x frames, against the measured HBM peak.  `roofline_fp32` puts the kernel and
+            the whole step against the fp32 FMA peak measured in the same run (cvf_fma_probe), which is the roofline
+            that actually binds this path; `kernels` lists every kernel's share of the step.
 `cpu_baseline` / `--impl reference`: oracle/ref_torch.py (restatement of the reference's PyTorch path; /root/reference does
-            not exist on the GPU box) on the host cores, on a bounded sample of the same workload.
+            not exist on the GPU box) on the host cores, on a bounded sample of the same workload.  Only these two legs
+            import oracle/.
 """
 from __future__ import annotations
 
@@ -48,6 +51,14 @@ WORKLOADS = {
            "nets [81,20,20,20,1]", 1996, 128500),
 }
 METRIC = "train-step frames/sec"
+# fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
+KERNEL_FLOPS = {
+    ("c3", "fast_pass2a"): 45240, ("c3", "fast_pass1"): 25680, ("c3", "fast_pass2b(dW1)"): 15840,
+    ("c1", "fast_pass2a"): 5080, ("c1", "fast_pass1"): 1760,
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture under profiles/ (per frame x frames of that run
+# is NOT extrapolated: null unless the capture used this configuration)
+KERNEL_TRAFFIC = {}
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -112,54 +123,17 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_frames_device(base, n, dev, seed):
-    """frame = base Q + t + eps on the device: Haar rotation from a random unit quaternion,
-    t ~ N(0,5^2) A, eps ~ N(0,0.3^2) A."""
-    g = torch.Generator(device=dev).manual_seed(seed)
-    base_t = torch.as_tensor(base, dtype=torch.float32, device=dev)
-    out = torch.empty(n, base_t.shape[0], 3, dtype=torch.float32, device=dev)
-    chunk = 1 << 20
-    for s in range(0, n, chunk):
-        m = min(chunk, n - s)
-        q = torch.randn(m, 4, generator=g, device=dev)
-        q = q / q.norm(dim=1, keepdim=True)
-        w, x, y, z = q.unbind(1)
-        Q = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
-                         2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
-                         2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1).reshape(m, 3, 3)
-        fr = torch.einsum("ni,bij->bnj", base_t, Q)
-        fr += 5.0 * torch.randn(m, 1, 3, generator=g, device=dev)
-        fr += 0.3 * torch.randn(m, base_t.shape[0], 3, generator=g, device=dev)
-        out[s:s + m] = fr
-    return out
-
-
-def boltzmann_weights_device(n, dev, seed):
-    g = torch.Generator(device=dev).manual_seed(seed + 1)
-    E = torch.randn(n, generator=g, device=dev)
-    w = torch.exp(-0.5 * (E - E.mean()))
-    return (w / w.mean()).contiguous()
-
-
-def c4_features():
-    """45 pair distances among 10 designated atoms + 18 backbone dihedrals of the 166-atom chain."""
-    sel = list(range(5, 166, 16))[:10]
-    feats = [("bond", [a, b]) for i, a in enumerate(sel) for b in sel[i + 1:]]
-    feats += [("dihedral", [s, s + 1, s + 2, s + 3]) for s in range(10, 10 + 18 * 8, 8)]
-    return feats, list(range(0, 160, 4))
-
-
 def build_workload(name, n_frames, dev, seed, lr=1e-3):
-    """Returns (step_fn(X, w) -> loss tensor, X, w, task, launches_per_step, dominant(X, w) -> None)."""
+    """Returns (step_fn(X, w) -> loss tensor, X, w, task)."""
     from colvarsfinder import core, nn, utils
-    from oracle import ref_torch
-    from oracle.ref_import import FakeTrajectory
+    import bench_data as bd
+    FakeTrajectory = bd.SyntheticTrajectory
     torch.manual_seed(2026)
     tmp = f"/tmp/cvf_bench_{os.getpid()}"
     if name in ("c3", "c2"):
-        base = ref_torch.DIPEPTIDE_NM * 10.0
-        X = synth_frames_device(base, n_frames, dev, seed)
-        w = boltzmann_weights_device(n_frames, dev, seed) if name == "c3" else torch.ones(n_frames, device=dev)
+        base = bd.DIPEPTIDE_NM * 10.0
+        X = bd.frames(base, n_frames, dev, seed)
+        w = bd.boltzmann_weights(n_frames, dev, seed) if name == "c3" else torch.ones(n_frames, device=dev)
         small = FakeTrajectory(X[:1024].cpu().numpy(), np.ones(1024), dt=1.0)
         align = utils.Align(base, list(range(22)))
         if name == "c3":
@@ -171,20 +145,17 @@ def build_workload(name, n_frames, dev, seed, lr=1e-3):
             task = core.AutoEncoderTask(small, align, model, tmp, learning_rate=lr, device=dev, verbose=False, debug_mode=False)
             X = task.preprocessing_layer(X).reshape(n_frames, 66).contiguous()   # the pre-pass is outside the step (core.py:635)
     elif name == "c1":
-        g = torch.Generator(device=dev).manual_seed(seed)
-        th = (torch.rand(n_frames, generator=g, device=dev) * 2 - 1) * np.pi
-        r = 1.0 + 0.25 * torch.randn(n_frames, generator=g, device=dev)
-        X = torch.stack([r * torch.cos(th), r * torch.sin(th)], 1).contiguous()
+        X = bd.ring_2d(n_frames, dev, seed)
         w = torch.ones(n_frames, device=dev)
         small = FakeTrajectory(X[:1024].cpu().numpy(), np.ones(1024), dt=0.1)
         model = nn.EigenFunctions([2, 20, 20, 20, 1], 1)
         task = core.EigenFunctionTask(small, torch.nn.Identity(), model, tmp, 20.0, [1.0], k=1, learning_rate=lr, device=dev,
                                       verbose=False, debug_mode=False)
     elif name == "c4":
-        base = ref_torch.chain_structure(166, seed=2026)
-        X = synth_frames_device(base, n_frames, dev, seed)
-        w = boltzmann_weights_device(n_frames, dev, seed)
-        feats, align_idx = c4_features()
+        base = bd.chain_structure(166, seed=2026)
+        X = bd.frames(base, n_frames, dev, seed)
+        w = bd.boltzmann_weights(n_frames, dev, seed)
+        feats, align_idx = bd.c4_features()
         pp = utils.Preprocessing(utils.Align(base[align_idx], align_idx), utils.FeatureMap(feats))
         small = FakeTrajectory(X[:1024].cpu().numpy(), np.ones(1024), dt=1.0)
         model = nn.EigenFunctions([81, 20, 20, 20, 1], 3)
@@ -200,13 +171,6 @@ def build_workload(name, n_frames, dev, seed, lr=1e-3):
             loss.backward()
             task.optimizer.step()
             return loss
-        launches = 5      # eigen_kernel<stats>, reduce, combine, eigen_kernel<grad>, reduce
-
-        def dominant(Xb, wb):
-            ctx = task._ctx
-            y, stats = ctx.stats(Xb, wb)
-            comb = ctx.combine(stats)
-            return lambda: ctx.grads(Xb, wb, y, comb)
     else:
         def step(Xb, wb):
             task.optimizer.zero_grad(set_to_none=True)
@@ -214,11 +178,7 @@ def build_workload(name, n_frames, dev, seed, lr=1e-3):
             loss.backward()
             task.optimizer.step()
             return loss
-        launches = 3      # ae_kernel, 2 x reduce
-
-        def dominant(Xb, wb):
-            return lambda: task._ctx.step(Xb, wb, True)
-    return step, X, w, task, launches, dominant
+    return step, X, w, task
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -244,7 +204,8 @@ def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
         base = ref_torch.chain_structure(166, seed=2026)
         X = torch.as_tensor(ref_torch.synth_frames(base, n_frames, seed=seed))
         w = torch.as_tensor(ref_torch.boltzmann_weights(n_frames, seed=seed))
-        feats, align_idx = c4_features()
+        import bench_data as bd
+        feats, align_idx = bd.c4_features()
         pp = ref_torch.Preprocess(ref_torch.Align(base[align_idx], align_idx), ref_torch.FeatureMap(feats))
     if name == "c2":
         enc = [p.requires_grad_() for p in ref_torch.init_mlp_params([66, 20, 20, 20, 2])]
@@ -328,7 +289,7 @@ def main():
     entry.build()
     from colvarsfinder import _lib
 
-    step, X, w, task, launches, dominant = build_workload(args.workload, args.frames, dev, seed=2026 + rank)
+    step, X, w, task = build_workload(args.workload, args.frames, dev, seed=2026 + rank)
     W = max(args.warmup, 3)
     K = args.steps
 
@@ -341,6 +302,7 @@ def main():
     for _ in range(W):
         step(X, w)
     barrier()
+    _lib.profile_read(reset=True)      # launch counters to zero: the timed region is counted exactly
     sampler = ClockSampler(local).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -354,7 +316,8 @@ def main():
         torch.distributed.all_reduce(ms_total, op=torch.distributed.ReduceOp.MAX)
     ms_total = float(ms_total)
     value = args.frames * world * K / (ms_total * 1e-3)
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
+    launches_timed = sum(v[2] for v in _lib.profile_read(reset=True).values())
 
     # ---- end to end: batch in pinned host memory, H2D + step + D2H(loss) per step, copy of step i+1 overlapped
     hosts = [torch.empty(X.shape, dtype=X.dtype).pin_memory() for _ in range(2)]
@@ -406,22 +369,20 @@ def main():
     e2e_value = args.frames * world * K / (float(ms_e2e) * 1e-3)
     del hosts, hw, devb, devw
 
-    # ---- dominant kernel alone (pass 2 / AE step) with CUDA events on the launching stream
-    run = dominant(X, w)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
+    # ---- per-kernel device time: K more steps with a CUDA-event pair around every launch of the library
+    L = _lib.lib()
+    _lib.check(L.cvf_profile_enable(1), "cvf_profile_enable")
     for _ in range(K):
-        run()
-    k1.record()
+        step(X, w)
     torch.cuda.synchronize()
-    kern_ms = k0.elapsed_time(k1) / K
+    prof = {k_: v for k_, v in _lib.profile_read(reset=True).items() if v[1] > 0}
+    _lib.check(L.cvf_profile_enable(0), "cvf_profile_enable")
+    dom_name = max(prof, key=lambda k_: prof[k_][0])
+    kern_ms = prof[dom_name][0] / prof[dom_name][1]
+    step_kernel_ms = sum(v[0] for v in prof.values()) / K
     # ---- fp32 FMA peak probe
     sink = torch.zeros(4, device=dev)
     flops = C.c_double(0.0)
-    L = _lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         _lib.check(L.cvf_fma_probe(sink.data_ptr(), 20000, C.byref(flops), stream), "cvf_fma_probe")
@@ -440,22 +401,27 @@ def main():
         return
     hbm_peak, peak_src = measured_peaks()
     achieved = bytes_per_frame * args.frames / (kern_ms * 1e-3) / 1e9
-    # flops of the dominant kernel per frame: C3/C4/C1 pass 2 ~ (step - pass 1); use the whole-step figure for the step
     step_tflops = value / world * flops_per_frame / 1e12
+    dom_flops = KERNEL_FLOPS.get((args.workload, dom_name))
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "clocks": clocks, "final_loss": final_loss,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                 "ms_per_step": float(ms_e2e) / K},
-        "gpu_launches": launches * K * world,
+        "gpu_launches": launches_timed * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "kernel": "eigen_kernel<GRAD>" if launches == 5 else "ae_kernel<GRAD>",
-                     "kernel_ms": kern_ms, "peak_source": peak_src,
-                     "note": "this step is fp32-FMA bound (SURVEY 8d), see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32_fma", "achieved": step_tflops, "peak": fma_peak, "unit": "TFLOP/s",
-                          "frac": step_tflops / fma_peak, "flops_per_frame": flops_per_frame,
-                          "peak_source": "cvf_fma_probe measured in this run"},
+                     "traffic": KERNEL_TRAFFIC.get((args.workload, dom_name)), "kernel": dom_name, "kernel_ms": kern_ms,
+                     "kernel_share_of_step": prof[dom_name][0] / K / step_kernel_ms, "peak_source": peak_src,
+                     "note": "this path is fp32-FMA bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32_fma", "peak": fma_peak, "unit": "TFLOP/s",
+                          "peak_source": "cvf_fma_probe measured in this run",
+                          "step": {"achieved": step_tflops, "frac": step_tflops / fma_peak, "flops_per_frame": flops_per_frame},
+                          "kernel": None if dom_flops is None else {
+                              "name": dom_name, "flops_per_frame": dom_flops,
+                              "achieved": dom_flops * args.frames / (kern_ms * 1e-3) / 1e12,
+                              "frac": dom_flops * args.frames / (kern_ms * 1e-3) / 1e12 / fma_peak}},
+        "kernels": {k_: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k_, v in sorted(prof.items())},
     }
     if not args.no_cpu_baseline:
         fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, 5, 1)
