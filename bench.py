@@ -241,7 +241,22 @@ def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
 
 
 # ------------------------------------------------------------------------------------------------ main
+def _quiet_stdout():
+    """Route everything libraries print on file descriptor 1 (e.g. NCCL's version banner) to stderr; returns a writer for
+    the one JSON line, so that stdout carries nothing else."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(saved, "w")
+
+    def emit(obj):
+        out.write(json.dumps(obj) + "\n")
+        out.flush()
+    return emit
+
+
 def main():
+    emit = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -267,7 +282,7 @@ def main():
                   "oracle/ref_torch.py (PyTorch CPU autograd restatement of core.py:387-457,517 + Adam)")
         config["frames_per_gpu_per_step"] = args.cpu_frames
         config["global_batch"] = args.cpu_frames
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": w_, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
@@ -427,7 +442,7 @@ def main():
         fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, 5, 1)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": f"{args.cpu_frames} frames/step x 5 steps (+1 warm-up), oracle/ref_torch.py on the host"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
