@@ -48,6 +48,9 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // warp-cooperative staging of `nrows` frame-minor row segments (32 frames = 128 B each) into padded shared-memory rows:
 // lane -> (row mod 4, 16-byte chunk); `src` points at the first frame of the tile in row 0
 __device__ __forceinline__ void stage_rows(float* dst, const float* src, int nrows, long long Bp, int lane) {
@@ -184,10 +187,14 @@ __global__ void __launch_bounds__(128) prep_align_kernel(const FastPlan P, const
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long f0 = tile * 128;
     if (f0 + 128 <= P.B) {
+      // contiguous tile: element i = tid + 128 m belongs to frame i / fl; (frame, coordinate) advance incrementally
       const float* src = x + (size_t)f0 * fl;
+      const int df = 128 / fl, dj = 128 - df * fl;
+      int f = tid / fl, j = tid - f * fl;
       for (int i = tid; i < 128 * fl; i += 128) {
-        const int f = i / fl;
-        st[f * S + (i - f * fl)] = __ldg(src + i);
+        st[f * S + j] = __ldg(src + i);
+        f += df, j += dj;
+        if (j >= fl) j -= fl, ++f;
       }
     } else {
       for (int i = tid; i < 128 * fl; i += 128) {
@@ -699,7 +706,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       __syncwarp();
 #pragma unroll
       for (int o = 0; o < H; ++o) Zr[o * RP + lane] = a[o], Zr[(H + o) * RP + lane] = tg[o];
-#pragma unroll
+#pragma unroll 1   // one copy of the layer code for every hidden layer: the kernel has to stay inside the instruction cache
       for (int l = 2; l <= NH; ++l) {
 #pragma unroll
         for (int j = 0; j < HP; ++j) z[j] = lds2(W + I::bl(drp, l) + 2 * j), zd[j] = make_float2(0.f, 0.f);
@@ -749,7 +756,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         }
       }
       // ---- reverse sweep over the hidden layers with the outer products of each layer as soon as (s_l, G_l) exist
-#pragma unroll
+#pragma unroll 1
       for (int l = NH; l >= 1; --l) {
         // db_l = sum_f s_l
         {
@@ -843,105 +850,102 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 }
 
 // Pass 2b:  dW_1[n] = sum_f s_1 (x) r + (scale G_1) (x) vhat  -- a product over the frames with the accumulators of one
-// network's [H][d_r] block held in the registers of a warp for a run of tiles.  The CTA's warps are dealt out to the networks
-// (the first `rem` networks get base + 1 warps, the others base); a warp takes every wpn-th tile of its CTA and stages the
-// operand rows (r, vhat left by pass 2a in place of u, s_1 | scale G_1) in warp-private shared memory.
-__host__ __device__ inline void dw1_warp_role(int warp, int base, int rem, int* n, int* slot, int* wpn) {
-  const int cut = rem * (base + 1);
-  if (warp < cut) {
-    *n = warp / (base + 1), *slot = warp - *n * (base + 1), *wpn = base + 1;
-  } else {
-    const int w2 = warp - cut;
-    *n = rem + w2 / base, *slot = w2 - (w2 / base) * base, *wpn = base;
-  }
-}
+// network's [H][d_r] block held in a warp's registers for a run of kRun tiles (32 frames each).  Work items
+// (network, run) are dealt round-robin to all warps of the grid, so the load is even for any k; a warp stages the operand
+// rows (r, vhat left by pass 2a in place of u, s_1 | scale G_1) in warp-private shared memory, and after a run adds its
+// fp32 sums to its own fp64 block of that network (one owner per address: deterministic).
+constexpr int kRun = 16;
 
 template <int H>
-__global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, int base, int rem, double* __restrict__ part2) {
+__global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* __restrict__ part2) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ, FLUSH = 8;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
-  const int drp = P.d_rp, d_r = P.d_r, nig = drp / 12;
-  const int rows_per_warp = 2 * drp + 2 * H;
-  float* Rr = sm + (size_t)warp * rows_per_warp * RP;
-  float* Vr = Rr + drp * RP;
-  float* Xr = Vr + drp * RP;
-  for (int i = tid; i < (nt >> 5) * rows_per_warp * RP; i += nt) sm[i] = 0.0f;
-  int n, slot, wpn;
-  dw1_warp_role(warp, base, rem, &n, &slot, &wpn);
-  double* part = part2 + ((size_t)blockIdx.x * (nt >> 5) + warp) * (size_t)(H * d_r);
-  for (int i = lane; i < H * d_r; i += 32) part[i] = 0.0;
+  constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const int drp = P.d_rp, d_r = P.d_r, nig = drp / 12, k = P.k, blk = H * d_r;
+  const int rows_per_buf = 2 * drp + 2 * H;
+  float* buf0 = sm + (size_t)warp * 2 * rows_per_buf * RP;   // two staging buffers per warp: r | vhat | s_1, scale G_1
+  for (int i = tid; i < nw * 2 * rows_per_buf * RP; i += nt) sm[i] = 0.0f;
+  double* part = part2 + ((size_t)blockIdx.x * nw + warp) * (size_t)(k * blk);   // [k][H * d_r]
+  for (int i = lane; i < k * blk; i += 32) part[i] = 0.0;
   __syncthreads();
   const int og = lane / LPO, ig = lane - og * LPO;
   const bool active = og < TQ && ig < nig;
-  float2 acc[4][12];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 12; ++i) acc[j][i] = make_float2(0.f, 0.f);
   const long long n_tiles = P.Bp / 32;
-  const long long step = (long long)gridDim.x * wpn;
-  int since_flush = 0;
-  for (long long t = (long long)blockIdx.x * wpn + slot; t < n_tiles; t += step) {
-    __syncwarp();
-    stage_rows(Rr, P.Y + t * 32, d_r, P.Bp, lane);
-    stage_rows(Vr, P.U + ((size_t)n * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
-    stage_rows(Xr, P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, 2 * H, P.Bp, lane);
-    if (t + step < n_tiles) {
-      const long long tn = (t + step) * 32;
-      prefetch_rows(P.Y + tn, d_r, P.Bp, lane);
-      prefetch_rows(P.U + ((size_t)n * drp) * P.Bp + tn, d_r, P.Bp, lane);
-      prefetch_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + tn, 2 * H, P.Bp, lane);
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    if (active)
-      outer_tile<4, 12>(acc, Xr + og * RP, Rr + ig * RP, Xr + (H + og) * RP, Vr + ig * RP, TQ * RP, nig * RP, 0, 32);
-    if (++since_flush == FLUSH || t + step >= n_tiles) {
-      // fp32 partial sums of FLUSH * 32 frames -> this warp's fp64 partial block, transposed through the r rows so that the
-      // additions are coalesced (one owner per address: deterministic)
-      since_flush = 0;
-      __syncwarp();
-      if (active) {
+  const long long n_runs = (n_tiles + kRun - 1) / kRun, n_items = n_runs * k;
+  const long long stride = (long long)gridDim.x * nw;
+  // the warp's tiles form one sequence (item q, tile t inside its run); tile i + 1 is staged while tile i is multiplied
+  auto stage = [&](int b, int n, long long t) {
+    float* R = buf0 + (size_t)b * rows_per_buf * RP;
+    stage_rows(R, P.Y + t * 32, d_r, P.Bp, lane);
+    stage_rows(R + drp * RP, P.U + ((size_t)n * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
+    stage_rows(R + 2 * drp * RP, P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, 2 * H, P.Bp, lane);
+    cp_async_commit();
+  };
+  long long q = (long long)blockIdx.x * nw + warp;
+  int cur = 0;
+  if (q < n_items) stage(0, (int)(q % k), (q / k) * kRun);
+  for (; q < n_items; q += stride) {
+    const int n = (int)(q % k);
+    const long long t0 = (q / k) * kRun, t1 = t0 + kRun < n_tiles ? t0 + kRun : n_tiles;
+    float2 acc[4][12];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int i = 0; i < 12; ++i) {
-            const int o = j * TQ + og, col = i * nig + ig;
-            if (col < d_r) Rr[o * d_r + col] = acc[j][i].x + acc[j][i].y;
-            acc[j][i] = make_float2(0.f, 0.f);
-          }
+      for (int i = 0; i < 12; ++i) acc[j][i] = make_float2(0.f, 0.f);
+    for (long long t = t0; t < t1; ++t) {
+      // successor of (q, t) in this warp's sequence
+      long long tn = t + 1, qn = q;
+      if (tn >= t1) qn = q + stride, tn = (qn / k) * kRun;
+      __syncwarp();   // every lane has finished reading the buffer that is staged next
+      if (qn < n_items) {
+        stage(cur ^ 1, (int)(qn % k), tn);
+        cp_async_wait_group<1>();
+      } else {
+        cp_async_wait_all();
       }
       __syncwarp();
-      for (int e = lane; e < H * d_r; e += 32) part[e] += (double)Rr[e];
+      const float* R = buf0 + (size_t)cur * rows_per_buf * RP;
+      if (active)
+        outer_tile<4, 12>(acc, R + (2 * drp + og) * RP, R + ig * RP, R + (2 * drp + H + og) * RP, R + (drp + ig) * RP, TQ * RP,
+                          nig * RP, 0, 32);
+      cur ^= 1;
     }
+    // fp32 sums of the run -> this warp's fp64 block of network n, transposed through the X rows of the buffer just used so
+    // that the additions are coalesced (those rows are restaged before their next use)
+    __syncwarp();
+    float* T = buf0 + (size_t)(cur ^ 1) * rows_per_buf * RP;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int o = j * TQ + og, col = i * nig + ig;
+          if (col < d_r) T[o * d_r + col] = acc[j][i].x + acc[j][i].y;
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < blk; e += 32) atomicAdd(part + (size_t)n * blk + e, (double)T[e]);   // result unused: RED
   }
-  // fold the blocks of the warps that share a network into the first of them
+  // fold the CTA's warps into the first warp's blocks (fixed order)
   __syncthreads();
   {
-    const int nwarps = nt >> 5, blk = H * d_r;
-    double* cta = part2 + (size_t)blockIdx.x * nwarps * blk;
-    for (int net = 0; net < P.k; ++net) {
-      const int cnt = net < rem ? base + 1 : base;
-      const int w0 = net < rem ? net * (base + 1) : rem * (base + 1) + (net - rem) * base;
-      for (int e = tid; e < blk; e += nt) {
-        double sacc = 0.0;
-        for (int q = 0; q < cnt; ++q) sacc += __ldcg(cta + (size_t)(w0 + q) * blk + e);
-        cta[(size_t)w0 * blk + e] = sacc;
-      }
+    double* cta = part2 + (size_t)blockIdx.x * nw * (size_t)(k * blk);
+    for (int e = tid; e < k * blk; e += nt) {
+      double sacc = 0.0;
+      for (int qq = 0; qq < nw; ++qq) sacc += __ldcg(cta + (size_t)qq * (k * blk) + e);
+      cta[e] = sacc;
     }
   }
 }
 
-// grad_out[n][W1 block] += sum over the per-warp partial blocks of network n
-__global__ void dw1_reduce_kernel(const double* __restrict__ part2, int n_ctas, int warps_per_cta, int base, int rem, int block,
-                                  int n_params, int w1_off, double* __restrict__ grad_out) {
+// grad_out[n][W1 block] += sum over the CTAs' folded blocks of network n
+__global__ void dw1_reduce_kernel(const double* __restrict__ part2, int n_ctas, size_t cta_stride, int block, int n_params,
+                                  int w1_off, double* __restrict__ grad_out) {
   const int n = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= block) return;
-  const int w0 = n < rem ? n * (base + 1) : rem * (base + 1) + (n - rem) * base;
   double s = 0.0;
-  for (int c = 0; c < n_ctas; ++c) s += part2[((size_t)c * warps_per_cta + w0) * block + e];   // folded per CTA by dw1_kernel
+  for (int c = 0; c < n_ctas; ++c) s += part2[(size_t)c * cta_stride + (size_t)n * block + e];
   grad_out[(size_t)n * n_params + w1_off + e] += s;
 }
 
@@ -968,10 +972,11 @@ static int pass2_warps(int k, int img2_floats, int geo_floats, int drp, int H, i
     if (pass2_smem_bytes(k, img2_floats, geo_floats, drp, H, NH, wv) <= (size_t)max_smem_optin()) return wv;
   return 0;
 }
-static size_t dw1_smem_bytes(int warps, int drp, int H) { return (size_t)warps * (2 * drp + 2 * H) * kRowPad * sizeof(float); }
-// warps of a pass-2b CTA: as many as fit (<= 8), at least one per network; 0 if they do not fit
+static size_t dw1_smem_bytes(int warps, int drp, int H) { return (size_t)warps * 2 * (2 * drp + 2 * H) * kRowPad * sizeof(float); }
+// warps of a pass-2b CTA (two staging buffers each): as many as fit (<= 8); 0 if fewer than 2 fit
 static int dw1_warps(int k, int drp, int H) {
-  for (int wv = kP2MaxWarps; wv >= k; --wv)
+  (void)k;
+  for (int wv = kP2MaxWarps; wv >= 2; --wv)
     if (dw1_smem_bytes(wv, drp, H) <= (size_t)max_smem_optin()) return wv;
   return 0;
 }
@@ -1046,7 +1051,7 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   };
   const int n_part = k * np.n_params > 1 + 2 * k + k * k ? k * np.n_params : 1 + 2 * k + k * k;
   P->part = (double*)take((size_t)sm_count() * kP2MaxWarps * n_part * sizeof(double));
-  P->part2 = (double*)take((size_t)sm_count() * kP2MaxWarps * H * P->d_r * sizeof(double));
+  P->part2 = (double*)take((size_t)sm_count() * kP2MaxWarps * k * H * P->d_r * sizeof(double));
   P->img = (float*)take(((size_t)k * P->img_floats + P->geo_floats) * sizeof(float));
   P->Y = (float*)take((size_t)P->d_rp * P->Bp * sizeof(float));
   P->Kinv = (float*)take((size_t)6 * P->Bp * sizeof(float));
@@ -1138,16 +1143,18 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, nw * n_part, 0, n_part, grad_out));
   CVF_CUDA(cudaGetLastError());
   // pass 2b: the first layer's weight gradient
-  const int warps_b = dw1_warps(k, P.d_rp, H), base = warps_b / k, rem = warps_b % k;
+  const int warps_b = dw1_warps(k, P.d_rp, H);
   const size_t smem3 = dw1_smem_bytes(warps_b, P.d_rp, H);
   CVF_CUDA(cudaFuncSetAttribute(dw1_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+  const long long n_items = (n_tiles + kRun - 1) / kRun * k;
   long long grid_b = sm_count();
-  if ((n_tiles + base - 1) / base < grid_b) grid_b = (n_tiles + base - 1) / base;
-  CVF_LAUNCH(K_FAST_PASS2B, stream, dw1_kernel<H><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, base, rem, P.part2));
+  if ((n_items + warps_b - 1) / warps_b < grid_b) grid_b = (n_items + warps_b - 1) / warps_b;
+  CVF_LAUNCH(K_FAST_PASS2B, stream, dw1_kernel<H><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, P.part2));
   CVF_CUDA(cudaGetLastError());
   const int block = H * P.d_r;
-  CVF_LAUNCH(K_REDUCE, stream, dw1_reduce_kernel<<<dim3((block + 127) / 128, k), 128, 0, stream>>>(P.part2, (int)grid_b, warps_b, base, rem, block, np.n_params,
-                                                                      np.gw_off[0], grad_out));
+  CVF_LAUNCH(K_REDUCE, stream,
+             dw1_reduce_kernel<<<dim3((block + 127) / 128, k), 128, 0, stream>>>(P.part2, (int)grid_b, (size_t)warps_b * k * block, block,
+                                                                                 np.n_params, np.gw_off[0], grad_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }

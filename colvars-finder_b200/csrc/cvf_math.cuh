@@ -101,7 +101,7 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0f : 0.0f;
-  for (int sweep = 0; sweep < 5; ++sweep) {
+  for (int sweep = 0; sweep < 4; ++sweep) {
     cvf_jacobi_rot<0, 1>(a, v);
     cvf_jacobi_rot<0, 2>(a, v);
     cvf_jacobi_rot<0, 3>(a, v);
