@@ -214,35 +214,35 @@ class EigenContext:
         self.n_comb = L.cvf_eigen_num_combine(self.k)
         self.n_per_net = int(L.cvf_mlp_param_count(C.byref(self.mlp)))
         self.fast_path = bool(L.cvf_eigen_path(self.spec.struct_ptr(), C.byref(self.mlp), self.k) == 1)
-        self.ws_bytes, self.ws_frames, self.workspace = 0, 0, None
-        self._scratch_key = None
+        # scratch slots: 0 for X, 1 for the time-lagged X of the transfer-operator loss (both must survive until backward)
+        self._ws = {}
 
-    def _workspace_for(self, B):
+    def _workspace_for(self, B, slot=0):
         """Scratch of the step kernels, grown to the largest batch seen (PyTorch's caching allocator owns it)."""
-        if self.workspace is None or B > self.ws_frames:
+        ws = self._ws.get(slot)
+        if ws is None or B > ws["frames"]:
             need = int(_lib.lib().cvf_eigen_workspace_bytes(self.spec.struct_ptr(), C.byref(self.mlp), self.k, B))
             if need <= 0:
                 raise RuntimeError("cvf_eigen_workspace_bytes: unsupported configuration")
-            self.workspace = None
-            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self.ws_bytes, self.ws_frames = need, B
-            self._scratch_key = None
-        return self.workspace.data_ptr()
+            self._ws[slot] = None
+            ws = {"buf": torch.empty(need, dtype=torch.uint8, device=self.device), "bytes": need, "frames": B, "key": None}
+            self._ws[slot] = ws
+        return ws
 
     def _key(self, X, weight):
         return (X.data_ptr(), X.shape[0], X._version, weight.data_ptr(), weight._version, self.flat.flat._version)
 
-    def stats(self, X, weight):
+    def stats(self, X, weight, slot=0):
         """Pass 1 on this rank's frames -> (y [k,B] fp32, stats fp64)."""
         L = _lib.lib()
         B = X.shape[0]
-        ws = self._workspace_for(B)
+        ws = self._workspace_for(B, slot)
         y = torch.empty(self.k, B, dtype=torch.float32, device=self.device)
         stats = torch.empty(self.n_stats, dtype=torch.float64, device=self.device)
         _lib.check(L.cvf_eigen_stats(X.data_ptr(), weight.data_ptr(), B, self.spec.struct_ptr(), C.byref(self.mlp), self.k,
-                                     self.flat.flat.data_ptr(), y.data_ptr(), stats.data_ptr(), ws, self.ws_bytes, _stream()),
-                   "cvf_eigen_stats")
-        self._scratch_key = self._key(X, weight)
+                                     self.flat.flat.data_ptr(), y.data_ptr(), stats.data_ptr(), ws["buf"].data_ptr(), ws["bytes"],
+                                     _stream()), "cvf_eigen_stats")
+        ws["key"] = self._key(X, weight)
         return y, stats
 
     def combine(self, stats):
@@ -251,19 +251,42 @@ class EigenContext:
                                                 comb.data_ptr(), _stream()), "cvf_eigen_combine")
         return comb
 
-    def grads(self, X, weight, y, comb):
+    def grads(self, X, weight, y, comb, seed_extra=None, slot=0):
         """Pass 2 on this rank's frames -> fp64 gradient sums [k * n_per_net]."""
         g = torch.empty(self.k * self.n_per_net, dtype=torch.float64, device=self.device)
-        ws = self._workspace_for(X.shape[0])
+        ws = self._workspace_for(X.shape[0], slot)
         # the scratch still holds pass 1's intermediates iff the last stats() call saw these very tensors and parameters
-        valid = 1 if self._scratch_key is not None and self._scratch_key == self._key(X, weight) else 0
+        valid = 1 if ws["key"] is not None and ws["key"] == self._key(X, weight) else 0
         _lib.check(_lib.lib().cvf_eigen_grad(X.data_ptr(), weight.data_ptr(), X.shape[0], self.spec.struct_ptr(),
                                              C.byref(self.mlp), self.k, self.flat.flat.data_ptr(), y.data_ptr(),
-                                             comb.data_ptr(), g.data_ptr(), ws, self.ws_bytes, valid, _stream()),
+                                             comb.data_ptr(), None if seed_extra is None else seed_extra.data_ptr(),
+                                             g.data_ptr(), ws["buf"].data_ptr(), ws["bytes"], valid, _stream()),
                    "cvf_eigen_grad")
         # pass 2 consumes the scratch (it leaves v = J J^T u where pass 1 left u): a second backward recomputes it
-        self._scratch_key = None
+        ws["key"] = None
         return g
+
+    def tlag_terms(self, y, y_lag, weight, coef=None):
+        """sum_f w (y' - y)^2 per network (coef None), or the per-frame seed term coef_i w (y_i - y'_i) of the backward pass."""
+        L, B = _lib.lib(), y.shape[1]
+        if coef is None:
+            sx = torch.empty(self.k, dtype=torch.float64, device=self.device)
+            ws = self._workspace_for(B, 0)
+            _lib.check(L.cvf_eigen_tlag_terms(y.data_ptr(), y_lag.data_ptr(), weight.data_ptr(), B, self.k, None, sx.data_ptr(),
+                                              None, ws["buf"].data_ptr(), ws["bytes"], _stream()), "cvf_eigen_tlag_terms")
+            return sx
+        extra = torch.empty(self.k, B, dtype=torch.float32, device=self.device)
+        _lib.check(L.cvf_eigen_tlag_terms(y.data_ptr(), y_lag.data_ptr(), weight.data_ptr(), B, self.k, coef.data_ptr(), None,
+                                          extra.data_ptr(), None, 0, _stream()), "cvf_eigen_tlag_terms")
+        return extra
+
+    def tlag_combine(self, stats, stats_lag, sx, tau):
+        comb = torch.empty(self.n_comb + self.k, dtype=torch.float64, device=self.device)
+        comb_lag = torch.empty(self.n_comb, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().cvf_eigen_tlag_combine(stats.data_ptr(), stats_lag.data_ptr(), sx.data_ptr(), self.k, self.alpha,
+                                                     self.eig_w, float(tau), self.sort, comb.data_ptr(), comb_lag.data_ptr(),
+                                                     _stream()), "cvf_eigen_tlag_combine")
+        return comb, comb_lag
 
 
 class _EigenLoss(torch.autograd.Function):
@@ -297,6 +320,50 @@ def eigen_loss(ectx: EigenContext, X, weight):
     X, weight = _check_batch(X, weight, "EigenFunctionTask.loss_func")
     ectx.flat.check()
     return _EigenLoss.apply(ectx, X, weight, *ectx.flat.params)
+
+
+class _EigenLagLoss(torch.autograd.Function):
+    """Transfer-operator branch of EigenFunctionTask.loss_func (reference core.py:412-416,428,440): forward passes on X and
+    on the time-lagged X, ONE all-reduce of {sums of y, sums of y', sum w (y'-y)^2}; backward = two first-order passes."""
+
+    @staticmethod
+    def forward(ctx, ectx, tau, X, weight, Xl, wl, *params):
+        k = ectx.k
+        with torch.cuda.device(ectx.device):
+            y, st = ectx.stats(X, weight, slot=0)
+            yl, stl = ectx.stats(Xl, wl, slot=1)
+            sx = ectx.tlag_terms(y, yl, weight)
+            packed = torch.cat([st, stl, sx])
+            allreduce_sum_(packed)
+            st, stl, sx = packed[:ectx.n_stats], packed[ectx.n_stats:2 * ectx.n_stats], packed[2 * ectx.n_stats:]
+            comb, comb_lag = ectx.tlag_combine(st.contiguous(), stl.contiguous(), sx.contiguous(), tau)
+        ctx.ectx, ctx.saved = ectx, (X, weight, Xl, wl, y, yl, comb, comb_lag)
+        out32 = comb[:3 + k].to(torch.float32)
+        loss, obj, pen, eig = out32[0], out32[1], out32[2], out32[3:3 + k]
+        cvec = comb[3 + k:3 + 2 * k].to(torch.int64)
+        ctx.mark_non_differentiable(obj, pen, eig, cvec)
+        return loss, eig, obj, pen, cvec
+
+    @staticmethod
+    def backward(ctx, g_loss, *unused):
+        ectx = ctx.ectx
+        X, weight, Xl, wl, y, yl, comb, comb_lag = ctx.saved
+        with torch.cuda.device(ectx.device):
+            extra = ectx.tlag_terms(y, yl, weight, coef=comb[ectx.n_comb:])
+            g = ectx.grads(X, weight, y, comb, seed_extra=extra, slot=0)
+            g += ectx.grads(Xl, wl, yl, comb_lag, seed_extra=extra.neg_(), slot=1)
+            allreduce_sum_(g)
+            g32 = (g * g_loss.to(torch.float64)).to(torch.float32)
+        return (None, None, None, None, None, None) + ectx.flat.split(g32)
+
+
+def eigen_lag_loss(ectx: EigenContext, tau, X, weight, X_lagged, weight_lagged):
+    X, weight = _check_batch(X, weight, "EigenFunctionTask.loss_func")
+    X_lagged, weight_lagged = _check_batch(X_lagged, weight_lagged, "EigenFunctionTask.loss_func (time-lagged data)")
+    if X_lagged.shape != X.shape:
+        raise RuntimeError(f"time-lagged batch has shape {tuple(X_lagged.shape)}, the batch {tuple(X.shape)}")
+    ectx.flat.check()
+    return _EigenLagLoss.apply(ectx, tau, X, weight, X_lagged, weight_lagged, *ectx.flat.params)
 
 
 # ------------------------------------------------------------------------------------------ autoencoder

@@ -10,8 +10,8 @@ logging names of the reference; what changes is where the arithmetic runs:
 * ``loss_func`` / ``weighted_MSE_loss`` return tensors whose ``backward()`` fills ``param.grad`` from the
   fused CUDA passes (``colvarsfinder._ops``); ``optimizer.step()`` is stock ``torch.optim``.
 
-Outside the envelope (non-Tanh activations, transfer-operator loss ``lag_tau > 0``, arbitrary pp_layer
-modules, non-CUDA devices) the constructors raise: there is no PyTorch fallback.
+Outside the envelope (non-Tanh activations, arbitrary pp_layer modules, non-CUDA devices) the constructors
+raise: there is no PyTorch fallback.
 """
 from __future__ import annotations
 
@@ -157,10 +157,6 @@ class EigenFunctionTask(TrainingTask):
         assert abs(lag_idx - int(lag_idx)) < 1e-6, \
             f'lag-time ({lag_tau}) not divisable by the timestep {self.traj_dt} of the trajectory'
         self.lag_idx = int(lag_idx)
-        if self.lag_idx > 0:
-            raise NotImplementedError(
-                "transfer-operator loss (lag_tau > 0, reference core.py:412-416,428,440) is not built yet in the CUDA "
-                "step; only the generator loss (lag_tau = 0) is available and there is no PyTorch fallback")
         self._ij_list = list(itertools.combinations(range(self.k), 2))
         self._num_ij_pairs = len(self._ij_list)
         if self.verbose:
@@ -176,8 +172,10 @@ class EigenFunctionTask(TrainingTask):
             self._diag_coeff = diag_coeff
         else:
             self._diag_coeff = torch.ones(self.tot_dim)
-        # this rank's contiguous shard of the frames, resident in HBM
-        lo, hi = self._shard(traj.shape[0])
+        # this rank's contiguous shard of the frames, resident in HBM; with a time lag, the shard carries the lag_idx frames
+        # that follow it so that index + lag_idx (reference core.py:511) stays local
+        lo, hi = self._shard(traj.shape[0] - self.lag_idx)
+        hi += self.lag_idx
         self._traj = torch.as_tensor(traj[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
         self._weights = torch.as_tensor(weights[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
         self._ctx = _ops.EigenContext(self.model, self.preprocessing_layer, traj.shape[1:], self.device, alpha, eig_weights,
@@ -199,15 +197,21 @@ class EigenFunctionTask(TrainingTask):
 
     def loss_func(self, X, weight, X_lagged=None, weight_lagged=None):
         """Total loss, eigenvalues (sorted when sort_eigvals_in_training), variational objective, penalty and
-        the ordering cvec -- reference core.py:387-457, generator branch.  ``loss.backward()`` runs pass 2."""
-        if X_lagged is not None or weight_lagged is not None:
-            raise NotImplementedError("time-lagged data belong to the transfer-operator loss, which is not built yet")
-        return _ops.eigen_loss(self._ctx, X, weight)
+        the ordering cvec -- reference core.py:387-457: generator branch when lag_tau = 0, transfer-operator branch
+        (X_lagged, weight_lagged used) otherwise.  ``loss.backward()`` runs the backward pass(es)."""
+        if self.lag_idx == 0:
+            return _ops.eigen_loss(self._ctx, X, weight)
+        if X_lagged is None or weight_lagged is None:
+            raise RuntimeError("lag_tau > 0: loss_func needs the time-lagged batch and its weights")
+        return _ops.eigen_lag_loss(self._ctx, self.traj_dt * self.lag_idx, X, weight, X_lagged, weight_lagged)
 
-    def _epoch_batches(self, X, w, bs):
+    def _epoch_batches(self, X, w, bs, Xl=None, wl=None):
         n = X.shape[0]
         for s in range(0, n - bs + 1, bs):
-            yield X[s:s + bs], w[s:s + bs]
+            if Xl is None:
+                yield X[s:s + bs], w[s:s + bs], None, None
+            else:
+                yield X[s:s + bs], w[s:s + bs], Xl[s:s + bs], wl[s:s + bs]
 
     def train(self):
         """Epoch / mini-batch loop of reference core.py:459-566 on device-resident shards."""
@@ -216,6 +220,10 @@ class EigenFunctionTask(TrainingTask):
         it, ie = torch.as_tensor(idx_train, device=self.device), torch.as_tensor(idx_test, device=self.device)
         X_train, w_train = self._traj[it], self._weights[it]
         X_test, w_test = self._traj[ie], self._weights[ie]
+        Xl_train = wl_train = Xl_test = wl_test = None
+        if self.lag_idx > 0:      # X_lagged = traj[index + lag_idx] (reference core.py:510-512,546-547)
+            Xl_train, wl_train = self._traj[it + self.lag_idx], self._weights[it + self.lag_idx]
+            Xl_test, wl_test = self._traj[ie + self.lag_idx], self._weights[ie + self.lag_idx]
         bs_train = min(self.batch_size, X_train.shape[0])
         bs_test = min(self.batch_size, X_test.shape[0])
         n_it_train, n_it_test = X_train.shape[0] // bs_train, X_test.shape[0] // bs_test
@@ -232,9 +240,9 @@ class EigenFunctionTask(TrainingTask):
             self.model.train()
             train_rows = []
             loss = None
-            for X, weight in self._epoch_batches(X_train, w_train, bs_train):
+            for X, weight, Xl, wl in self._epoch_batches(X_train, w_train, bs_train, Xl_train, wl_train):
                 self.optimizer.zero_grad(set_to_none=True)
-                loss, eig_vals, non_penalty_loss, penalty, self._cvec = self.loss_func(X, weight, None, None)
+                loss, eig_vals, non_penalty_loss, penalty, self._cvec = self.loss_func(X, weight, Xl, wl)
                 loss.backward()
                 train_rows.append(torch.cat([torch.stack([loss.detach(), non_penalty_loss, penalty]), eig_vals]))
                 self.optimizer.step()
@@ -247,8 +255,8 @@ class EigenFunctionTask(TrainingTask):
                 if self.plot_class is not None:
                     self.plot_class.plot(self.colvar_model(), epoch=epoch)
             test_rows = []
-            for X, weight in self._epoch_batches(X_test, w_test, bs_test):
-                loss_t, eig_vals, non_penalty_loss, penalty, _ = self.loss_func(X, weight, None, None)
+            for X, weight, Xl, wl in self._epoch_batches(X_test, w_test, bs_test, Xl_test, wl_test):
+                loss_t, eig_vals, non_penalty_loss, penalty, _ = self.loss_func(X, weight, Xl, wl)
                 test_rows.append(torch.cat([torch.stack([loss_t.detach(), non_penalty_loss, penalty]), eig_vals]))
             # one device->host transfer per epoch for the whole log
             tr = torch.stack(train_rows).cpu() if train_rows else torch.zeros(0, 3 + self.k)

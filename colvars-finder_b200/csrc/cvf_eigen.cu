@@ -25,8 +25,8 @@ size_t fast_eigen_workspace_bytes(const cvf_preproc* pp, const NetPlan& np, int 
 int fast_eigen_stats(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
                      const float* params, float* y_out, double* stats_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int fast_eigen_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
-                    const float* params, const double* combine, double* grad_out, void* workspace, size_t ws_bytes,
-                    int scratch_valid, cudaStream_t stream);
+                    const float* params, const double* combine, const float* seed_extra, double* grad_out, void* workspace,
+                    size_t ws_bytes, int scratch_valid, cudaStream_t stream);
 static int g_eigen_path = 0;   // 0: fast path whenever it applies, 1: always the general row-engine kernels
 
 // Optional per-phase cycle counters (profiling builds only: -DCVF_PHASE_TIMERS, see profiles/phase_timing.py).
@@ -506,7 +506,7 @@ template <bool GRAD, int FPL>
 __global__ void __launch_bounds__(384, 1)
 eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __restrict__ w, long long B,
              const float* __restrict__ params, float* __restrict__ y_io, const double* __restrict__ combine,
-             double* __restrict__ partial) {
+             double* __restrict__ partial, const float* __restrict__ seed_extra) {
   extern __shared__ __align__(16) float smem[];
   const NetPlan& np = P.net;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -636,7 +636,9 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
           scale = (float)(2.0 * (double)wf * c_cD[n]);
           double s = 0.0;
           for (int j = 0; j < k; ++j) s += c_C2[n * k + j] * ((double)rows[(P.row_y + j) * FS + f] - c_mean[j]);
-          rows[P.row_seed * FS + f] = (float)((double)wf * s);
+          float sd = (float)((double)wf * s);
+          if (seed_extra != nullptr && f_base + f < B) sd += seed_extra[(size_t)n * B + f_base + f];   // transfer-operator term
+          rows[P.row_seed * FS + f] = sd;
         }
         const float D = jphase_frame(P, rows, netrows, f, GRAD, scale);
         if (!GRAD) rows[(P.row_D + n) * FS + f] = D;
@@ -827,8 +829,8 @@ __global__ void eigen_combine_kernel(const double* __restrict__ S, int k, double
 }
 
 static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
-                        int k, const float* params, float* y_io, const double* combine, double* out, void* workspace,
-                        size_t ws_bytes, int scratch_valid, void* stream_) {
+                        int k, const float* params, float* y_io, const double* combine, const float* seed_extra, double* out,
+                        void* workspace, size_t ws_bytes, int scratch_valid, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EigenPlan P;
   int e = build_plan(pp, net, k, &P);
@@ -838,7 +840,8 @@ static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, co
     return CVF_E_ARG;
   }
   if (g_eigen_path == 0 && fast_eigen_supported(pp, P.net, k)) {
-    if (grad) return fast_eigen_grad(pp, P.net, k, x, w, B, params, combine, out, workspace, ws_bytes, scratch_valid, stream);
+    if (grad)
+      return fast_eigen_grad(pp, P.net, k, x, w, B, params, combine, seed_extra, out, workspace, ws_bytes, scratch_valid, stream);
     return fast_eigen_stats(pp, P.net, k, x, w, B, params, y_io, out, workspace, ws_bytes, stream);
   }
   e = finish_plan(&P, pp->kind == 1 && pp->positions_only != 0);   // largest tile that fits
@@ -853,15 +856,103 @@ static int eigen_launch(bool grad, const float* x, const float* w, int64_t B, co
   }
   if (grad) {
     CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    CVF_LAUNCH(K_EIGEN_GRAD, stream, eigen_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace));
+    CVF_LAUNCH(K_EIGEN_GRAD, stream, eigen_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace, seed_extra));
   } else {
     CVF_CUDA(cudaFuncSetAttribute(eigen_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    CVF_LAUNCH(K_EIGEN_STATS, stream, eigen_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace));
+    CVF_LAUNCH(K_EIGEN_STATS, stream, eigen_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, x, w, B, params, y_io, combine, (double*)workspace, nullptr));
   }
   CVF_CUDA(cudaGetLastError());
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 0, n_part, out));
   CVF_CUDA(cudaGetLastError());
   return 0;
+}
+
+// ---- transfer-operator branch (core.py:412-416,428,440): forward-only on X and on the time-lagged X' --------------
+// mode 0: sx[i] = sum_f w_f (y'_i - y_i)^2 (per-block partials);  mode 1: extra[i][f] = E_i w_f (y_i - y'_i)
+__global__ void __launch_bounds__(256)
+tlag_terms_kernel(const float* __restrict__ y, const float* __restrict__ yl, const float* __restrict__ w, long long B, int k,
+                  const double* __restrict__ coef, double* __restrict__ part, float* __restrict__ extra) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = 0; i < k; ++i) {
+    double acc = 0.0;
+    const float e = extra ? (float)coef[i] : 0.0f;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < B; f += (long long)gridDim.x * blockDim.x) {
+      const float d = yl[(size_t)i * B + f] - y[(size_t)i * B + f];
+      if (extra) extra[(size_t)i * B + f] = -e * w[f] * d;
+      else acc += (double)w[f] * (double)d * (double)d;
+    }
+    if (extra) continue;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < 8; ++q) t += red[q];
+      part[(size_t)blockIdx.x * k + i] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// Loss, eigenvalues, ordering and the coefficient vectors of both backward passes.  Stats layout as cvf_eigen_stats
+// (S0, S1[k], S2[k*k], SD[k]; SD unused).  Outputs in the cvf_eigen_combine layout with cD = 0, plus E[k] at the end of `out`.
+__global__ void tlag_combine_kernel(const double* __restrict__ S, const double* __restrict__ Sl, const double* __restrict__ SX, int k,
+                                    double alpha, double tau, int sort, const EigW eig_w, double* __restrict__ out,
+                                    double* __restrict__ out_lag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double S0 = S[0], S0l = Sl[0];
+  const double *S1 = S + 1, *S2 = S + 1 + k, *S1l = Sl + 1, *S2l = Sl + 1 + k;
+  double mean[kMaxK], var[kMaxK], meanl[kMaxK], varl[kMaxK], eig[kMaxK], a[kMaxK], b[kMaxK];
+  int cvec[kMaxK];
+  for (int i = 0; i < k; ++i) {
+    mean[i] = S1[i] / S0, var[i] = S2[i * k + i] / S0 - mean[i] * mean[i];
+    meanl[i] = S1l[i] / S0l, varl[i] = S2l[i * k + i] / S0l - meanl[i] * meanl[i];
+    eig[i] = SX[i] / (tau * S0 * (var[i] + varl[i]));   // core.py:428
+    cvec[i] = i, b[i] = 0.0;
+  }
+  if (sort) {
+    for (int i = 1; i < k; ++i) {
+      const int c = cvec[i];
+      int j = i - 1;
+      while (j >= 0 && eig[cvec[j]] > eig[c]) cvec[j + 1] = cvec[j], --j;
+      cvec[j + 1] = c;
+    }
+  }
+  // core.py:440 -- the numerator of term idx is that of network idx, its denominator that of network cvec[idx]
+  double obj = 0.0, pen = 0.0;
+  for (int idx = 0; idx < k; ++idx) {
+    const int c = cvec[idx];
+    const double V = var[c] + varl[c];
+    obj += eig_w.v[idx] * SX[idx] / (tau * S0 * V);
+    a[idx] = eig_w.v[idx] / (tau * S0 * V);
+    b[c] -= eig_w.v[idx] * SX[idx] / (tau * S0 * V * V);
+  }
+  double* C2 = out + 3 + 4 * k;
+  double* C2l = out_lag + 3 + 4 * k;
+  for (int i = 0; i < k; ++i) {
+    pen += (var[i] - 1.0) * (var[i] - 1.0);
+    for (int j = 0; j < k; ++j) {
+      C2l[i * k + j] = i == j ? 2.0 * b[i] / S0l : 0.0;
+      if (i == j) {
+        C2[i * k + j] = 2.0 * (b[i] + 2.0 * alpha * (var[i] - 1.0)) / S0;
+      } else {
+        const double cov = S2[i * k + j] / S0 - mean[i] * mean[j];
+        if (j > i) pen += cov * cov;
+        C2[i * k + j] = 2.0 * alpha * cov / S0;
+      }
+    }
+  }
+  out[0] = obj + alpha * pen, out[1] = obj, out[2] = pen;
+  for (int r = 0; r < k; ++r) {
+    out[3 + r] = eig[cvec[r]], out[3 + k + r] = (double)cvec[r];
+    out[3 + 2 * k + r] = mean[r], out[3 + 3 * k + r] = 0.0;
+    out_lag[3 + r] = eig[cvec[r]], out_lag[3 + k + r] = (double)cvec[r];
+    out_lag[3 + 2 * k + r] = meanl[r], out_lag[3 + 3 * k + r] = 0.0;
+    out[3 + 4 * k + k * k + r] = 2.0 * a[r];   // E
+  }
+  out_lag[0] = out[0], out_lag[1] = out[1], out_lag[2] = out[2];
 }
 
 }  // namespace cvf
@@ -914,7 +1005,7 @@ extern "C" int cvf_eigen_path(const cvf_preproc* pp, const cvf_mlp* net, int32_t
 extern "C" int cvf_eigen_stats(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net, int32_t k,
                                const float* params, float* y_out, double* stats_out, void* workspace, size_t workspace_bytes,
                                void* stream) {
-  return eigen_launch(false, x, w, B, pp, net, k, params, y_out, nullptr, stats_out, workspace, workspace_bytes, 0, stream);
+  return eigen_launch(false, x, w, B, pp, net, k, params, y_out, nullptr, nullptr, stats_out, workspace, workspace_bytes, 0, stream);
 }
 
 extern "C" int cvf_eigen_combine(const double* stats, int32_t k, double alpha, const double* eig_w, double beta, int32_t sort,
@@ -932,8 +1023,46 @@ extern "C" int cvf_eigen_combine(const double* stats, int32_t k, double alpha, c
 }
 
 extern "C" int cvf_eigen_grad(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net, int32_t k,
-                              const float* params, const float* y_in, const double* combine, double* grad_out, void* workspace,
-                              size_t workspace_bytes, int32_t scratch_valid, void* stream) {
-  return eigen_launch(true, x, w, B, pp, net, k, params, const_cast<float*>(y_in), combine, grad_out, workspace, workspace_bytes,
-                      scratch_valid, stream);
+                              const float* params, const float* y_in, const double* combine, const float* seed_extra,
+                              double* grad_out, void* workspace, size_t workspace_bytes, int32_t scratch_valid, void* stream) {
+  return eigen_launch(true, x, w, B, pp, net, k, params, const_cast<float*>(y_in), combine, seed_extra, grad_out, workspace,
+                      workspace_bytes, scratch_valid, stream);
+}
+
+extern "C" int cvf_eigen_tlag_terms(const float* y, const float* y_lag, const float* w, int64_t B, int32_t k, const double* coef,
+                                    double* sx_out, float* extra_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!y || !y_lag || !w || B < 1 || k < 1 || k > kMaxK || (!extra_out && (!sx_out || !workspace)) || (extra_out && !coef)) {
+    set_error("cvf_eigen_tlag_terms: bad argument");
+    return CVF_E_ARG;
+  }
+  long long grid = (long long)sm_count() * 4;
+  if ((B + 255) / 256 < grid) grid = (B + 255) / 256;
+  if (!extra_out && (size_t)grid * k * sizeof(double) > workspace_bytes) {
+    set_error("workspace too small");
+    return CVF_E_WORKSPACE;
+  }
+  CVF_LAUNCH(K_EIGEN_STATS, stream, tlag_terms_kernel<<<(int)grid, 256, 0, stream>>>(y, y_lag, w, B, k, coef, (double*)workspace, extra_out));
+  CVF_CUDA(cudaGetLastError());
+  if (!extra_out) {
+    CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<1, 32, 0, stream>>>((const double*)workspace, (int)grid, k, 0, k, sx_out));
+    CVF_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int cvf_eigen_tlag_combine(const double* stats, const double* stats_lag, const double* sx, int32_t k, double alpha,
+                                      const double* eig_w, double tau, int32_t sort, double* combine_out, double* combine_lag_out,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!stats || !stats_lag || !sx || !eig_w || !combine_out || !combine_lag_out || k < 1 || k > kMaxK || !(tau > 0.0)) {
+    set_error("cvf_eigen_tlag_combine: bad argument");
+    return CVF_E_ARG;
+  }
+  EigW ew;
+  for (int i = 0; i < kMaxK; ++i) ew.v[i] = i < k ? eig_w[i] : 0.0;
+  CVF_LAUNCH(K_EIGEN_COMBINE, stream,
+             tlag_combine_kernel<<<1, 32, 0, stream>>>(stats, stats_lag, sx, k, alpha, tau, sort, ew, combine_out, combine_lag_out));
+  CVF_CUDA(cudaGetLastError());
+  return 0;
 }

@@ -573,7 +573,8 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
 // rows, which would halve the number of resident warps: (s_1, scale G_1) go to global memory and pass 2b does that product.
 template <int H, int NH>
 __global__ void __launch_bounds__(256, 1)
-pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp) {
+pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp,
+             const float* __restrict__ seed_extra) {
   extern __shared__ __align__(16) float sm[];
   typedef Img<H, NH> I;
   constexpr int HP = H / 2, RP = kRowPad, TQ = H / 4;
@@ -632,6 +633,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         for (int j = 0; j < kMaxK; ++j)
           if (j < k) s += c_C2[n * k + j] * ((double)ysv[j] - c_mean[j]);
         seed = (float)((double)wf * s);
+        if (seed_extra != nullptr && f < P.B) seed += __ldg(seed_extra + (size_t)n * P.B + f);   // transfer-operator term
       }
       const float scale = (float)(2.0 * (double)wf * c_cD[n]);
       // ---- joint forward, layer 1: (z, zdot) = W1 (r, v) + (b1, 0); v = scale * J_r J_r^T u built on the fly
@@ -1115,8 +1117,8 @@ static int run_stats(const cvf_preproc* pp, const NetPlan& np, int k, const floa
 
 template <int H, int NH>
 static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
-                    const float* params, const double* combine, double* grad_out, void* workspace, size_t ws_bytes,
-                    int scratch_valid, cudaStream_t stream) {
+                    const float* params, const double* combine, const float* seed_extra, double* grad_out, void* workspace,
+                    size_t ws_bytes, int scratch_valid, cudaStream_t stream) {
   FastPlan P;
   const size_t need = plan_scratch<H, NH>(&P, pp, np, k, B, workspace);
   if (need > ws_bytes) {
@@ -1137,7 +1139,7 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   const long long n_tiles = P.Bp / 32;
   long long grid = sm_count();
   if ((n_tiles + nw - 1) / nw < grid) grid = (n_tiles + nw - 1) / nw;
-  CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH)));
+  CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra));
   CVF_CUDA(cudaGetLastError());
   const int n_part = k * np.n_params;
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, nw * n_part, 0, n_part, grad_out));
@@ -1190,9 +1192,9 @@ int fast_eigen_stats(const cvf_preproc* pp, const NetPlan& np, int k, const floa
 }
 
 int fast_eigen_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
-                    const float* params, const double* combine, double* grad_out, void* workspace, size_t ws_bytes,
-                    int scratch_valid, cudaStream_t stream) {
-  CVF_FAST_DISPATCH(run_grad, pp, np, k, x, w, B, params, combine, grad_out, workspace, ws_bytes, scratch_valid, stream);
+                    const float* params, const double* combine, const float* seed_extra, double* grad_out, void* workspace,
+                    size_t ws_bytes, int scratch_valid, cudaStream_t stream) {
+  CVF_FAST_DISPATCH(run_grad, pp, np, k, x, w, B, params, combine, seed_extra, grad_out, workspace, ws_bytes, scratch_valid, stream);
   set_error("fast eigen path: shape not instantiated");
   return CVF_E_UNSUPPORTED;
 }

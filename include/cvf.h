@@ -112,8 +112,24 @@ int cvf_eigen_combine(const double* stats, int32_t k, double alpha, const double
  * summed over this rank's frames.  scratch_valid = 1 promises that `workspace` still holds what the cvf_eigen_stats
  * call on the SAME x, w, params left there (the normal loss -> backward sequence); 0 recomputes it. */
 int cvf_eigen_grad(const float* x, const float* w, int64_t B, const cvf_preproc* pp, const cvf_mlp* net,
-                   int32_t k, const float* params, const float* y_in, const double* combine,
+                   int32_t k, const float* params, const float* y_in, const double* combine, const float* seed_extra,
                    double* grad_out, void* workspace, size_t workspace_bytes, int32_t scratch_valid, void* stream);
+/* seed_extra (NULL for the generator loss): [k,B] per-frame additions to d loss / d y_i, see the transfer-operator calls below */
+
+/* ---- EigenFunctionTask.loss_func, transfer-operator branch (lag_tau > 0: core.py:412-416,428,440) ----
+ * y = model(pp(X)) and y' = model(pp(X_lagged)) come from two cvf_eigen_stats calls (their SD entries are not used).
+ * cvf_eigen_tlag_terms, extra_out == NULL: sx_out[i] = sum_f w_f (y'_i - y_i)^2 (workspace: >= 4 * SMs * k doubles);
+ *                       extra_out != NULL: extra_out[i][f] = coef[i] w_f (y_i - y'_i), the seed_extra of the backward pass on X
+ *                       (its negative is the seed_extra of the backward pass on X_lagged).
+ * cvf_eigen_tlag_combine: loss, eigenvalues, cvec, objective, penalty (core.py:428-455, including the reference's pairing of
+ *   numerator idx with denominator cvec[idx] at core.py:440) and the coefficient vectors of the two backward passes, both in the
+ *   cvf_eigen_combine layout; combine_out carries k more doubles at its end, the coef[] of cvf_eigen_tlag_terms.
+ *   tau = traj_dt * lag_idx;  eig_w: HOST array [k]. */
+int cvf_eigen_tlag_terms(const float* y, const float* y_lag, const float* w, int64_t B, int32_t k, const double* coef,
+                         double* sx_out, float* extra_out, void* workspace, size_t workspace_bytes, void* stream);
+int cvf_eigen_tlag_combine(const double* stats, const double* stats_lag, const double* sx, int32_t k, double alpha,
+                           const double* eig_w, double tau, int32_t sort, double* combine_out, double* combine_lag_out,
+                           void* stream);
 
 /* ---- AutoEncoderTask.weighted_MSE_loss + backward (core.py:652-666,708) ---- */
 size_t cvf_ae_workspace_bytes(const cvf_mlp* net);

@@ -334,6 +334,117 @@ def test_eigen_train_matches_reference_run(tmp_path):
         np.testing.assert_allclose(p.detach().cpu().numpy(), d[f"final_{j}"], atol=2e-4)
 
 
+# --------------------------------------------------------------------------------------------- transfer operator
+def test_eigen_lag_loss_matches_reference_golden(tmp_path):
+    """Transfer-operator branch (lag_tau > 0, reference core.py:412-416,428,440) against the reference's own golden run:
+    loss, eigenvalues, objective, penalty, cvec and every parameter gradient."""
+    from colvarsfinder import core, nn
+    c = C.eigen_case("eigen_2d_lag")
+    lag = int(round(c["lag_tau"] / c["dt"]))
+    model = nn.EigenFunctions(c["layer_dims"], c["k"])
+    with torch.no_grad():
+        for i in range(c["k"]):
+            for p, v in zip(model.eigen_funcs[i].parameters(), c["params"][i]):
+                p.copy_(torch.as_tensor(v))
+    traj = FakeTrajectory(c["X"], c["w"].astype(np.float64), dt=c["dt"])
+    task = core.EigenFunctionTask(traj, torch.nn.Identity(), model, str(tmp_path), c["alpha"], c["eig_w"], beta=c["beta"],
+                                  lag_tau=c["lag_tau"], sort_eigvals_in_training=c["sort"], k=c["k"], device=DEV, verbose=False,
+                                  debug_mode=False)
+    assert task.lag_idx == lag
+    X, w = task._traj, task._weights
+    out = task.loss_func(X[:-lag].contiguous(), w[:-lag].contiguous(), X[lag:].contiguous(), w[lag:].contiguous())
+    out[0].backward()
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    gold = dict(loss=float(c["g64_loss"]), obj=float(c["g64_obj"]), pen=float(c["g64_pen"]), eig=c["g64_eig"],
+                cvec=c["g64_cvec"], grads=c["g64"], loss32=float(c["r32_loss"]), obj32=float(c["r32_obj"]),
+                pen32=float(c["r32_pen"]), eig32=c["r32_eig"], grads32=c["g32"])
+    _check_eigen(c, out, grads, gold, "eigen_2d_lag")
+
+
+@pytest.mark.parametrize("case", ["dipeptide_fast_k3", "ring_general_k2_nosort"])
+def test_eigen_lag_loss_matches_autograd_oracle(case, tmp_path):
+    """Same branch on the fast kernels (aligned dipeptide frames, k = 3) and the general kernels (unsorted, k = 2) against
+    the autograd restatement of the reference formula."""
+    from colvarsfinder import core, nn, utils
+    lag, B = 3, 1000
+    if case == "dipeptide_fast_k3":
+        dims, k, sort = [66, 20, 20, 20, 1], 3, True
+        X = ref_torch.synth_frames(BASE, B + lag, seed=31)
+        pp, ppo = utils.Align(BASE, list(range(22))), ref_torch.Preprocess(ref_torch.Align(BASE, list(range(22))), None)
+    else:
+        dims, k, sort = [2, 9, 7, 1], 2, False
+        X = np.random.default_rng(5).normal(size=(B + lag, 2)).astype(np.float32)
+        pp, ppo = torch.nn.Identity(), ref_torch.Preprocess()
+    w = ref_torch.boltzmann_weights(B + lag, seed=8)
+    nets = _random_nets(dims, k, seed=17)
+    eig_w = [1.0, 0.6, 0.3][:k]
+    model = nn.EigenFunctions(dims, k)
+    with torch.no_grad():
+        for i in range(k):
+            for p, v in zip(model.eigen_funcs[i].parameters(), nets[i]):
+                p.copy_(torch.as_tensor(v))
+    task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64), dt=0.5), pp, model, str(tmp_path), 15.0, eig_w,
+                                  lag_tau=1.5, sort_eigvals_in_training=sort, k=k, device=DEV, verbose=False, debug_mode=False)
+    assert task.lag_idx == lag and task._ctx.fast_path == (case == "dipeptide_fast_k3")
+    Xd, wd = task._traj, task._weights
+    out = task.loss_func(Xd[:-lag].contiguous(), wd[:-lag].contiguous(), Xd[lag:].contiguous(), wd[lag:].contiguous())
+    out[0].backward()
+    # oracle in float64
+    tn = [[torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in net] for net in nets]
+    Xt, wt = torch.tensor(X, dtype=torch.float64), torch.tensor(w, dtype=torch.float64)
+    ref = ref_torch.eigen_loss(Xt[:-lag], wt[:-lag], tn, ppo.double(), 15.0, eig_w, sort=sort, X_lagged=Xt[lag:],
+                               weight_lagged=wt[lag:], lag_time=1.5)
+    ref[0].backward()
+    assert abs(float(out[0]) - float(ref[0])) <= 2e-5 * abs(float(ref[0]))
+    np.testing.assert_allclose(out[1].cpu().numpy(), np.asarray(ref[1], dtype=np.float64), rtol=2e-4)
+    assert list(out[4].cpu().numpy()) == [int(v) for v in ref[4]]
+    for i in range(k):
+        for p, t in zip(model.eigen_funcs[i].parameters(), tn[i]):
+            g64 = t.grad.numpy()
+            if np.abs(g64).max() < 1e-9 * abs(float(ref[0])):
+                continue
+            assert C.rel_l2(p.grad.cpu().numpy(), g64) < 2e-4, (i, C.rel_l2(p.grad.cpu().numpy(), g64))
+
+
+def test_eigen_lag_train_follows_oracle_loop(tmp_path):
+    """train() with a time lag: the split is drawn on the first n - lag frames, X_lagged = traj[index + lag]
+    (reference core.py:461-512); per-iteration losses follow a CPU autograd loop on the same batches."""
+    from colvarsfinder import core, nn
+    n, lag, bs = 900, 2, 200
+    rng = np.random.default_rng(3)
+    X = np.cumsum(rng.normal(scale=0.2, size=(n, 2)), 0).astype(np.float32)
+    X -= X.mean(0)
+    w = ref_torch.boltzmann_weights(n, seed=4)
+    torch.manual_seed(21)
+    model = nn.EigenFunctions([2, 8, 8, 1], 2)
+    nets = [[p.detach().clone().double().requires_grad_() for p in f.parameters()] for f in model.eigen_funcs]
+    task = core.EigenFunctionTask(FakeTrajectory(X.astype(np.float64), w.astype(np.float64), dt=0.1), torch.nn.Identity(), model,
+                                  str(tmp_path), 10.0, [1.0, 0.5], lag_tau=0.2, learning_rate=0.01, k=2, batch_size=bs,
+                                  num_epochs=2, test_ratio=0.25, save_model_every_step=0, device=DEV, verbose=False,
+                                  debug_mode=False)
+    np.random.seed(5)
+    task.train()
+    got = np.concatenate([l[0].numpy()[:, 0] for l in task.loss_list])
+    # oracle loop
+    np.random.seed(5)
+    tr, te = ref_torch.split_indices(n - lag, 0.25, draws=2)
+    Xt, wt = torch.tensor(X, dtype=torch.float64), torch.tensor(w, dtype=torch.float64)
+    opt = torch.optim.Adam([p for net in nets for p in net], lr=0.01)
+    want = []
+    spans, _ = ref_torch.batches(len(tr), bs)
+    for epoch in range(2):
+        for a, b in spans:
+            idx = torch.as_tensor(tr[a:b])
+            opt.zero_grad()
+            out = ref_torch.eigen_loss(Xt[idx], wt[idx], nets, ref_torch.Preprocess(), 10.0, [1.0, 0.5], X_lagged=Xt[idx + lag],
+                                       weight_lagged=wt[idx + lag], lag_time=0.2)
+            out[0].backward()
+            opt.step()
+            want.append(float(out[0]))
+    assert got.shape == (len(want),)
+    np.testing.assert_allclose(got, want, rtol=2e-3)
+
+
 # --------------------------------------------------------------------------------------------- autoencoder
 def _ae_task(c, tmp, F=None, w=None):
     from colvarsfinder import core, nn
@@ -419,9 +530,9 @@ def test_save_model_and_unsupported(tmp_path):
     sd = torch.load(tmp_path / "latest" / "model.pt")
     assert "eigen_funcs.1.2.bias" in sd
     traj = FakeTrajectory(c["X"], c["w"].astype(np.float64), dt=0.1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError, match="not divisable"):
         core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1), str(tmp_path), 1.0, [1.0],
-                               lag_tau=0.2, device=DEV, verbose=False)
+                               lag_tau=0.25, device=DEV, verbose=False)
     with pytest.raises(RuntimeError, match="Tanh"):
         core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1, torch.nn.ReLU()), str(tmp_path), 1.0,
                                [1.0], device=DEV, verbose=False)
