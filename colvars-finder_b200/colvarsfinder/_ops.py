@@ -49,6 +49,7 @@ class PreprocSpec:
         from . import utils
         self.device = torch.device(device)
         self._keep = []
+        self.alignment_elided = False
         s = _lib.Preproc()
         frame_shape = tuple(int(v) for v in frame_shape)
         tot_dim = int(np.prod(frame_shape))
@@ -95,6 +96,12 @@ class PreprocSpec:
             n_feat_atoms = len(used)
             positions_only = all(t == _lib.FEAT_POSITION for t, _ in records) and len(records) == n_feat_atoms
             align_idx = [] if align is None else [int(a) for a in align.align_idx.cpu().tolist()]
+            # Bond lengths, angles and dihedrals do not change under the rigid motion the alignment applies, and with
+            # diag_coeff = 1 neither does |grad_x f|^2: r(x) and its Jacobian products are evaluated on the raw frame and
+            # the Kabsch step (with its Jacobian) drops out of the training step.  (pp_layer(x) itself still aligns.)
+            self.alignment_elided = bool(align_idx) and diag is None and all(t != _lib.FEAT_POSITION for t, _ in records)
+            if self.alignment_elided:
+                align_idx = []
             for a in align_idx:
                 if not 0 <= a < n_atoms:
                     raise RuntimeError(f"alignment atom {a} outside the {n_atoms} input atoms")

@@ -589,6 +589,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   float* Xr = Zr + 2 * NH * H * RP;                        // [2H]     s_l | G_l; flush buffer
   float* Sr = Zr;                                          // [drp]    r staged for layer 1
   float* Su = Zr + drp * RP;                               // [drp]    u staged for layer 1
+  float* Sj = Zr + 2 * drp * RP;                           // [12]     alignment-Jacobian vectors staged for layer 1
   for (int n = 0; n < k; ++n)
     for (int i = tid; i < P.img2_floats; i += nt) wsm[n * P.img2_floats + i] = P.img[(size_t)n * P.img_floats + i];
   for (int i = tid; i < P.geo_floats; i += nt) geo[i] = P.img[(size_t)k * P.img_floats + i];
@@ -617,6 +618,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       __syncwarp();   // the previous network's flush has finished reading the X rows
       stage_rows(Sr, P.Y + t * 32, d_r, P.Bp, lane);
       stage_rows(Su, Ut, d_r, P.Bp, lane);
+      if (P.kind == 1) stage_rows(Sj, P.JQ + ((size_t)n * 12) * P.Bp + t * 32, 12, P.Bp, lane);
       // L2 prefetch of what is read next: the next network's u rows, or the next tile's r rows and first u rows
       if (n + 1 < k) {
         prefetch_rows(P.U + ((size_t)(n + 1) * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
@@ -625,6 +627,8 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         prefetch_rows(P.Y + t_next * 32, d_r, P.Bp, lane);
         prefetch_rows(P.U + t_next * 32, d_r, P.Bp, lane);
         if (P.kind == 1) prefetch_rows(P.JQ + t_next * 32, 12, P.Bp, lane);
+        prefetch_rows(P.Ys + t_next * 32, k, P.Bp, lane);
+        if (lane == 0) prefetch_l2_line(w + t_next * 32);
       }
       float seed;
       {
@@ -641,13 +645,13 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll
       for (int j = 0; j < HP; ++j) z[j] = lds2(W + I::b1(drp) + 2 * j), zd[j] = make_float2(0.f, 0.f);
       if (P.kind == 1) {
-        const float* jq = P.JQ + ((size_t)n * 12) * P.Bp + f;
-        const cvf_v3 gm = v3(__ldg(jq), __ldg(jq + P.Bp), __ldg(jq + 2 * P.Bp));
-        const cvf_v3 q = v3(__ldg(jq + 3 * P.Bp), __ldg(jq + 4 * P.Bp), __ldg(jq + 5 * P.Bp));
-        const cvf_v3 dc = v3(__ldg(jq + 6 * P.Bp), __ldg(jq + 7 * P.Bp), __ldg(jq + 8 * P.Bp));
-        const cvf_v3 omv = v3(__ldg(jq + 9 * P.Bp), __ldg(jq + 10 * P.Bp), __ldg(jq + 11 * P.Bp));
         cp_async_wait_all();
         __syncwarp();
+        const float* jq = Sj + lane;
+        const cvf_v3 gm = v3(jq[0], jq[RP], jq[2 * RP]);
+        const cvf_v3 q = v3(jq[3 * RP], jq[4 * RP], jq[5 * RP]);
+        const cvf_v3 dc = v3(jq[6 * RP], jq[7 * RP], jq[8 * RP]);
+        const cvf_v3 omv = v3(jq[9 * RP], jq[10 * RP], jq[11 * RP]);
 #pragma unroll 2
         for (int a = 0; a < P.n_atoms; ++a) {
           const int r = 3 * a;
@@ -960,7 +964,7 @@ static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int drp) {
   return ((size_t)k * img_floats + geo_floats + (size_t)drp * kP1Frames) * sizeof(float);
 }
 static int pass2_rows_per_warp(int drp, int H, int NH) {
-  const int need = 2 * NH * H + 2 * H, stage = 2 * drp;
+  const int need = 2 * NH * H + 2 * H, stage = 2 * drp + 12;
   return need > stage ? need : stage;
 }
 static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH, int warps) {

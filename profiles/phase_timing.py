@@ -26,7 +26,7 @@ import bench  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 wl = sys.argv[2] if len(sys.argv) > 2 else "c3"
 dev = torch.device("cuda", 0)
-step, X, w, task, launches, dominant = bench.build_workload(wl, n, dev, seed=1)
+step, X, w, task = bench.build_workload(wl, n, dev, seed=1)
 lib = _lib.lib()
 lib.cvf_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int]
 buf = (C.c_ulonglong * 16)()

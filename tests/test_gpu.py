@@ -259,6 +259,40 @@ def test_eigen_general_kernels_on_fast_shapes(name, tmp_path):
     assert abs(res[0][0] - res[1][0]) <= 2e-5 * abs(res[1][0])
 
 
+def test_eigen_invariant_features_with_alignment_matches_oracle(tmp_path):
+    """C4-style pre-processing: Kabsch alignment followed by bond / angle / dihedral features only.  The step elides the
+    alignment (the features are invariant under it); the oracle goes through the alignment and its Jacobian."""
+    from colvarsfinder import core, nn, utils
+    B, k, dims = 700, 2, [8, 16, 16, 1]
+    heavy = [1, 4, 5, 6, 8, 10, 14, 15, 16, 18]
+    feats = [("bond", [1, 4]), ("bond", [4, 8]), ("angle", [4, 6, 8]), ("dihedral", [4, 6, 8, 14]), ("dihedral", [6, 8, 14, 16]),
+             ("bond", [10, 18])]
+    X = ref_torch.synth_frames(BASE, B, seed=41)
+    w = ref_torch.boltzmann_weights(B, seed=42)
+    nets = _random_nets(dims, k, seed=43)
+    pp = utils.Preprocessing(utils.Align(BASE[heavy], heavy), utils.FeatureMap(feats))
+    ppo = cf.Preproc(align_idx=heavy, ref=BASE[heavy], feats=feats)
+    model = nn.EigenFunctions(dims, k)
+    with torch.no_grad():
+        for i in range(k):
+            for p, v in zip(model.eigen_funcs[i].parameters(), nets[i]):
+                p.copy_(torch.as_tensor(v))
+    task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64), dt=1.0), pp, model, str(tmp_path), 20.0, [1.0, 0.5], k=k,
+                                  device=DEV, verbose=False, debug_mode=False)
+    assert task._ctx.spec.alignment_elided
+    out = task.loss_func(task._traj, task._weights, None, None)
+    out[0].backward()
+    comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, [1.0, 0.5])
+    assert list(out[4].cpu().numpy()) == list(comb["cvec"])
+    assert abs(float(out[0]) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
+    np.testing.assert_allclose(out[1].cpu().numpy(), comb["eig"], rtol=2e-4)
+    for i in range(k):
+        for p, g in zip(model.eigen_funcs[i].parameters(), g64[i]):
+            if np.abs(g).max() < 1e-9 * abs(comb["loss"]):
+                continue
+            assert C.rel_l2(p.grad.cpu().numpy(), g) < 2e-3
+
+
 def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
     """Size-independent property at BASELINE scale (2^20 frames of C3): the fp64 batch sums of a batch equal the sum over
     its halves, and the gradient sums of pass 2 (at fixed coefficients) are additive too."""
