@@ -49,6 +49,8 @@ WORKLOADS = {
     "c1": ("2-d EigenFunctionTask, generator loss, k=1, Identity pre-processing, net [2,20,20,20,1]", 12, 12040),
     "c4": ("166-atom chain EigenFunctionTask, generator loss, k=3, 45 distances + 18 dihedrals (d_r=81), "
            "nets [81,20,20,20,1]", 1996, 128500),
+    "c5": ("1000-atom AutoEncoderTask step on position features (d_r=3000), enc [3000,512,512,2], dec [2,512,512,3000]; "
+           "layer-wise fp32 SIMT products (no tensor-core path yet)", 12004, 21590016),
 }
 METRIC = "train-step frames/sec"
 # fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
@@ -144,6 +146,14 @@ def build_workload(name, n_frames, dev, seed, lr=1e-3):
             model = nn.AutoEncoder([66, 20, 20, 20, 2], [2, 10, 10, 66])
             task = core.AutoEncoderTask(small, align, model, tmp, learning_rate=lr, device=dev, verbose=False, debug_mode=False)
             X = task.preprocessing_layer(X).reshape(n_frames, 66).contiguous()   # the pre-pass is outside the step (core.py:635)
+    elif name == "c5":
+        g = torch.Generator(device=dev).manual_seed(seed)
+        X = torch.randn(n_frames, 3000, generator=g, device=dev)          # features of the pre-pass (core.py:635) directly
+        w = torch.ones(n_frames, device=dev)
+        small = FakeTrajectory(X[:256].cpu().numpy(), np.ones(256), dt=1.0)
+        model = nn.AutoEncoder([3000, 512, 512, 2], [2, 512, 512, 3000])
+        task = core.AutoEncoderTask(small, torch.nn.Identity(), model, tmp, learning_rate=lr, device=dev, verbose=False,
+                                    debug_mode=False)
     elif name == "c1":
         X = bd.ring_2d(n_frames, dev, seed)
         w = torch.ones(n_frames, device=dev)
@@ -189,7 +199,11 @@ def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(2026)
-    if name in ("c3", "c2"):
+    if name == "c5":
+        X = torch.randn(n_frames, 3000)
+        w = torch.ones(n_frames)
+        pp = None
+    elif name in ("c3", "c2"):
         base = ref_torch.DIPEPTIDE_NM * 10.0
         X = torch.as_tensor(ref_torch.synth_frames(base, n_frames, seed=seed))
         w = torch.as_tensor(ref_torch.boltzmann_weights(n_frames, seed=seed)) if name == "c3" else torch.ones(n_frames)
@@ -207,12 +221,13 @@ def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
         import bench_data as bd
         feats, align_idx = bd.c4_features()
         pp = ref_torch.Preprocess(ref_torch.Align(base[align_idx], align_idx), ref_torch.FeatureMap(feats))
-    if name == "c2":
-        enc = [p.requires_grad_() for p in ref_torch.init_mlp_params([66, 20, 20, 20, 2])]
-        dec = [p.requires_grad_() for p in ref_torch.init_mlp_params([2, 10, 10, 66])]
+    if name in ("c2", "c5"):
+        ed, dd = ([66, 20, 20, 20, 2], [2, 10, 10, 66]) if name == "c2" else ([3000, 512, 512, 2], [2, 512, 512, 3000])
+        enc = [p.requires_grad_() for p in ref_torch.init_mlp_params(ed)]
+        dec = [p.requires_grad_() for p in ref_torch.init_mlp_params(dd)]
         params = enc + dec
         with torch.no_grad():
-            Fx = pp(X.double()).float()
+            Fx = pp(X.double()).float() if pp is not None else X
 
         def loss_fn():
             return ref_torch.ae_loss(Fx, w, enc, dec)
@@ -263,15 +278,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=1 << 22, help="frames per GPU per step")
-    ap.add_argument("--cpu-frames", type=int, default=100000, help="frames per step of the CPU sample")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 2^22; 2^16 for c5)")
+    ap.add_argument("--cpu-frames", type=int, default=None, help="frames per step of the CPU sample (default 100000; 4096 for c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world, local = dist_env()
+    if args.frames is None:
+        args.frames = 1 << 16 if args.workload == "c5" else 1 << 22
+    if args.cpu_frames is None:
+        args.cpu_frames = 4096 if args.workload == "c5" else 100000
     desc, bytes_per_frame, flops_per_frame = WORKLOADS[args.workload]
     config = {"workload": f"{args.workload.upper()}: {desc}", "frames_per_gpu_per_step": args.frames,
               "global_batch": args.frames * max(world, 1), "optimizer": "Adam", "parallelism": f"dp{max(world, 1)}",
               "l2_policy": "inputs larger than L2 (no flush needed)"}
+    if args.frames * bytes_per_frame < 160e6:
+        config["l2_policy"] = "batch smaller than L2: steps are back to back on the same batch (intermediates exceed L2)"
 
     if args.impl == "reference":
         if rank != 0:

@@ -383,17 +383,27 @@ class AEContext:
         L = _lib.lib()
         self.n_params = int(L.cvf_mlp_param_count(C.byref(self.mlp)))
         assert self.n_params == self.flat.n
-        self.ws_bytes = int(L.cvf_ae_workspace_bytes(C.byref(self.mlp)))
-        self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.ws_bytes, self.ws_frames, self.workspace = 0, 0, None
         self.d_r = e_dims[0]
+
+    def _workspace_for(self, B):
+        if self.workspace is None or B > self.ws_frames:
+            need = int(_lib.lib().cvf_ae_workspace_bytes(C.byref(self.mlp), B))
+            if need <= 0:
+                raise RuntimeError("cvf_ae_workspace_bytes: " + _lib.lib().cvf_last_error_string().decode("utf-8", "replace"))
+            self.workspace = None
+            self.workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.ws_bytes, self.ws_frames = need, B
+        return self.workspace.data_ptr()
 
     def step(self, F, weight, want_grad):
         """One pass over this rank's frames -> fp64 [2 + n_params]: sum w|e|^2, sum w, gradient of the first sum."""
         buf = torch.empty(2 + (self.n_params if want_grad else 0), dtype=torch.float64, device=self.device)
         gptr = buf.data_ptr() + 16 if want_grad else None
+        ws = self._workspace_for(F.shape[0])
         _lib.check(_lib.lib().cvf_ae_step(F.data_ptr(), weight.data_ptr(), F.shape[0], C.byref(self.mlp),
-                                          self.flat.flat.data_ptr(), buf.data_ptr(), gptr, self.workspace.data_ptr(),
-                                          self.ws_bytes, _stream()), "cvf_ae_step")
+                                          self.flat.flat.data_ptr(), buf.data_ptr(), gptr, ws, self.ws_bytes, _stream()),
+                   "cvf_ae_step")
         return buf
 
 

@@ -193,6 +193,11 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
   if (tid < 2) part[tid] = stat_acc;
 }
 
+// cvf_ae_wide.cu: layer-by-layer dense products for networks whose weights do not fit shared memory
+size_t wide_ae_workspace_bytes(const NetPlan& np, long long B);
+int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long B, const float* params, double* sums_out,
+                 double* grad_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace cvf
 
 using namespace cvf;
@@ -210,8 +215,7 @@ static int ae_plan(const cvf_mlp* net, AePlan* P) {
   for (int c = 0; c < 3; ++c) {
     if (ae_layout(P, Fs[c]) <= cap) break;
     if (c == 2) {
-      set_error("autoencoder state does not fit shared memory (%zu B at 32 frames, %zu available); wide layers need the "
-                "tensor-core path, which this build does not have", P->smem_bytes, cap);
+      set_error("autoencoder state does not fit shared memory (%zu B at 32 frames, %zu available)", P->smem_bytes, cap);
       return CVF_E_UNSUPPORTED;
     }
   }
@@ -219,22 +223,39 @@ static int ae_plan(const cvf_mlp* net, AePlan* P) {
   return 0;
 }
 
-extern "C" size_t cvf_ae_workspace_bytes(const cvf_mlp* net) {
+// 1 if the fused shared-memory kernel takes this chain, 0 if the layer-wise products do, < 0 if neither can
+static int ae_path(const cvf_mlp* net, AePlan* P) {
+  const int e = ae_plan(net, P);
+  if (e == 0) return 1;
+  if (e != CVF_E_UNSUPPORTED) return e;
   NetPlan np;
-  if (make_net_plan(net, &np)) return 0;
-  return (size_t)(2 + np.n_params) * sizeof(double) * (size_t)sm_count();
+  if (make_net_plan(net, &np)) return CVF_E_ARG;
+  if (np.dims[0] != np.dims[np.L] || np.act[np.L - 1] != 0) {
+    set_error("layer-wise autoencoder path: the chain must map R^d to R^d and end in a linear layer");
+    return CVF_E_UNSUPPORTED;
+  }
+  return 0;
+}
+
+extern "C" size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B) {
+  AePlan P;
+  const int path = ae_path(net, &P);
+  if (path < 0 || B < 1) return 0;
+  if (path == 0) return wide_ae_workspace_bytes(P.net, B);
+  return (size_t)(2 + P.net.n_params) * sizeof(double) * (size_t)sm_count();
 }
 
 extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
                            double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AePlan P;
-  int e = ae_plan(net, &P);
-  if (e) return e;
+  const int path = ae_path(net, &P);
+  if (path < 0) return path;
   if (!feat || !w || !params || !sums_out || !workspace || B < 1) {
     set_error("cvf_ae_step: null pointer or empty batch");
     return CVF_E_ARG;
   }
+  if (path == 0) return wide_ae_step(P.net, feat, w, B, params, sums_out, grad_out, workspace, workspace_bytes, stream);
   const bool grad = grad_out != nullptr;
   const int n_part = 2 + (grad ? P.net.n_params : 0);
   const long long n_tiles = (B + P.F - 1) / P.F;

@@ -132,7 +132,9 @@ int cvf_eigen_tlag_combine(const double* stats, const double* stats_lag, const d
                            void* stream);
 
 /* ---- AutoEncoderTask.weighted_MSE_loss + backward (core.py:652-666,708) ---- */
-size_t cvf_ae_workspace_bytes(const cvf_mlp* net);
+/* bytes of scratch for a batch of B frames.  Chains whose weights fit shared memory run in one fused kernel (per-CTA partial
+ * sums only); wider ones run layer by layer as dense fp32 products over chunks of frames and keep the chunk's activations here. */
+size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B);
 /* sums_out[2] = { sum_f w_f |dec(enc(F_f)) - F_f|^2 , sum_f w_f };  grad_out [param_count] fp64 holds the
  * gradient of the FIRST sum (not yet divided by sum w).  grad_out may be NULL (evaluation only). */
 int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,

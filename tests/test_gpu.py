@@ -526,6 +526,37 @@ def test_ae_loss_matches_oracle_ragged_sizes(B, tmp_path):
         assert C.rel_l2(g, go) < 2e-5
 
 
+@pytest.mark.parametrize("B", [130, 1000, 33000])
+def test_ae_wide_layers_match_oracle(B, tmp_path):
+    """Networks whose weights do not fit shared memory take the layer-wise path (cvf_ae_wide.cu: fp32 SGEMMs with fused
+    epilogues, split-K weight gradients); 33000 frames span two chunks."""
+    from colvarsfinder import core, nn
+    e_dims, d_dims = [150, 260, 200, 2], [2, 200, 260, 150]
+    torch.manual_seed(B)
+    enc = [p.numpy() for p in ref_torch.init_mlp_params(e_dims)]
+    dec = [p.numpy() for p in ref_torch.init_mlp_params(d_dims)]
+    rng = np.random.default_rng(B)
+    F = rng.normal(size=(B, 150)).astype(np.float32)
+    w = ref_torch.boltzmann_weights(B, seed=B)
+    model = nn.AutoEncoder(e_dims, d_dims)
+    with torch.no_grad():
+        for p, v in zip(model.encoder.parameters(), enc):
+            p.copy_(torch.as_tensor(v))
+        for p, v in zip(model.decoder.parameters(), dec):
+            p.copy_(torch.as_tensor(v))
+    task = core.AutoEncoderTask(FakeTrajectory(F, w.astype(np.float64)), torch.nn.Identity(), model, str(tmp_path), device=DEV,
+                                verbose=False, debug_mode=False)
+    loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+    loss.backward()
+    lo, genc, gdec = cf.ae_loss_and_grads(F, w, enc, dec)
+    assert abs(float(loss) - lo) <= 1e-5 * abs(lo)
+    got = [p.grad.cpu().numpy() for p in model.encoder.parameters()] + [p.grad.cpu().numpy() for p in model.decoder.parameters()]
+    for g, go in zip(got, genc + gdec):
+        assert C.rel_l2(g, go) < 2e-5, C.rel_l2(g, go)
+    with torch.no_grad():
+        assert torch.equal(task.weighted_MSE_loss(task._feature_traj, task._weights), loss.detach())
+
+
 def test_ae_prepass_and_train_match_reference_run(tmp_path):
     from colvarsfinder import core, nn, utils
     d = C.load("train_ae_2d")

@@ -35,7 +35,11 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.cvf_eigen_num_stats(3) == 1 + 6 + 9 and lib.cvf_eigen_num_combine(3) == 3 + 12 + 9
     m = _lib.make_mlp([66, 20, 20, 20, 1], [1, 1, 1, 0])
     assert lib.cvf_mlp_param_count(C.byref(m)) == 2201
-    assert lib.cvf_ae_workspace_bytes(C.byref(m)) > 0
+    ae = _lib.make_mlp([66, 20, 2, 20, 66], [1, 0, 1, 0])
+    assert lib.cvf_ae_workspace_bytes(C.byref(ae), 1000) > 0
+    wide = _lib.make_mlp([3000, 512, 512, 2, 512, 512, 3000], [1, 1, 0, 1, 1, 0])      # layer-wise path: needs room for a chunk
+    assert lib.cvf_ae_workspace_bytes(C.byref(wide), 1000) > 1000 * 4 * (3000 + 512 + 512 + 2 + 512 + 512 + 3000)
+    assert lib.cvf_ae_workspace_bytes(C.byref(m), 1000) == 0                            # not an R^d -> R^d chain
 
 
 def test_sass_is_sm100_with_bulk_copies(built):
