@@ -194,6 +194,7 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
 }
 
 // cvf_ae_wide.cu: layer-by-layer dense products for networks whose weights do not fit shared memory
+int wide_ae_set_mode(int mode);
 size_t wide_ae_workspace_bytes(const NetPlan& np, long long B);
 int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long B, const float* params, double* sums_out,
                  double* grad_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
@@ -279,5 +280,13 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
     CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(P.net.n_params + 127) / 128, 128, 0, stream>>>((const double*)workspace, grid, n_part, 2,
                                                                              P.net.n_params, grad_out));
   CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cvf_ae_set_wide_path(int32_t mode) {
+  if (wide_ae_set_mode(mode)) {
+    set_error("cvf_ae_set_wide_path: mode must be 0 (tensor cores) or 1 (fp32 SIMT)");
+    return CVF_E_ARG;
+  }
   return 0;
 }

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include "cvf_common.cuh"
+#include "cvf_gemm.cuh"
 
 namespace cvf {
 namespace wide {
@@ -33,25 +34,6 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 }
 
 constexpr int BM = 128, BN = 128, BK = 16, LDS_ = BM + 4;   // shared tiles are [BK][BM + 4] floats
-
-enum Epilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2, EPI_MUL_OM = 3 };
-
-struct Gemm {
-  // C[m][n] = sum_k Aop[m][k] Bop[k][n],  m < M, n < N, k in this split's range
-  const float* A;
-  long long lda;
-  int a_kcontig;   // 1: Aop[m][k] = A[m * lda + k];   0: Aop[m][k] = A[k * lda + m]
-  const float* B;
-  long long ldb;
-  int b_kcontig;   // 1: Bop[k][n] = B[n * ldb + k];   0: Bop[k][n] = B[k * ldb + n]
-  float* C;
-  long long ldc;
-  long long c_split_stride;   // floats between the outputs of consecutive k-splits (0: single split)
-  int M, N, K, k_per_split;
-  int epi;
-  const float* bias;   // [N]
-  const float* act;    // EPI_MUL_OM: [M][ldc] activations A with C *= 1 - A^2
-};
 
 // Load one BK x 128 operand tile into registers (2 float4 per thread), then store it k-major into shared memory.
 struct TileRegs {
@@ -320,8 +302,10 @@ static void make_plan(const NetPlan& np, WidePlan* P) {
 }
 
 constexpr int kMaxSplits = 32;
+int g_wide_mode = 0;   // 0: tensor-core products (tcgen05, 3 x TF32; default), 1: fp32 SIMT products
 
 static int launch_gemm(const Gemm& g, int splits, cudaStream_t stream) {
+  if (g_wide_mode == 0) return launch_gemm_tc(g, splits, stream);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
   CVF_LAUNCH(K_AE_STEP, stream, sgemm_kernel<<<grid, 256, 0, stream>>>(g));
   CVF_CUDA(cudaGetLastError());
@@ -329,6 +313,12 @@ static int launch_gemm(const Gemm& g, int splits, cudaStream_t stream) {
 }
 
 }  // namespace wide
+
+int wide_ae_set_mode(int mode) {
+  if (mode != 0 && mode != 1) return CVF_E_ARG;
+  wide::g_wide_mode = mode;
+  return 0;
+}
 
 // bytes of workspace the layer-wise path wants for a batch of B frames (it works in chunks of frames that fit)
 size_t wide_ae_workspace_bytes(const NetPlan& np, long long B) {
@@ -433,7 +423,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         const int tiles = ((rows + BM - 1) / BM) * ((cols + BN - 1) / BN);
         int splits = (2 * sm_count() + tiles - 1) / tiles;
         if (splits > kMaxSplits) splits = kMaxSplits;
-        int kps = ((M + splits - 1) / splits + BK - 1) / BK * BK;
+        int kps = ((M + splits - 1) / splits + 31) / 32 * 32;
         splits = (M + kps - 1) / kps;
         Gemm g;
         memset(&g, 0, sizeof(g));

@@ -1,0 +1,298 @@
+// cvf_gemm_tc.cu -- C[M x N] = Aop[M x K] Bop[K x N] in fp32 accuracy on the 5th-generation tensor cores (tcgen05).
+//
+// fp32 operands are split while they are staged into shared memory, x = hi + lo with hi = x truncated to TF32 (10-bit
+// mantissa), and every 128 x 128 x 32 block is three kind::tf32 products accumulated in fp32 in tensor memory:
+//     D += Ahi Bhi + Alo Bhi + Ahi Blo          (the dropped lo*lo term is 2^-20 relative)
+// which keeps the 1e-5 parity target of the training step that a single TF32 pass (2^-11) cannot.
+//
+//   * operands: both tiles are staged K-major ([row][32 k] = 128-byte rows) in the canonical 128-byte-swizzled layout the
+//     UMMA shared-memory descriptor expects (8-row groups of 1024 bytes, 16-byte chunk index XOR row mod 8); the staging threads
+//     transpose on the fly when the global operand is contiguous along the other dimension;
+//   * one thread issues the MMAs (M = 128, N = 128, K = 8 per instruction; 12 per stage), completion is tracked with
+//     tcgen05.commit on an mbarrier per stage; the 256 threads stage block i+1 while the tensor core works on block i;
+//   * the 128 x 128 fp32 accumulator lives in 128 columns of tensor memory and is read back with tcgen05.ld (32 lanes x 32
+//     columns per warp instruction) for the fused epilogue (bias / tanh / multiplication by 1 - act^2).
+#include <stdint.h>
+
+#include "cvf_common.cuh"
+#include "cvf_gemm.cuh"
+
+namespace cvf {
+namespace wide {
+
+constexpr int TM = 128, TN = 128, TK = 32;            // CTA tile; TK fp32 = one 128-byte swizzle row
+constexpr int kTileBytes = TM * TK * 4;               // 16 KB per operand tile
+constexpr int kStageBytes = 4 * kTileBytes;           // Ahi, Alo, Bhi, Blo
+constexpr int kStages = 2;
+constexpr uint32_t kTmemCols = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// bounded wait: a descriptor mistake must not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spin = 0; spin < (1 << 26); ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: start address, stride between 8-row groups 1024 B,
+// descriptor version 1 (sm_100), layout type SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // bits 0-13
+  d |= (uint64_t)1 << 16;                             // leading byte offset: unused for a swizzled K-major atom (CUTLASS writes 1)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // version
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D fp32, A and B TF32, both K-major, N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// byte offset of (row, 16-byte chunk) inside a K-major 128-byte-swizzled tile
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+struct Stage4 {
+  float4 v[4];
+};
+
+// global -> registers: this thread's 16 floats of a 128 x 32 operand tile (rows = m or n, k0 .. k0+31), zero beyond the edges
+__device__ __forceinline__ void tc_load(Stage4& r, const float* __restrict__ P, long long ld, int kcontig, int row0, int nrows, int k0,
+                                        int k1, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kcontig) {   // (row = idx / 8, chunk = idx % 8): 4 consecutive k
+      const int idx = tid + 256 * i, row = row0 + (idx >> 3), k = k0 + 4 * (idx & 7);
+      if (row < nrows && k < k1) {
+        v = __ldg(reinterpret_cast<const float4*>(P + (size_t)row * ld + k));
+        if (k + 3 >= k1) {
+          if (k + 1 >= k1) v.y = 0.f;
+          if (k + 2 >= k1) v.z = 0.f;
+          v.w = 0.f;
+        }
+      }
+    } else {         // (k = idx / 32, 4 consecutive rows)
+      const int idx = tid + 256 * i, k = k0 + (idx >> 5), row = row0 + 4 * (idx & 31);
+      if (k < k1 && row < nrows) {
+        v = __ldg(reinterpret_cast<const float4*>(P + (size_t)k * ld + row));
+        if (row + 3 >= nrows) {
+          if (row + 1 >= nrows) v.y = 0.f;
+          if (row + 2 >= nrows) v.z = 0.f;
+          v.w = 0.f;
+        }
+      }
+    }
+    r.v[i] = v;
+  }
+}
+
+// registers -> the hi and lo tiles of one operand (K-major, swizzled)
+__device__ __forceinline__ void tc_store(uint8_t* hi_tile, uint8_t* lo_tile, const Stage4& r, int kcontig, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float x[4] = {r.v[i].x, r.v[i].y, r.v[i].z, r.v[i].w};
+    float h[4], l[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) split_tf32(x[c], h[c], l[c]);
+    if (kcontig) {
+      const int idx = tid + 256 * i, row = idx >> 3, chunk = idx & 7;
+      const uint32_t o = sw_off(row, chunk);
+      *reinterpret_cast<float4*>(hi_tile + o) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(lo_tile + o) = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+      const int idx = tid + 256 * i, k = idx >> 5, row = 4 * (idx & 31);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t o = sw_off(row + c, k >> 2) + 4 * (k & 3);
+        *reinterpret_cast<float*>(hi_tile + o) = h[c];
+        *reinterpret_cast<float*>(lo_tile + o) = l[c];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const Gemm g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_done[kStages];
+  __shared__ uint32_t tmem_base_slot;
+  // 1024-byte aligned operand area (the swizzle pattern is a function of the absolute address bits)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
+  const int n_blocks = (kend - kbeg + TK - 1) / TK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&mma_done[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+
+  Stage4 ra, rb;
+  if (n_blocks > 0) {
+    tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg, kend, tid);
+    tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg, kend, tid);
+  }
+  uint32_t phase[kStages] = {0, 0};
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const int s = blk % kStages;
+    uint8_t* st = tiles + (size_t)s * kStageBytes;
+    // the MMAs that last read this stage (block blk - kStages) must have finished
+    if (blk >= kStages) {
+      mbar_wait(&mma_done[s], phase[s]);
+      phase[s] ^= 1;
+    }
+    tc_store(st, st + kTileBytes, ra, g.a_kcontig, tid);
+    tc_store(st + 2 * kTileBytes, st + 3 * kTileBytes, rb, g.b_kcontig, tid);
+    if (blk + 1 < n_blocks) {   // next block's global loads are in flight during this block's MMAs
+      tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + (blk + 1) * TK, kend, tid);
+      tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + (blk + 1) * TK, kend, tid);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
+#pragma unroll
+      for (int kk = 0; kk < TK / 8; ++kk) {
+        const uint32_t ko = kk * 32;   // 8 TF32 = 32 bytes along K inside the swizzle row
+        umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), (blk | kk) != 0);
+        umma_tf32(tmem_d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1);
+        umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1);
+      }
+      umma_commit(&mma_done[s]);
+    }
+  }
+  // wait for the last commit of every stage that was used
+  if (n_blocks > 0) {
+    const int last = (n_blocks - 1) % kStages;
+    mbar_wait(&mma_done[last], phase[last]);
+    if (n_blocks > 1) {
+      const int prev = (n_blocks - 2) % kStages;
+      if (prev != last) mbar_wait(&mma_done[prev], phase[prev]);
+    }
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // epilogue: warp w reads lanes 32 (w % 4) .. +31 (rows) and columns 64 (w / 4) .. +63
+  float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
+  const int row = m0 + 32 * (warp & 3) + lane;
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    const int col0 = 64 * (warp >> 2) + 32 * cb;
+    uint32_t v[32];
+    if (n_blocks > 0) {
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = 0u;
+    }
+    if (row < g.M) {
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const int n = n0 + col0 + 4 * c4;
+        if (n >= g.N) continue;
+        float o[4] = {__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]),
+                      __uint_as_float(v[4 * c4 + 3])};
+        if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (n + c < g.N) {
+              o[c] += g.bias[n + c];
+              if (g.epi == EPI_BIAS_TANH) o[c] = cvf_tanh(o[c]);
+            }
+        } else if (g.epi == EPI_MUL_OM) {
+          const float4 a4 = *reinterpret_cast<const float4*>(g.act + (size_t)row * g.ldc + n);
+          o[0] *= fmaf(-a4.x, a4.x, 1.0f), o[1] *= fmaf(-a4.y, a4.y, 1.0f), o[2] *= fmaf(-a4.z, a4.z, 1.0f), o[3] *= fmaf(-a4.w, a4.w, 1.0f);
+        }
+        if (n + 3 < g.N) {
+          *reinterpret_cast<float4*>(C + (size_t)row * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (n + c < g.N) C[(size_t)row * g.ldc + n + c] = o[c];
+        }
+      }
+    }
+  }
+  // every warp's tensor-memory reads are done before the allocation is returned
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream) {
+  const size_t smem = (size_t)kStages * kStageBytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    CVF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM, splits);
+  CVF_LAUNCH(K_AE_STEP, stream, tc_gemm_kernel<<<grid, 256, smem, stream>>>(g));
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace wide
+}  // namespace cvf

@@ -140,6 +140,10 @@ size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B);
 int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
                 double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Products of the layer-wise autoencoder path: 0 = tcgen05 tensor cores, fp32 operands split into two TF32 terms and three
+ * products per block (hi*hi + lo*hi + hi*lo) accumulated in fp32 in tensor memory; 1 = fp32 SIMT (FFMA2). */
+int cvf_ae_set_wide_path(int32_t mode);
+
 /* Launch accounting for bench.py (no reference counterpart).  The library counts every kernel it launches; with
  * cvf_profile_enable(1) each launch is also bracketed by CUDA events on the stream it was enqueued on.
  * cvf_profile_read fills, per kernel id < cvf_profile_num_kernels(): summed milliseconds of the timed launches, how many were

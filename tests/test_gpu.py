@@ -526,11 +526,14 @@ def test_ae_loss_matches_oracle_ragged_sizes(B, tmp_path):
         assert C.rel_l2(g, go) < 2e-5
 
 
+@pytest.mark.parametrize("mode", ["tensor_cores", "simt"])
 @pytest.mark.parametrize("B", [130, 1000, 33000])
-def test_ae_wide_layers_match_oracle(B, tmp_path):
-    """Networks whose weights do not fit shared memory take the layer-wise path (cvf_ae_wide.cu: fp32 SGEMMs with fused
-    epilogues, split-K weight gradients); 33000 frames span two chunks."""
-    from colvarsfinder import core, nn
+def test_ae_wide_layers_match_oracle(B, mode, tmp_path):
+    """Networks whose weights do not fit shared memory take the layer-wise path (cvf_ae_wide.cu): dense products with fused
+    epilogues and split-K weight gradients, either on the tensor cores (tcgen05, 3 x TF32 split, cvf_gemm_tc.cu) or as fp32
+    SIMT products; 33000 frames span two chunks."""
+    from colvarsfinder import core, nn, _lib
+    _lib.check(_lib.lib().cvf_ae_set_wide_path(0 if mode == "tensor_cores" else 1), "cvf_ae_set_wide_path")
     e_dims, d_dims = [150, 260, 200, 2], [2, 200, 260, 150]
     torch.manual_seed(B)
     enc = [p.numpy() for p in ref_torch.init_mlp_params(e_dims)]
