@@ -121,6 +121,14 @@ class PreprocSpec:
                 table.append([t] + [pos[a] for a in atoms] + [0] * (4 - len(atoms)))
                 d_r += {_lib.FEAT_POSITION: 3, _lib.FEAT_BOND: 1, _lib.FEAT_ANGLE: 1, _lib.FEAT_DIHEDRAL: 2}[t]
             s.n_feat, s.d_r = len(records), d_r
+            for t, _ in records:
+                s.n_feat_by_type[t] += 1
+            reads = {}
+            for t, atoms in records:
+                for a in atoms:
+                    reads[a] = reads.get(a, 0) + (2 if t == _lib.FEAT_POSITION else 1)
+            s.n_self_records = sum(1 for t, atoms in records
+                                   if t != _lib.FEAT_POSITION and any(reads[a] == 1 for a in atoms))
             s.feat = self._dev(torch.tensor(table, dtype=torch.int32).reshape(-1))
             s.positions_only = 1 if positions_only else 0
             s.used_identity = 1 if used == list(range(n_atoms)) else 0

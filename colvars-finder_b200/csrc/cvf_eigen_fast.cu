@@ -23,6 +23,7 @@
 
 #include "cvf_common.cuh"
 #include "cvf_math.cuh"
+#include "cvf_tma.cuh"
 
 namespace cvf {
 namespace fast {
@@ -91,8 +92,17 @@ struct Img {
 };
 
 struct FastPlan {
-  int k, d_r, d_rp, kind;        // kind 0: identity on [B,d_r];  1: aligned positions of all n_atoms atoms (d_r = 3 n_atoms)
+  int k, d_r, d_rp, kind;        // kind 0: identity on [B,d_r];  1: aligned positions of all n_atoms atoms (d_r = 3 n_atoms);
+                                 // 2: feature map (position / bond / angle / dihedral records) on the raw frame, no alignment
   int n_atoms, n_align;
+  int n_used, n_feat, n_st, n_adj;   // kind 2: atoms the features read, records, bounds on the stencil rows per frame and
+                                     // on the (atom, record) pairs (the actual counts are in the table header)
+  int n_self;                        // kind 2: self rows the builder may hand out
+  int tile_rows;                 // rows of the pass-1 frame tile: d_rp for kind 1 (the Jacobian sums read whole atoms), else d_r
+  const int32_t* used_atoms;     // kind 2: [n_used] atom index
+  const int32_t* feat;           // kind 2: [n_feat][5] type + positions in used_atoms
+  int* tab;                      // kind 2: tables built by pack_kernel (layout: tab_* below)
+  float* ST;                     // kind 2: [n_st][Bp] gradient stencils of every record (prep -> jjt)
   int img_floats, img2_floats, geo_floats, n_params;
   int gw_off[kMaxLayers], gb_off[kMaxLayers];   // torch-order offsets inside one network's parameters
   long long B, Bp;
@@ -115,16 +125,116 @@ struct FastPlan {
 // inA [d_rp] (1 if aligned), Iref [6] (sum |ref|^2 I - ref ref^T), nA, 1/nA;   kind 0: diag [d_rp], unused [d_rp], ...
 __host__ __device__ inline int geo_floats_of(int drp) { return 2 * drp + 8; }
 
+// ---- kind 2 tables (ints, built on the device by pack_kernel because the record list lives in device memory):
+//   header    [4]            pairs in adj, atoms in the CSR, stencil rows per frame, 0
+//   finfo     [n_feat][12]   type | self mask << 8, first output row, first stencil row, self row or -1,
+//                            atom index of each of up to 4 atoms, position in used_atoms of each
+//   adj_start [n_used + 1]   CSR over the atoms that need one (padded to a multiple of 4 ints)
+//   catom     [n_used]       position in used_atoms of CSR atom c (padded)
+//   adj       [n_adj][4]     (kind, byte offset of the output row, byte offset of the stencil row, 0) of every (atom, record)
+//                            pair, offsets inside 32-frame tiles (row = 128 bytes)
+//   scratch   [2 n_used]     of the builder
+// Stencil rows of a record (floats per frame, written by prep_feat_kernel): bond 3 (unit vector a -> b), angle 6 (d cos / d a,
+// d cos / d c), dihedral 10 (d phi / d p0, d phi / d p3, p, q, cos, sin; d phi / d p1 = (-1-p) g0 + q g3,
+// d phi / d p2 = p g0 + (-1-q) g3 -- cvf_dihedral in cvf_math.cuh), position 0; then one "self" row for a record with atoms
+// that no other record reads: m = sum over those atoms of stencil . (a stencil), so that their whole contribution is
+// vhat_f += m u_f, D += m u_f^2 and they stay out of the CSR.  jjt_kernel appends 5 constant rows (0,0,1,0,0) to its staged
+// tile: a position record is three pairs whose "stencils" are the unit vectors found there.
+// adj kinds: 1 +stencil, 2 -stencil, 3 angle apex -(s + s'), 4 dihedral p1, 5 dihedral p2.
+constexpr int kTabHdr = 4, kFinfoInts = 12;
+__host__ __device__ inline int tab_finfo() { return kTabHdr; }
+__host__ __device__ inline int tab_adj_start(int n_feat) { return kTabHdr + kFinfoInts * n_feat; }
+__host__ __device__ inline int tab_catom(int n_feat, int n_used) { return tab_adj_start(n_feat) + ((n_used + 1 + 3) & ~3); }
+__host__ __device__ inline int tab_adj(int n_feat, int n_used) { return tab_catom(n_feat, n_used) + ((n_used + 3) & ~3); }
+__host__ __device__ inline int tab_scratch(int n_feat, int n_used, int n_adj) { return tab_adj(n_feat, n_used) + 4 * (n_adj > 0 ? n_adj : 1); }
+__host__ __device__ inline int tab_ints(int n_feat, int n_used, int n_adj) { return tab_scratch(n_feat, n_used, n_adj) + 2 * n_used; }
+constexpr int kStBond = 3, kStAngle = 6, kStDihedral = 10, kStConstRows = 5;
+__host__ __device__ inline int feat_atoms(int type) {
+  return type == CVF_FEAT_POSITION ? 1 : type == CVF_FEAT_BOND ? 2 : type == CVF_FEAT_ANGLE ? 3 : 4;
+}
+__host__ __device__ inline int feat_rows(int type) {
+  return type == CVF_FEAT_BOND ? kStBond : type == CVF_FEAT_ANGLE ? kStAngle : type == CVF_FEAT_DIHEDRAL ? kStDihedral : 0;
+}
+
+__device__ void build_feature_tables(const FastPlan& P) {
+  int* hdr = P.tab;
+  int* finfo = P.tab + tab_finfo();
+  int* start = P.tab + tab_adj_start(P.n_feat);
+  int* catom = P.tab + tab_catom(P.n_feat, P.n_used);
+  int* adj = P.tab + tab_adj(P.n_feat, P.n_used);
+  int* reads = P.tab + tab_scratch(P.n_feat, P.n_used, P.n_adj);   // records reading each used atom (a position record counts 2)
+  int* slot = reads + P.n_used;                                    // pairs of the atom, then its fill cursor
+  for (int a = 0; a < P.n_used; ++a) reads[a] = slot[a] = 0;
+  for (int i = 0; i < P.n_feat; ++i) {
+    const int* rec = P.feat + 5 * i;
+    for (int j = 0; j < feat_atoms(rec[0]); ++j) reads[rec[1 + j]] += rec[0] == CVF_FEAT_POSITION ? 2 : 1;
+  }
+  int fo = 0, sr = 0, n_self = 0;
+  for (int i = 0; i < P.n_feat; ++i) {
+    const int* rec = P.feat + 5 * i;
+    const int type = rec[0], na = feat_atoms(type);
+    int mask = 0;
+    if (type != CVF_FEAT_POSITION)
+      for (int j = 0; j < na; ++j)
+        if (reads[rec[1 + j]] == 1) mask |= 1 << j;
+    int self_row = -1;
+    if (mask != 0 && n_self < P.n_self) self_row = sr + feat_rows(type), ++n_self;
+    else mask = 0;
+    int* fi = finfo + kFinfoInts * i;
+    fi[0] = type | (mask << 8), fi[1] = fo, fi[2] = sr, fi[3] = self_row;
+    for (int j = 0; j < 4; ++j) fi[4 + j] = j < na ? P.used_atoms[rec[1 + j]] : 0, fi[8 + j] = j < na ? rec[1 + j] : 0;
+    for (int j = 0; j < na; ++j)
+      if (!((mask >> j) & 1)) slot[rec[1 + j]] += type == CVF_FEAT_POSITION ? 3 : 1;
+    fo += type == CVF_FEAT_POSITION ? 3 : type == CVF_FEAT_DIHEDRAL ? 2 : 1;
+    sr += feat_rows(type) + (self_row >= 0 ? 1 : 0);
+  }
+  int nc = 0, acc = 0;
+  for (int a = 0; a < P.n_used; ++a)
+    if (slot[a] > 0) {
+      const int cnt = slot[a];
+      catom[nc] = a, start[nc] = acc, slot[a] = acc, acc += cnt, ++nc;
+    }
+  start[nc] = acc;
+  hdr[0] = acc, hdr[1] = nc, hdr[2] = sr, hdr[3] = 0;
+  for (int i = 0; i < P.n_feat; ++i) {
+    const int* rec = P.feat + 5 * i;
+    const int* fi = finfo + kFinfoInts * i;
+    const int type = fi[0] & 0xff, mask = fi[0] >> 8, fo_i = fi[1], sr_i = fi[2];
+    if (type == CVF_FEAT_POSITION) {
+      for (int c = 0; c < 3; ++c) {
+        int* e = adj + 4 * slot[rec[1]]++;
+        e[0] = 1, e[1] = 128 * (fo_i + c), e[2] = 128 * (sr + 2 - c), e[3] = 0;
+      }
+      continue;
+    }
+    for (int j = 0; j < feat_atoms(type); ++j) {
+      if ((mask >> j) & 1) continue;
+      int kind, srj = sr_i;
+      if (type == CVF_FEAT_BOND) kind = j == 0 ? 2 : 1;
+      else if (type == CVF_FEAT_ANGLE) kind = j == 1 ? 3 : 1, srj = sr_i + (j == 2 ? 3 : 0);
+      else kind = j == 0 || j == 3 ? 1 : (j == 1 ? 4 : 5), srj = sr_i + (j == 3 ? 3 : 0);
+      int* e = adj + 4 * slot[rec[1 + j]]++;
+      e[0] = kind, e[1] = 128 * fo_i, e[2] = 128 * srj, e[3] = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pack
 template <int H, int NH>
 __global__ void pack_kernel(const FastPlan P, const float* __restrict__ params) {
   const int drp = P.d_rp, d_r = P.d_r;
   typedef Img<H, NH> I;
+  if (blockIdx.x == (unsigned)P.k + 1) {   // kind 2: record / adjacency tables
+    if (threadIdx.x == 0) build_feature_tables(P);
+    return;
+  }
   if (blockIdx.x == (unsigned)P.k) {   // geometry block
     float* g = P.img + (size_t)P.k * P.img_floats;
     for (int i = threadIdx.x; i < P.geo_floats; i += blockDim.x) g[i] = 0.0f;
     __syncthreads();
-    if (P.kind == 0) {
+    if (P.kind == 2) {
+      for (int i = threadIdx.x; i < d_r; i += blockDim.x) g[i] = 1.0f;   // diag_coeff is applied by jjt_kernel
+    } else if (P.kind == 0) {
       for (int i = threadIdx.x; i < d_r; i += blockDim.x) g[i] = P.diag ? P.diag[i] : 1.0f;
     } else {
       for (int j = threadIdx.x; j < P.n_align; j += blockDim.x) {
@@ -250,6 +360,241 @@ __global__ void __launch_bounds__(256) prep_transpose_kernel(const FastPlan P, c
   }
 }
 
+// kind 2: feature values and their gradient stencils from the raw frame (the pp_layer of core.py:403 without alignment:
+// _ops.py drops the Kabsch step when every record is invariant under it).  A CTA holds up to four groups of four warps; a group
+// owns one staging buffer of 32 consecutive frames -- one contiguous block of global memory, fetched by a single 1-D bulk
+// asynchronous copy (TMA) that completes on the group's mbarrier -- and then lane = frame, the group's warps taking every
+// fourth record.  Groups run out of phase, so the copies of some overlap the arithmetic and the stores of the others.
+// bulk = 0 (x not 16-byte aligned, or a frame length that would put every lane in the same bank): cooperative loads into
+// rows of odd stride.
+__global__ void __launch_bounds__(512) prep_feat_kernel(const FastPlan P, const float* __restrict__ x, int bulk) {
+  extern __shared__ __align__(16) float st[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = warp >> 2, wg = warp & 3, ng = blockDim.x >> 7;
+  const int fl = 3 * P.n_atoms, S = bulk ? fl : (fl | 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st);
+  int4* finfo = reinterpret_cast<int4*>(st + 32);
+  float* my = st + 32 + kFinfoInts * P.n_feat + (size_t)grp * ((32 * S + 3) & ~3);
+  if (tid == 0) {
+    for (int g = 0; g < ng; ++g) mbar_init(&bars[g], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 3 * P.n_feat; i += blockDim.x) finfo[i] = reinterpret_cast<const int4*>(P.tab + tab_finfo())[i];
+  __syncthreads();
+  uint32_t phase = 0;
+  const long long n_tiles = P.Bp / 32;
+  for (long long t = (long long)blockIdx.x * ng + grp; t < n_tiles; t += (long long)gridDim.x * ng) {
+    const long long f0 = t * 32;
+    if (bulk && f0 + 32 <= P.B) {
+      if (wg == 0 && lane == 0) {
+        const uint32_t bytes = (uint32_t)(32 * fl * sizeof(float));
+        mbar_expect_tx(&bars[grp], bytes);
+        bulk_g2s(my, x + (size_t)f0 * fl, bytes, &bars[grp]);
+      }
+      mbar_wait(&bars[grp], phase);
+      phase ^= 1;
+    } else {
+      for (int i = wg * 32 + lane; i < 32 * fl; i += 128) {
+        const int f = i / fl, j = i - f * fl;
+        const long long fr = min(f0 + f, P.B - 1);   // padding frames repeat the last frame (their weight is 0)
+        my[f * S + j] = __ldg(x + (size_t)fr * fl + j);
+      }
+      named_barrier(1 + grp, 128);
+    }
+    const float* fr = my + lane * S;
+    float* Yt = P.Y + f0 + lane;
+    float* St = P.ST + f0 + lane;
+    for (int i = wg; i < P.n_feat; i += 4) {
+      const int4 fa = finfo[3 * i], fb = finfo[3 * i + 1], fc = finfo[3 * i + 2];
+      const int type = fa.x & 0xff, mask = fa.x >> 8;
+      float* yo = Yt + (size_t)fa.y * P.Bp;
+      float* so = St + (size_t)fa.z * P.Bp;
+      // self term of an atom that only this record reads: stencil . (a stencil)
+      auto self = [&](int j, int up, cvf_v3 sv) -> float {
+        if (!((mask >> j) & 1)) return 0.0f;
+        if (!P.diag) return dot(sv, sv);
+        return __ldg(P.diag + 3 * up) * sv.x * sv.x + __ldg(P.diag + 3 * up + 1) * sv.y * sv.y + __ldg(P.diag + 3 * up + 2) * sv.z * sv.z;
+      };
+      const cvf_v3 p0 = v3(fr[3 * fb.x], fr[3 * fb.x + 1], fr[3 * fb.x + 2]);
+      if (type == CVF_FEAT_POSITION) {
+        yo[0] = p0.x, yo[P.Bp] = p0.y, yo[2 * P.Bp] = p0.z;
+        continue;
+      }
+      float* mo = St + (size_t)fa.w * P.Bp;   // self row (only written when fa.w >= 0)
+      const cvf_v3 p1 = v3(fr[3 * fb.y], fr[3 * fb.y + 1], fr[3 * fb.y + 2]);
+      if (type == CVF_FEAT_BOND) {
+        cvf_v3 g;
+        yo[0] = cvf_bond(p0, p1, g);
+        so[0] = g.x, so[P.Bp] = g.y, so[2 * P.Bp] = g.z;
+        if (fa.w >= 0) mo[0] = self(0, fc.x, g) + self(1, fc.y, g);
+        continue;
+      }
+      const cvf_v3 p2 = v3(fr[3 * fb.z], fr[3 * fb.z + 1], fr[3 * fb.z + 2]);
+      if (type == CVF_FEAT_ANGLE) {
+        cvf_v3 ga, gc;
+        yo[0] = cvf_angle(p0, p1, p2, ga, gc);
+        so[0] = ga.x, so[P.Bp] = ga.y, so[2 * P.Bp] = ga.z, so[3 * P.Bp] = gc.x, so[4 * P.Bp] = gc.y, so[5 * P.Bp] = gc.z;
+        if (fa.w >= 0) mo[0] = self(0, fc.x, ga) + self(1, fc.y, ga + gc) + self(2, fc.z, gc);
+        continue;
+      }
+      const cvf_v3 p3 = v3(fr[3 * fb.w], fr[3 * fb.w + 1], fr[3 * fb.w + 2]);
+      float cs, sn, pc, qc;
+      cvf_v3 g0, g3;
+      cvf_dihedral_compact(p0, p1, p2, p3, cs, sn, g0, g3, pc, qc);
+      yo[0] = cs, yo[P.Bp] = sn;
+      so[0] = g0.x, so[P.Bp] = g0.y, so[2 * P.Bp] = g0.z, so[3 * P.Bp] = g3.x, so[4 * P.Bp] = g3.y, so[5 * P.Bp] = g3.z;
+      so[6 * P.Bp] = pc, so[7 * P.Bp] = qc, so[8 * P.Bp] = cs, so[9 * P.Bp] = sn;
+      if (fa.w >= 0)
+        mo[0] = self(0, fc.x, g0) + self(1, fc.y, (-1.0f - pc) * g0 + qc * g3) + self(2, fc.z, pc * g0 + (-1.0f - qc) * g3) +
+                self(3, fc.w, g3);
+    }
+    named_barrier(1 + grp, 128);   // every warp of the group has finished reading the buffer
+  }
+}
+
+// kind 2, between pass 1 and the batch sums: for every network, vhat = J diag(a) J^T u (the tangent direction of pass 2,
+// SURVEY 7.3-B) and the Dirichlet density D = u^T J diag(a) J^T u (core.py:426), where J = d r / d x is assembled from the
+// stencils prep_feat_kernel left.  One CTA per 32-frame tile, one warp per network, lane = frame: the stencil tile is staged
+// once and shared by the networks.  Atoms that a single record reads are folded into that record's self row by prep_feat_kernel
+// (vhat_f += m u_f, D += m u_f^2); for every other atom (CSR over its (atom, record) pairs): g = sum_pairs u_f * stencil,
+// D += a |g|^2, then vhat_f += stencil . (a g) -- the per-atom gradient never leaves registers.  The pair stream is read
+// through a one-ahead register pipeline.  vhat replaces u in P.U.
+struct JjtLoad {
+  cvf_v3 s0, s1;
+  float p, q, u;
+};
+__device__ __forceinline__ void jjt_issue(JjtLoad& L, const int4 en, const char* STl, const char* Sul) {
+  const float* sp = reinterpret_cast<const float*>(STl + en.z);
+  L.u = *reinterpret_cast<const float*>(Sul + en.y);
+  L.s0 = v3(sp[0], sp[32], sp[64]);
+  if (en.x >= 3) {
+    L.s1 = v3(sp[96], sp[128], sp[160]);
+    if (en.x >= 4) L.p = sp[192], L.q = sp[224];
+  }
+}
+__device__ __forceinline__ cvf_v3 jjt_combine(const JjtLoad& L, int kind) {
+  if (kind == 1) return L.s0;
+  if (kind == 2) return v3(-L.s0.x, -L.s0.y, -L.s0.z);
+  float c0 = -1.0f, c1 = -1.0f;
+  if (kind == 4) c0 = -1.0f - L.p, c1 = L.q;
+  if (kind == 5) c0 = L.p, c1 = -1.0f - L.q;
+  return c0 * L.s0 + c1 * L.s1;
+}
+
+__global__ void __launch_bounds__(256) jjt_kernel(const FastPlan P) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, n = tid >> 5, nt = blockDim.x;
+  const int d_r = P.d_r, n_used = P.n_used, n_feat = P.n_feat;
+  const int n_adj = P.tab[0], nc = P.tab[1], n_st = P.tab[2];   // actual counts (<= the host-side bounds that size the buffers)
+  int* s_start = reinterpret_cast<int*>(sm);
+  int* s_catom = s_start + ((n_used + 1 + 3) & ~3);
+  int4* s_adj = reinterpret_cast<int4*>(s_catom + ((n_used + 3) & ~3));
+  int4* s_fi = s_adj + (P.n_adj > 0 ? P.n_adj : 1);
+  float* s_dg = reinterpret_cast<float*>(s_fi + n_feat);
+  float* STs = s_dg + ((3 * n_used + 3) & ~3);
+  float* Su = STs + (size_t)(P.n_st + kStConstRows) * 32 + (size_t)n * 2 * d_r * 32;
+  float* Sv = Su + (size_t)d_r * 32;
+  {
+    const int* g_start = P.tab + tab_adj_start(n_feat);
+    const int* g_catom = P.tab + tab_catom(n_feat, n_used);
+    const int4* g_adj = reinterpret_cast<const int4*>(P.tab + tab_adj(n_feat, n_used));
+    const int4* g_fi = reinterpret_cast<const int4*>(P.tab + tab_finfo());
+    for (int i = tid; i <= nc; i += nt) s_start[i] = g_start[i];
+    for (int i = tid; i < nc; i += nt) s_catom[i] = g_catom[i];
+    for (int i = tid; i < n_adj; i += nt) s_adj[i] = g_adj[i];
+    for (int i = tid; i < n_feat; i += nt) {
+      const int4 v = g_fi[3 * i];
+      s_fi[i] = make_int4(v.x & 0xff, 128 * v.y, 128 * v.z, v.w >= 0 ? 128 * v.w : -1);
+    }
+    for (int i = tid; i < 3 * n_used; i += nt) s_dg[i] = P.diag ? P.diag[i] : 1.0f;
+    for (int i = tid; i < kStConstRows * 32; i += nt) STs[n_st * 32 + i] = (i >> 5) == 2 ? 1.0f : 0.0f;
+  }
+  const int c4 = 4 * (lane & 7);
+  const char* STl = reinterpret_cast<const char*>(STs + lane);
+  char* Sul = reinterpret_cast<char*>(Su + lane);
+  char* Svl = reinterpret_cast<char*>(Sv + lane);
+  const long long n_tiles = P.Bp / 32;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __syncthreads();   // tables loaded / the previous tile's stencils are no longer read
+    for (int r = tid >> 3; r < n_st; r += nt >> 3) cp_async16(STs + r * 32 + 4 * (tid & 7), P.ST + (size_t)r * P.Bp + t * 32 + 4 * (tid & 7));
+    float* Un = P.U + ((size_t)n * P.d_rp) * P.Bp + t * 32;
+    for (int r = lane >> 3; r < d_r; r += 4) cp_async16(Su + r * 32 + c4, Un + (size_t)r * P.Bp + c4);
+    {
+      const long long tn = t + gridDim.x;
+      if (tn < n_tiles) {
+        for (int r = tid; r < n_st; r += nt) prefetch_l2_line(P.ST + (size_t)r * P.Bp + tn * 32);
+        prefetch_rows(P.U + ((size_t)n * P.d_rp) * P.Bp + tn * 32, d_r, P.Bp, lane);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float D = 0.0f;
+    // per record: dihedral (u_cos, u_sin) -> u_phi = -sin u_cos + cos u_sin (d cos = -sin d phi, d sin = cos d phi); the self
+    // term; the first value of vhat
+    for (int i = 0; i < n_feat; ++i) {
+      const int4 fi = s_fi[i];
+      float* up = reinterpret_cast<float*>(Sul + fi.y);
+      float* vp = reinterpret_cast<float*>(Svl + fi.y);
+      float u = up[0];
+      if (fi.x == CVF_FEAT_DIHEDRAL) {
+        const float* sp = reinterpret_cast<const float*>(STl + fi.z);
+        u = fmaf(sp[8 * 32], up[32], -sp[9 * 32] * u);
+        up[0] = u;
+      }
+      float v0 = 0.0f;
+      if (fi.w >= 0) {
+        v0 = *reinterpret_cast<const float*>(STl + fi.w) * u;
+        D = fmaf(v0, u, D);
+      }
+      vp[0] = v0;
+      if (fi.x == CVF_FEAT_POSITION) vp[32] = 0.0f, vp[64] = 0.0f;
+    }
+    if (n_adj > 0) {
+      int e = 0;
+      int4 enA = s_adj[0];
+      JjtLoad LA;
+      jjt_issue(LA, enA, STl, Sul);
+      for (int c = 0; c < nc; ++c) {
+        const int e_beg = e, e_end = s_start[c + 1], a = s_catom[c];
+        cvf_v3 g = v3(0.f, 0.f, 0.f);
+        for (; e < e_end; ++e) {
+          const int4 enB = s_adj[e + 1 < n_adj ? e + 1 : n_adj - 1];
+          JjtLoad LB;
+          jjt_issue(LB, enB, STl, Sul);
+          g = g + LA.u * jjt_combine(LA, enA.x);
+          LA = LB, enA = enB;
+        }
+        const cvf_v3 dg = v3(s_dg[3 * a], s_dg[3 * a + 1], s_dg[3 * a + 2]);
+        D = fmaf(dg.x * g.x, g.x, fmaf(dg.y * g.y, g.y, fmaf(dg.z * g.z, g.z, D)));
+        g = v3(dg.x * g.x, dg.y * g.y, dg.z * g.z);
+        int ee = e_beg;
+        int4 en = s_adj[ee];
+        JjtLoad L;
+        jjt_issue(L, en, STl, Sul);
+        for (; ee < e_end; ++ee) {
+          const int4 en2 = s_adj[ee + 1 < n_adj ? ee + 1 : n_adj - 1];
+          JjtLoad L2;
+          jjt_issue(L2, en2, STl, Sul);
+          float* vp = reinterpret_cast<float*>(Svl + en.y);
+          *vp += dot(jjt_combine(L, en.x), g);
+          L = L2, en = en2;
+        }
+      }
+    }
+    for (int i = 0; i < n_feat; ++i) {
+      const int4 fi = s_fi[i];
+      if (fi.x != CVF_FEAT_DIHEDRAL) continue;
+      const float* sp = reinterpret_cast<const float*>(STl + fi.z);
+      float* vp = reinterpret_cast<float*>(Svl + fi.y);
+      const float vphi = vp[0];
+      vp[0] = -sp[9 * 32] * vphi, vp[32] = sp[8 * 32] * vphi;
+    }
+    __syncwarp();
+    for (int r = lane >> 3; r < d_r; r += 4)
+      *reinterpret_cast<float4*>(Un + (size_t)r * P.Bp + c4) = *reinterpret_cast<const float4*>(Sv + r * 32 + c4);
+    P.Dq[(size_t)n * P.Bp + t * 32 + lane] = D;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pass 1
 // One CTA per SM, 256 threads, tiles of 512 frames; thread t owns frames 2t, 2t+1 of the tile.
 template <int H, int NH>
@@ -268,7 +613,7 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
     const long long f0 = t * F;
     __syncthreads();
     {
-      const int nv = drp * (F / 4);
+      const int nv = P.tile_rows * (F / 4);
       for (int i = tid; i < nv; i += kP1Threads) {
         const int r = i / (F / 4), c4 = i - r * (F / 4);
         st4(tile + r * F + 4 * c4, __ldg(reinterpret_cast<const float4*>(P.Y + (size_t)r * P.Bp + f0) + c4));
@@ -862,12 +1207,12 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 // fp32 sums to its own fp64 block of that network (one owner per address: deterministic).
 constexpr int kRun = 16;
 
-template <int H>
+template <int H, int TI>
 __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* __restrict__ part2) {
   extern __shared__ __align__(16) float sm[];
   constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  const int drp = P.d_rp, d_r = P.d_r, nig = drp / 12, k = P.k, blk = H * d_r;
+  const int drp = P.d_rp, d_r = P.d_r, nig = drp / TI, k = P.k, blk = H * d_r;
   const int rows_per_buf = 2 * drp + 2 * H;
   float* buf0 = sm + (size_t)warp * 2 * rows_per_buf * RP;   // two staging buffers per warp: r | vhat | s_1, scale G_1
   for (int i = tid; i < nw * 2 * rows_per_buf * RP; i += nt) sm[i] = 0.0f;
@@ -893,11 +1238,11 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* _
   for (; q < n_items; q += stride) {
     const int n = (int)(q % k);
     const long long t0 = (q / k) * kRun, t1 = t0 + kRun < n_tiles ? t0 + kRun : n_tiles;
-    float2 acc[4][12];
+    float2 acc[4][TI];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 12; ++i) acc[j][i] = make_float2(0.f, 0.f);
+      for (int i = 0; i < TI; ++i) acc[j][i] = make_float2(0.f, 0.f);
     for (long long t = t0; t < t1; ++t) {
       // successor of (q, t) in this warp's sequence
       long long tn = t + 1, qn = q;
@@ -912,7 +1257,7 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* _
       __syncwarp();
       const float* R = buf0 + (size_t)cur * rows_per_buf * RP;
       if (active)
-        outer_tile<4, 12>(acc, R + (2 * drp + og) * RP, R + ig * RP, R + (2 * drp + H + og) * RP, R + (drp + ig) * RP, TQ * RP,
+        outer_tile<4, TI>(acc, R + (2 * drp + og) * RP, R + ig * RP, R + (2 * drp + H + og) * RP, R + (drp + ig) * RP, TQ * RP,
                           nig * RP, 0, 32);
       cur ^= 1;
     }
@@ -924,7 +1269,7 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* _
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
+        for (int i = 0; i < TI; ++i) {
           const int o = j * TQ + og, col = i * nig + ig;
           if (col < d_r) T[o * d_r + col] = acc[j][i].x + acc[j][i].y;
         }
@@ -960,8 +1305,8 @@ struct Shape {
   int H, NH;
 };
 
-static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int drp) {
-  return ((size_t)k * img_floats + geo_floats + (size_t)drp * kP1Frames) * sizeof(float);
+static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int tile_rows) {
+  return ((size_t)k * img_floats + geo_floats + (size_t)tile_rows * kP1Frames) * sizeof(float);
 }
 static int pass2_rows_per_warp(int drp, int H, int NH) {
   const int need = 2 * NH * H + 2 * H, stage = 2 * drp + 12;
@@ -990,6 +1335,42 @@ static int dw1_warps(int k, int drp, int H) {
 static int img2_floats_of(int H, int NH, int drp) { return drp * H + H + (NH - 1) * (H * H + H) + H + 4 + (NH - 1) * H * H; }
 static int img_floats_of(int H, int NH, int drp) { return img2_floats_of(H, NH, drp) + H * drp; }
 
+// pass 2b register tile: 4 outputs x TI columns of dW_1 per lane, lanes = (H/4 output groups) x (d_rp / TI column groups)
+static int dw1_cols_per_lane(int drp, int H) {
+  const int lpo = 32 / (H / 4);
+  for (int ti = 12; ti <= 16; ti += 2)
+    if (drp % ti == 0 && drp / ti <= lpo) return ti;
+  return 0;
+}
+// kind 2
+static int n_adj_of(const int* c) { return 3 * c[0] + 2 * c[1] + 3 * c[2] + 4 * c[3]; }
+static int n_st_of(const int* c, int n_self) {
+  const int cap = c[1] + c[2] + c[3];
+  return kStBond * c[1] + kStAngle * c[2] + kStDihedral * c[3] + (n_self < 0 ? 0 : n_self > cap ? cap : n_self);
+}
+static bool prep_feat_bulk_ok(int n_atoms, const void* x) {
+  const int fl = 3 * n_atoms;
+  int g = fl, b = 32;
+  while (b) {
+    const int r = g % b;
+    g = b, b = r;
+  }
+  return g <= 2 && ((uintptr_t)x & 15) == 0;   // gcd(fl, 32): lanes reading the same coordinate are at most 2 deep in a bank
+}
+static size_t prep_feat_smem_bytes(int groups, int n_atoms, int n_feat) {
+  const int S = (3 * n_atoms) | 1;   // the larger of the two row strides
+  return (size_t)(32 + kFinfoInts * n_feat + (size_t)groups * ((32 * S + 3) & ~3)) * sizeof(float);
+}
+static int prep_feat_groups(int n_atoms, int n_feat) {
+  for (int g = 4; g >= 1; --g)
+    if (prep_feat_smem_bytes(g, n_atoms, n_feat) <= (size_t)max_smem_optin()) return g;
+  return 0;
+}
+static size_t jjt_smem_bytes(int k, int d_r, int n_used, int n_feat, int n_adj, int n_st) {
+  return (size_t)(((n_used + 1 + 3) & ~3) + ((n_used + 3) & ~3)) * 4 + (size_t)((n_adj > 0 ? n_adj : 1) + n_feat) * 16 +
+         (size_t)((3 * n_used + 3) & ~3) * 4 + (size_t)(n_st + kStConstRows) * 32 * 4 + (size_t)k * 2 * d_r * 32 * 4;
+}
+
 static bool supported_shape(const NetPlan& np, Shape* s) {
   if (np.L < 2) return false;
   const int H = np.dims[1];
@@ -1007,20 +1388,29 @@ bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k) {
   fast::Shape s;
   if (!fast::supported_shape(np, &s)) return false;
   if (k < 1 || k > kMaxK) return false;
-  int d_r;
+  int d_r, tile_rows;
+  const size_t cap = (size_t)max_smem_optin();
   if (pp->kind == 0) {
-    d_r = pp->dim;
+    d_r = tile_rows = pp->dim;
+  } else if (pp->kind == 1 && pp->n_align == 0) {
+    // feature map on the raw frame (kind 2 of the plan): the host-side record counts must be filled in
+    const int* c = pp->n_feat_by_type;
+    if (pp->n_feat < 1 || c[0] + c[1] + c[2] + c[3] != pp->n_feat || !pp->feat || !pp->used_atoms || pp->n_used < 1) return false;
+    if (c[0] * 3 + c[1] + c[2] + c[3] * 2 != pp->d_r) return false;
+    d_r = tile_rows = pp->d_r;
+    if (fast::prep_feat_groups(pp->n_atoms, pp->n_feat) == 0) return false;
+    if (fast::jjt_smem_bytes(k, d_r, pp->n_used, pp->n_feat, fast::n_adj_of(c), fast::n_st_of(c, pp->n_self_records)) > cap) return false;
   } else if (pp->kind == 1) {
     if (!pp->positions_only || !pp->used_identity || pp->n_align < 3 || pp->diag != nullptr || pp->n_used != pp->n_atoms) return false;
     d_r = 3 * pp->n_atoms;
+    tile_rows = (d_r + 11) / 12 * 12;
   } else {
     return false;
   }
   if (d_r < 1) return false;
   const int drp = (d_r + 11) / 12 * 12, geo = fast::geo_floats_of(drp);
-  const size_t cap = (size_t)max_smem_optin();
-  if (drp / 12 > 32 / (s.H / 4)) return false;   // pass 2b: one 12-column group of dW_1 per lane
-  return fast::pass1_smem_bytes(k, fast::img_floats_of(s.H, s.NH, drp), geo, drp) <= cap &&
+  if (fast::dw1_cols_per_lane(drp, s.H) == 0) return false;   // pass 2b: the [H][d_rp] block of dW_1 must fit one warp's registers
+  return fast::pass1_smem_bytes(k, fast::img_floats_of(s.H, s.NH, drp), geo, tile_rows) <= cap &&
          fast::pass2_warps(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) > 0 &&
          fast::dw1_warps(k, drp, s.H) > 0;
 }
@@ -1033,11 +1423,20 @@ template <int H, int NH>
 static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np, int k, long long B, void* workspace) {
   typedef Img<H, NH> I;
   P->k = k;
-  P->kind = pp->kind;
-  P->d_r = pp->kind == 0 ? pp->dim : 3 * pp->n_atoms;
+  P->kind = pp->kind == 1 && pp->n_align == 0 ? 2 : pp->kind;
+  P->d_r = P->kind == 0 ? pp->dim : P->kind == 2 ? pp->d_r : 3 * pp->n_atoms;
   P->d_rp = (int)round_up(P->d_r, 12);
+  P->tile_rows = P->kind == 1 ? P->d_rp : P->d_r;
   P->n_atoms = pp->kind == 1 ? pp->n_atoms : 0;
   P->n_align = pp->kind == 1 ? pp->n_align : 0;
+  P->n_used = P->n_feat = P->n_st = P->n_adj = P->n_self = 0;
+  P->used_atoms = P->feat = nullptr;
+  if (P->kind == 2) {
+    P->n_used = pp->n_used, P->n_feat = pp->n_feat;
+    P->n_self = pp->n_self_records < 0 ? 0 : pp->n_self_records;
+    P->n_st = n_st_of(pp->n_feat_by_type, pp->n_self_records), P->n_adj = n_adj_of(pp->n_feat_by_type);
+    P->used_atoms = pp->used_atoms, P->feat = pp->feat;
+  }
   P->img_floats = I::floats(P->d_rp);
   P->img2_floats = I::p2_floats(P->d_rp);
   P->geo_floats = geo_floats_of(P->d_rp);
@@ -1066,14 +1465,28 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   P->Dq = (float*)take((size_t)k * P->Bp * sizeof(float));
   P->Ys = (float*)take((size_t)k * P->Bp * sizeof(float));
   P->SG = (float*)take((size_t)k * 2 * H * P->Bp * sizeof(float));
+  P->tab = nullptr, P->ST = nullptr;
+  if (P->kind == 2) {
+    P->tab = (int*)take((size_t)tab_ints(P->n_feat, P->n_used, P->n_adj) * sizeof(int));
+    P->ST = (float*)take((size_t)(P->n_st > 0 ? P->n_st : 1) * P->Bp * sizeof(float));
+  }
   return off;
 }
 
 template <int H, int NH>
 static int run_forward(const FastPlan& P, const float* x, const float* params, float* y_out, cudaStream_t stream) {
-  CVF_LAUNCH(K_FAST_PACK, stream, pack_kernel<H, NH><<<P.k + 1, 256, 0, stream>>>(P, params));
+  CVF_LAUNCH(K_FAST_PACK, stream, pack_kernel<H, NH><<<P.k + 1 + (P.kind == 2 ? 1 : 0), 256, 0, stream>>>(P, params));
   CVF_CUDA(cudaGetLastError());
-  if (P.kind == 1) {
+  if (P.kind == 2) {
+    const int ng = prep_feat_groups(P.n_atoms, P.n_feat);
+    const size_t smem = prep_feat_smem_bytes(ng, P.n_atoms, P.n_feat);
+    CVF_CUDA(cudaFuncSetAttribute(prep_feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_tiles = P.Bp / 32;
+    long long grid = sm_count();
+    if ((n_tiles + ng - 1) / ng < grid) grid = (n_tiles + ng - 1) / ng;
+    CVF_LAUNCH(K_FAST_PREP, stream,
+               prep_feat_kernel<<<(int)grid, 128 * ng, smem, stream>>>(P, x, prep_feat_bulk_ok(P.n_atoms, x) ? 1 : 0));
+  } else if (P.kind == 1) {
     const size_t smem = (size_t)(128 * ((3 * P.n_atoms) | 1) + 6 * 128) * sizeof(float);
     CVF_CUDA(cudaFuncSetAttribute(prep_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (long long)sm_count() * 4;
@@ -1085,7 +1498,7 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
     CVF_LAUNCH(K_FAST_PREP, stream, prep_transpose_kernel<<<(int)grid, 256, 0, stream>>>(P, x));
   }
   CVF_CUDA(cudaGetLastError());
-  const size_t smem1 = pass1_smem_bytes(P.k, P.img_floats, P.geo_floats, P.d_rp);
+  const size_t smem1 = pass1_smem_bytes(P.k, P.img_floats, P.geo_floats, P.tile_rows);
   if (smem1 > (size_t)max_smem_optin()) {
     set_error("fast eigen path: pass 1 needs %zu B of shared memory", smem1);
     return CVF_E_UNSUPPORTED;
@@ -1095,6 +1508,17 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
   if (P.Bp / kP1Frames < grid) grid = P.Bp / kP1Frames;
   CVF_LAUNCH(K_FAST_PASS1, stream, pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out));
   CVF_CUDA(cudaGetLastError());
+  if (P.kind == 2) {
+    const size_t smemj = jjt_smem_bytes(P.k, P.d_r, P.n_used, P.n_feat, P.n_adj, P.n_st);
+    CVF_CUDA(cudaFuncSetAttribute(jjt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemj));
+    long long per_sm = (long long)(228 * 1024) / (long long)(smemj + 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 32 / P.k) per_sm = 32 / P.k;
+    long long gj = (long long)sm_count() * per_sm;
+    if (P.Bp / 32 < gj) gj = P.Bp / 32;
+    CVF_LAUNCH(K_FAST_JJT, stream, jjt_kernel<<<(int)gj, 32 * P.k, smemj, stream>>>(P));
+    CVF_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -1151,11 +1575,23 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   // pass 2b: the first layer's weight gradient
   const int warps_b = dw1_warps(k, P.d_rp, H);
   const size_t smem3 = dw1_smem_bytes(warps_b, P.d_rp, H);
-  CVF_CUDA(cudaFuncSetAttribute(dw1_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
   const long long n_items = (n_tiles + kRun - 1) / kRun * k;
   long long grid_b = sm_count();
   if ((n_items + warps_b - 1) / warps_b < grid_b) grid_b = (n_items + warps_b - 1) / warps_b;
-  CVF_LAUNCH(K_FAST_PASS2B, stream, dw1_kernel<H><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, P.part2));
+  const int ti = dw1_cols_per_lane(P.d_rp, H);
+#define CVF_DW1(TI_)                                                                                                       \
+  do {                                                                                                                     \
+    CVF_CUDA(cudaFuncSetAttribute(dw1_kernel<H, TI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));           \
+    CVF_LAUNCH(K_FAST_PASS2B, stream, dw1_kernel<H, TI_><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, P.part2));        \
+  } while (0)
+  if (ti == 12) CVF_DW1(12);
+  else if (ti == 14) CVF_DW1(14);
+  else if (ti == 16) CVF_DW1(16);
+  else {
+    set_error("fast eigen path: pass 2b has no register tile for d_rp = %d", P.d_rp);
+    return CVF_E_UNSUPPORTED;
+  }
+#undef CVF_DW1
   CVF_CUDA(cudaGetLastError());
   const int block = H * P.d_r;
   CVF_LAUNCH(K_REDUCE, stream,

@@ -233,3 +233,18 @@ CVF_HD void cvf_dihedral(cvf_v3 p0, cvf_v3 p1, cvf_v3 p2, cvf_v3 p3, float& cs, 
   g[1] = (-1.0f - p) * g[0] + q * g[3];
   g[2] = p * g[0] + (-1.0f - q) * g[3];
 }
+// the same with the two middle gradients left implicit: g[1] = (-1-p) g0 + q g3, g[2] = p g0 + (-1-q) g3
+CVF_HD void cvf_dihedral_compact(cvf_v3 p0, cvf_v3 p1, cvf_v3 p2, cvf_v3 p3, float& cs, float& sn, cvf_v3& g0, cvf_v3& g3, float& p,
+                                 float& q) {
+  const cvf_v3 r12 = p1 - p0, r23 = p2 - p1, r34 = p3 - p2;
+  const cvf_v3 n1 = cross(r12, r23), n2 = cross(r23, r34);
+  const float n1s = dot(n1, n1), n2s = dot(n2, n2), l23s = dot(r23, r23);
+  const float l23 = sqrtf(l23s);
+  const float iden = 1.0f / sqrtf(n1s * n2s);
+  cs = dot(n1, n2) * iden;
+  sn = dot(n1, r34) * l23 * iden;
+  g0 = (-l23 / n1s) * n1;
+  g3 = (l23 / n2s) * n2;
+  p = dot(r12, r23) / l23s;
+  q = dot(r34, r23) / l23s;
+}

@@ -58,6 +58,13 @@ typedef struct cvf_preproc {
                                  r is the aligned frame itself and the kernels skip the feature copy */
   int32_t used_identity;      /* 1: used_atoms is 0,1,..,n_atoms-1 (every atom is read, in order) */
   const float* diag;          /* diag_coeff (core.py:348-354) gathered to [n_used*3] (kind 1) or [dim] (kind 0); NULL = ones */
+  int32_t n_feat_by_type[4];  /* records of each CVF_FEAT_* type in feat (host-side counts: they size the scratch of the
+                                 feature-Jacobian kernel, whose per-frame gradient stencils take 3 / 6 / 14 floats per
+                                 bond / angle / dihedral) */
+  int32_t n_self_records;     /* bond / angle / dihedral records with at least one atom that no other record reads (an atom
+                                 read by a POSITION record never counts): their contribution through those atoms is a per-frame
+                                 scalar ("self term") that the feature-Jacobian kernel keeps as one more stencil row.  Sizing
+                                 hint only: a smaller value costs speed, not correctness; a larger one costs scratch */
 } cvf_preproc;
 
 /* Linear+activation chain built by nn.create_sequential_nn (nn.py:29-59).  For nn.AutoEncoder the

@@ -293,6 +293,84 @@ def test_eigen_invariant_features_with_alignment_matches_oracle(tmp_path):
             assert C.rel_l2(p.grad.cpu().numpy(), g) < 2e-3
 
 
+FEATURE_FAST_CASES = {
+    # name: (molecule, records, alignment atoms or None, diag_coeff, k)
+    "dipep_invariant_aligned": ("dipeptide", [("bond", [1, 4]), ("bond", [4, 8]), ("angle", [4, 6, 8]), ("dihedral", [4, 6, 8, 14]),
+                                              ("dihedral", [6, 8, 14, 16]), ("bond", [10, 18]), ("angle", [14, 16, 18])],
+                                [1, 4, 5, 6, 8, 10, 14, 15, 16, 18], False, 2),
+    "dipep_positions_bonds_diag": ("dipeptide", [("position", [4]), ("bond", [4, 6]), ("dihedral", [4, 6, 8, 14]), ("position", [8]),
+                                                 ("angle", [6, 8, 14]), ("bond", [1, 18])], None, True, 3),
+    "c4_chain": ("chain166", None, list(range(0, 160, 4)), False, 3),
+}
+
+
+def _c4_records():
+    sel = list(range(5, 166, 16))[:10]
+    feats = [("bond", [a, b]) for i, a in enumerate(sel) for b in sel[i + 1:]]
+    feats += [("dihedral", [s, s + 1, s + 2, s + 3]) for s in range(10, 10 + 18 * 8, 8)]
+    return feats
+
+
+@pytest.mark.parametrize("B", [2, 37, 512, 1500])
+@pytest.mark.parametrize("name", sorted(FEATURE_FAST_CASES))
+def test_eigen_fast_feature_path_matches_oracle(name, B, tmp_path):
+    """Feature maps (position / bond / angle / dihedral records) on the thread-private kernels: features and gradient stencils
+    from the raw frame (prep_feat), J diag(a) J^T applied per atom (jjt), then the common pass 2.  Checked against the fp64
+    closed-form oracle (which goes through the alignment and its Jacobian where one is configured) and against the general
+    row-engine kernels on the same inputs."""
+    from colvarsfinder import _lib, core, nn, utils
+    mol, feats, align_idx, use_diag, k = FEATURE_FAST_CASES[name]
+    base = BASE if mol == "dipeptide" else ref_torch.chain_structure(166, seed=2026)
+    if feats is None:
+        feats = _c4_records()
+    d_r = sum({"position": 3, "bond": 1, "angle": 1, "dihedral": 2}[t] for t, _ in feats)
+    dims = [d_r, 20, 20, 20, 1]
+    nets = _random_nets(dims, k, seed=len(name) + B)
+    rng = np.random.default_rng(B + k)
+    X = ref_torch.synth_frames(base, B, seed=B + 3)
+    w = ref_torch.boltzmann_weights(B, seed=B)
+    fmap = utils.FeatureMap(feats)
+    if align_idx is None:
+        pp, ppo = fmap, cf.Preproc(feats=feats)
+    else:
+        pp = utils.Preprocessing(utils.Align(base[align_idx], align_idx), fmap)
+        ppo = cf.Preproc(align_idx=align_idx, ref=base[align_idx], feats=feats)
+    diag = (0.5 + rng.random(3 * base.shape[0])).astype(np.float32) if use_diag else None
+    eig_w = [1.0, 0.6, 0.3][:k]
+    res = {}
+    for mode in (0, 1):
+        _lib.check(_lib.lib().cvf_eigen_set_path(mode), "cvf_eigen_set_path")
+        try:
+            model = nn.EigenFunctions(dims, k)
+            with torch.no_grad():
+                for i in range(k):
+                    for p, v in zip(model.eigen_funcs[i].parameters(), nets[i]):
+                        p.copy_(torch.as_tensor(v))
+            task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64), dt=1.0), pp, model, str(tmp_path), 20.0, eig_w,
+                                          diag_coeff=None if diag is None else torch.as_tensor(diag), k=k, device=DEV,
+                                          verbose=False, debug_mode=False)
+            assert task._ctx.fast_path == (mode == 0)
+            out = task.loss_func(task._traj, task._weights, None, None)
+            out[0].backward()
+            res[mode] = (out, [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs])
+        finally:
+            _lib.lib().cvf_eigen_set_path(0)
+    comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, eig_w, diag)
+    for mode in (0, 1):
+        (loss, eig, obj, pen, cvec), grads = res[mode]
+        assert list(cvec.cpu().numpy()) == list(comb["cvec"]), mode
+        # two frames: var = E[y^2] - E[y]^2 is a difference of nearly equal fp32-rounded outputs, so the loss keeps fewer digits
+        assert abs(float(loss) - comb["loss"]) <= (1e-4 if B > 2 else 5e-4) * abs(comb["loss"]), mode
+        np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
+        for i in range(k):
+            for j in range(len(g64[i])):
+                if np.abs(g64[i][j]).max() < 1e-9 * abs(comb["loss"]):
+                    assert np.abs(grads[i][j]).max() < 1e-4 * abs(comb["loss"])
+                    continue
+                assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (mode, i, j, C.rel_l2(grads[i][j], g64[i][j]))
+    assert abs(float(res[0][0][0]) - float(res[1][0][0])) <= (5e-5 if B > 2 else 5e-4) * abs(float(res[1][0][0]))
+
+
 def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
     """Size-independent property at BASELINE scale (2^20 frames of C3): the fp64 batch sums of a batch equal the sum over
     its halves, and the gradient sums of pass 2 (at fixed coefficients) are additive too."""
