@@ -22,7 +22,7 @@ class Preproc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n_atoms", C.c_int32), ("n_used", C.c_int32),
                 ("used_atoms", C.c_void_p), ("n_align", C.c_int32), ("align_used", C.c_void_p), ("ref", C.c_void_p),
                 ("n_feat", C.c_int32), ("feat", C.c_void_p), ("d_r", C.c_int32), ("positions_only", C.c_int32), ("used_identity", C.c_int32),
-                ("diag", C.c_void_p), ("n_feat_by_type", C.c_int32 * 4), ("n_self_records", C.c_int32)]
+                ("diag", C.c_void_p), ("n_feat_by_type", C.c_int32 * 4), ("n_self_records", C.c_int32), ("n_shared_atoms", C.c_int32)]
 
 
 class Mlp(C.Structure):

@@ -129,6 +129,7 @@ class PreprocSpec:
                     reads[a] = reads.get(a, 0) + (2 if t == _lib.FEAT_POSITION else 1)
             s.n_self_records = sum(1 for t, atoms in records
                                    if t != _lib.FEAT_POSITION and any(reads[a] == 1 for a in atoms))
+            s.n_shared_atoms = sum(1 for c in reads.values() if c > 1)
             s.feat = self._dev(torch.tensor(table, dtype=torch.int32).reshape(-1))
             s.positions_only = 1 if positions_only else 0
             s.used_identity = 1 if used == list(range(n_atoms)) else 0

@@ -97,7 +97,7 @@ struct FastPlan {
   int n_atoms, n_align;
   int n_used, n_feat, n_st, n_adj;   // kind 2: atoms the features read, records, bounds on the stencil rows per frame and
                                      // on the (atom, record) pairs (the actual counts are in the table header)
-  int n_self;                        // kind 2: self rows the builder may hand out
+  int n_self, n_shared;              // kind 2: self rows the builder may hand out; bound on the atoms in the CSR
   int tile_rows;                 // rows of the pass-1 frame tile: d_rp for kind 1 (the Jacobian sums read whole atoms), else d_r
   const int32_t* used_atoms;     // kind 2: [n_used] atom index
   const int32_t* feat;           // kind 2: [n_feat][5] type + positions in used_atoms
@@ -126,13 +126,16 @@ struct FastPlan {
 __host__ __device__ inline int geo_floats_of(int drp) { return 2 * drp + 8; }
 
 // ---- kind 2 tables (ints, built on the device by pack_kernel because the record list lives in device memory):
-//   header    [4]            pairs in adj, atoms in the CSR, stencil rows per frame, 0
+//   header    [4]            pairs in adj, atoms in the CSR, stencil rows per frame, 1 if the tables do not fit the host's bounds
 //   finfo     [n_feat][12]   type | self mask << 8, first output row, first stencil row, self row or -1,
 //                            atom index of each of up to 4 atoms, position in used_atoms of each
 //   adj_start [n_used + 1]   CSR over the atoms that need one (padded to a multiple of 4 ints)
 //   catom     [n_used]       position in used_atoms of CSR atom c (padded)
 //   adj       [n_adj][4]     (kind, byte offset of the output row, byte offset of the stencil row, 0) of every (atom, record)
 //                            pair, offsets inside 32-frame tiles (row = 128 bytes)
+//   rstart    [n_feat + 1]   the same pairs grouped by record (padded)
+//   radj      [n_adj][4]     (kind, byte offset of the atom's first row in the per-atom gradient block, byte offset of the stencil
+//                            row, 0); kind 0 = position record (its three outputs are the atom's gradient itself)
 //   scratch   [2 n_used]     of the builder
 // Stencil rows of a record (floats per frame, written by prep_feat_kernel): bond 3 (unit vector a -> b), angle 6 (d cos / d a,
 // d cos / d c), dihedral 10 (d phi / d p0, d phi / d p3, p, q, cos, sin; d phi / d p1 = (-1-p) g0 + q g3,
@@ -146,7 +149,9 @@ __host__ __device__ inline int tab_finfo() { return kTabHdr; }
 __host__ __device__ inline int tab_adj_start(int n_feat) { return kTabHdr + kFinfoInts * n_feat; }
 __host__ __device__ inline int tab_catom(int n_feat, int n_used) { return tab_adj_start(n_feat) + ((n_used + 1 + 3) & ~3); }
 __host__ __device__ inline int tab_adj(int n_feat, int n_used) { return tab_catom(n_feat, n_used) + ((n_used + 3) & ~3); }
-__host__ __device__ inline int tab_scratch(int n_feat, int n_used, int n_adj) { return tab_adj(n_feat, n_used) + 4 * (n_adj > 0 ? n_adj : 1); }
+__host__ __device__ inline int tab_rstart(int n_feat, int n_used, int n_adj) { return tab_adj(n_feat, n_used) + 4 * (n_adj > 0 ? n_adj : 1); }
+__host__ __device__ inline int tab_radj(int n_feat, int n_used, int n_adj) { return tab_rstart(n_feat, n_used, n_adj) + ((n_feat + 1 + 3) & ~3); }
+__host__ __device__ inline int tab_scratch(int n_feat, int n_used, int n_adj) { return tab_radj(n_feat, n_used, n_adj) + 4 * (n_adj > 0 ? n_adj : 1); }
 __host__ __device__ inline int tab_ints(int n_feat, int n_used, int n_adj) { return tab_scratch(n_feat, n_used, n_adj) + 2 * n_used; }
 constexpr int kStBond = 3, kStAngle = 6, kStDihedral = 10, kStConstRows = 5;
 __host__ __device__ inline int feat_atoms(int type) {
@@ -195,7 +200,35 @@ __device__ void build_feature_tables(const FastPlan& P) {
       catom[nc] = a, start[nc] = acc, slot[a] = acc, acc += cnt, ++nc;
     }
   start[nc] = acc;
-  hdr[0] = acc, hdr[1] = nc, hdr[2] = sr, hdr[3] = 0;
+  hdr[0] = acc, hdr[1] = nc, hdr[2] = sr, hdr[3] = (nc > P.n_shared || sr > P.n_st || acc > P.n_adj || fo != P.d_r) ? 1 : 0;
+  if (hdr[3]) {   // the descriptor's sizing fields do not cover this record list: jjt_kernel poisons its output
+    hdr[0] = hdr[1] = 0;
+    return;
+  }
+  int* rstart = P.tab + tab_rstart(P.n_feat, P.n_used, P.n_adj);
+  int* radj = P.tab + tab_radj(P.n_feat, P.n_used, P.n_adj);
+  for (int a = 0; a < P.n_used; ++a) reads[a] = -1;          // reuse: CSR index of the used atom
+  for (int c = 0; c < nc; ++c) reads[catom[c]] = c;
+  {
+    int racc = 0;
+    for (int i = 0; i < P.n_feat; ++i) {
+      const int* rec = P.feat + 5 * i;
+      const int* fi = finfo + kFinfoInts * i;
+      const int type = fi[0] & 0xff, mask = fi[0] >> 8, sr_i = fi[2];
+      rstart[i] = racc;
+      for (int j = 0; j < feat_atoms(type); ++j) {
+        if ((mask >> j) & 1) continue;
+        int kind, srj = sr_i;
+        if (type == CVF_FEAT_POSITION) kind = 0;
+        else if (type == CVF_FEAT_BOND) kind = j == 0 ? 2 : 1;
+        else if (type == CVF_FEAT_ANGLE) kind = j == 1 ? 3 : 1, srj = sr_i + (j == 2 ? 3 : 0);
+        else kind = j == 0 || j == 3 ? 1 : (j == 1 ? 4 : 5), srj = sr_i + (j == 3 ? 3 : 0);
+        int* e = radj + 4 * racc++;
+        e[0] = kind, e[1] = 128 * 3 * reads[rec[1 + j]], e[2] = 128 * srj, e[3] = 0;
+      }
+    }
+    rstart[P.n_feat] = racc;
+  }
   for (int i = 0; i < P.n_feat; ++i) {
     const int* rec = P.feat + 5 * i;
     const int* fi = finfo + kFinfoInts * i;
@@ -378,6 +411,7 @@ __global__ void __launch_bounds__(512) prep_feat_kernel(const FastPlan P, const 
     for (int g = 0; g < ng; ++g) mbar_init(&bars[g], 1);
     fence_barrier_init();
   }
+  if (P.tab[3] != 0) return;   // tables rejected by the builder (see jjt_kernel)
   for (int i = tid; i < 3 * P.n_feat; i += blockDim.x) finfo[i] = reinterpret_cast<const int4*>(P.tab + tab_finfo())[i];
   __syncthreads();
   uint32_t phase = 0;
@@ -453,18 +487,21 @@ __global__ void __launch_bounds__(512) prep_feat_kernel(const FastPlan P, const 
 
 // kind 2, between pass 1 and the batch sums: for every network, vhat = J diag(a) J^T u (the tangent direction of pass 2,
 // SURVEY 7.3-B) and the Dirichlet density D = u^T J diag(a) J^T u (core.py:426), where J = d r / d x is assembled from the
-// stencils prep_feat_kernel left.  One CTA per 32-frame tile, one warp per network, lane = frame: the stencil tile is staged
-// once and shared by the networks.  Atoms that a single record reads are folded into that record's self row by prep_feat_kernel
-// (vhat_f += m u_f, D += m u_f^2); for every other atom (CSR over its (atom, record) pairs): g = sum_pairs u_f * stencil,
-// D += a |g|^2, then vhat_f += stencil . (a g) -- the per-atom gradient never leaves registers.  The pair stream is read
-// through a one-ahead register pipeline.  vhat replaces u in P.U.
+// stencils prep_feat_kernel left.  One CTA per 32-frame tile (lane = frame); the stencil tile is staged once and shared by
+// the networks, and W warps work on each network.  Atoms that a single record reads are folded into that record's self row by
+// prep_feat_kernel (vhat_f += m u_f, D += m u_f^2).  For the others:
+//   phase 1, atom-major (a warp takes every W-th atom): g = sum over the atom's records of u_f * stencil, D += a |g|^2, and a g
+//            goes to the network's per-atom gradient rows;
+//   phase 2, record-major (a warp takes every W-th record): vhat_f = m u_f + sum over the record's atoms of stencil . (a g),
+//            written in place of u_f.
+// Every sum has one owner and a fixed order: the result is deterministic.  The pair streams are read through a one-ahead
+// register pipeline.  vhat replaces u in P.U.
 struct JjtLoad {
   cvf_v3 s0, s1;
-  float p, q, u;
+  float p, q;
 };
-__device__ __forceinline__ void jjt_issue(JjtLoad& L, const int4 en, const char* STl, const char* Sul) {
+__device__ __forceinline__ void jjt_issue(JjtLoad& L, const int4 en, const char* STl) {
   const float* sp = reinterpret_cast<const float*>(STl + en.z);
-  L.u = *reinterpret_cast<const float*>(Sul + en.y);
   L.s0 = v3(sp[0], sp[32], sp[64]);
   if (en.x >= 3) {
     L.s1 = v3(sp[96], sp[128], sp[160]);
@@ -480,118 +517,143 @@ __device__ __forceinline__ cvf_v3 jjt_combine(const JjtLoad& L, int kind) {
   return c0 * L.s0 + c1 * L.s1;
 }
 
-__global__ void __launch_bounds__(256) jjt_kernel(const FastPlan P) {
+__global__ void __launch_bounds__(384, 2) jjt_kernel(const FastPlan P, int W) {
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, lane = tid & 31, n = tid >> 5, nt = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+  const int n = warp / W, q = warp - n * W;   // network, warp of the network
   const int d_r = P.d_r, n_used = P.n_used, n_feat = P.n_feat;
-  const int n_adj = P.tab[0], nc = P.tab[1], n_st = P.tab[2];   // actual counts (<= the host-side bounds that size the buffers)
-  int* s_start = reinterpret_cast<int*>(sm);
-  int* s_catom = s_start + ((n_used + 1 + 3) & ~3);
-  int4* s_adj = reinterpret_cast<int4*>(s_catom + ((n_used + 3) & ~3));
-  int4* s_fi = s_adj + (P.n_adj > 0 ? P.n_adj : 1);
-  float* s_dg = reinterpret_cast<float*>(s_fi + n_feat);
-  float* STs = s_dg + ((3 * n_used + 3) & ~3);
-  float* Su = STs + (size_t)(P.n_st + kStConstRows) * 32 + (size_t)n * 2 * d_r * 32;
-  float* Sv = Su + (size_t)d_r * 32;
+  const bool poisoned = P.tab[3] != 0;   // the record list does not fit the descriptor's sizing fields: D = NaN, nothing else
+  const int n_adj = P.tab[0], nc = P.tab[1], n_st = poisoned ? 0 : P.tab[2];   // actual counts (<= the host-side bounds)
+  const int adj_cap = P.n_adj > 0 ? P.n_adj : 1;
+  int* s_start = reinterpret_cast<int*>(sm);                          // [n_shared + 1]
+  int* s_catom = s_start + ((P.n_shared + 1 + 3) & ~3);               // [n_shared]
+  int* s_rstart = s_catom + ((P.n_shared + 3) & ~3);                  // [n_feat + 1]
+  int4* s_adj = reinterpret_cast<int4*>(s_rstart + ((n_feat + 1 + 3) & ~3));
+  int4* s_radj = s_adj + adj_cap;
+  int4* s_fi = s_radj + adj_cap;
+  float* s_dg = reinterpret_cast<float*>(s_fi + n_feat);             // [3 n_shared] diag_coeff of the CSR atoms
+  float* STs = s_dg + ((3 * P.n_shared + 3) & ~3);
+  const int net_floats = (d_r + 3 * P.n_shared + W) * 32;
+  float* Su = STs + (size_t)(P.n_st + kStConstRows) * 32 + (size_t)n * net_floats;   // [d_r][32]  u, then vhat
+  float* Sg = Su + (size_t)d_r * 32;                                                  // [3 nc][32] a g of every CSR atom
+  float* Sd = Sg + (size_t)3 * P.n_shared * 32;                                       // [W][32]    partial D
   {
     const int* g_start = P.tab + tab_adj_start(n_feat);
     const int* g_catom = P.tab + tab_catom(n_feat, n_used);
+    const int* g_rstart = P.tab + tab_rstart(n_feat, n_used, P.n_adj);
     const int4* g_adj = reinterpret_cast<const int4*>(P.tab + tab_adj(n_feat, n_used));
+    const int4* g_radj = reinterpret_cast<const int4*>(P.tab + tab_radj(n_feat, n_used, P.n_adj));
     const int4* g_fi = reinterpret_cast<const int4*>(P.tab + tab_finfo());
     for (int i = tid; i <= nc; i += nt) s_start[i] = g_start[i];
-    for (int i = tid; i < nc; i += nt) s_catom[i] = g_catom[i];
-    for (int i = tid; i < n_adj; i += nt) s_adj[i] = g_adj[i];
+    for (int i = tid; i < nc; i += nt) {
+      const int a = g_catom[i];
+      s_catom[i] = a;
+      for (int c = 0; c < 3; ++c) s_dg[3 * i + c] = P.diag ? P.diag[3 * a + c] : 1.0f;
+    }
+    for (int i = tid; i <= n_feat; i += nt) s_rstart[i] = poisoned ? 0 : g_rstart[i];
+    for (int i = tid; i < n_adj; i += nt) s_adj[i] = g_adj[i], s_radj[i] = g_radj[i];
     for (int i = tid; i < n_feat; i += nt) {
       const int4 v = g_fi[3 * i];
       s_fi[i] = make_int4(v.x & 0xff, 128 * v.y, 128 * v.z, v.w >= 0 ? 128 * v.w : -1);
     }
-    for (int i = tid; i < 3 * n_used; i += nt) s_dg[i] = P.diag ? P.diag[i] : 1.0f;
     for (int i = tid; i < kStConstRows * 32; i += nt) STs[n_st * 32 + i] = (i >> 5) == 2 ? 1.0f : 0.0f;
   }
   const int c4 = 4 * (lane & 7);
   const char* STl = reinterpret_cast<const char*>(STs + lane);
   char* Sul = reinterpret_cast<char*>(Su + lane);
-  char* Svl = reinterpret_cast<char*>(Sv + lane);
+  char* Sgl = reinterpret_cast<char*>(Sg + lane);
+  const int bar_id = 1 + n, bar_n = 32 * W;
   const long long n_tiles = P.Bp / 32;
   for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     __syncthreads();   // tables loaded / the previous tile's stencils are no longer read
     for (int r = tid >> 3; r < n_st; r += nt >> 3) cp_async16(STs + r * 32 + 4 * (tid & 7), P.ST + (size_t)r * P.Bp + t * 32 + 4 * (tid & 7));
     float* Un = P.U + ((size_t)n * P.d_rp) * P.Bp + t * 32;
-    for (int r = lane >> 3; r < d_r; r += 4) cp_async16(Su + r * 32 + c4, Un + (size_t)r * P.Bp + c4);
+    for (int r = 4 * q + (lane >> 3); r < d_r; r += 4 * W) cp_async16(Su + r * 32 + c4, Un + (size_t)r * P.Bp + c4);
     {
       const long long tn = t + gridDim.x;
       if (tn < n_tiles) {
         for (int r = tid; r < n_st; r += nt) prefetch_l2_line(P.ST + (size_t)r * P.Bp + tn * 32);
-        prefetch_rows(P.U + ((size_t)n * P.d_rp) * P.Bp + tn * 32, d_r, P.Bp, lane);
+        for (int r = 32 * q + lane; r < d_r; r += 32 * W) prefetch_l2_line(P.U + ((size_t)n * P.d_rp + r) * P.Bp + tn * 32);
       }
     }
     cp_async_wait_all();
     __syncthreads();
-    float D = 0.0f;
-    // per record: dihedral (u_cos, u_sin) -> u_phi = -sin u_cos + cos u_sin (d cos = -sin d phi, d sin = cos d phi); the self
-    // term; the first value of vhat
-    for (int i = 0; i < n_feat; ++i) {
-      const int4 fi = s_fi[i];
-      float* up = reinterpret_cast<float*>(Sul + fi.y);
-      float* vp = reinterpret_cast<float*>(Svl + fi.y);
-      float u = up[0];
-      if (fi.x == CVF_FEAT_DIHEDRAL) {
-        const float* sp = reinterpret_cast<const float*>(STl + fi.z);
-        u = fmaf(sp[8 * 32], up[32], -sp[9 * 32] * u);
-        up[0] = u;
-      }
-      float v0 = 0.0f;
-      if (fi.w >= 0) {
-        v0 = *reinterpret_cast<const float*>(STl + fi.w) * u;
-        D = fmaf(v0, u, D);
-      }
-      vp[0] = v0;
-      if (fi.x == CVF_FEAT_POSITION) vp[32] = 0.0f, vp[64] = 0.0f;
-    }
-    if (n_adj > 0) {
-      int e = 0;
-      int4 enA = s_adj[0];
-      JjtLoad LA;
-      jjt_issue(LA, enA, STl, Sul);
-      for (int c = 0; c < nc; ++c) {
-        const int e_beg = e, e_end = s_start[c + 1], a = s_catom[c];
-        cvf_v3 g = v3(0.f, 0.f, 0.f);
-        for (; e < e_end; ++e) {
-          const int4 enB = s_adj[e + 1 < n_adj ? e + 1 : n_adj - 1];
-          JjtLoad LB;
-          jjt_issue(LB, enB, STl, Sul);
-          g = g + LA.u * jjt_combine(LA, enA.x);
-          LA = LB, enA = enB;
-        }
-        const cvf_v3 dg = v3(s_dg[3 * a], s_dg[3 * a + 1], s_dg[3 * a + 2]);
-        D = fmaf(dg.x * g.x, g.x, fmaf(dg.y * g.y, g.y, fmaf(dg.z * g.z, g.z, D)));
-        g = v3(dg.x * g.x, dg.y * g.y, dg.z * g.z);
-        int ee = e_beg;
-        int4 en = s_adj[ee];
-        JjtLoad L;
-        jjt_issue(L, en, STl, Sul);
-        for (; ee < e_end; ++ee) {
-          const int4 en2 = s_adj[ee + 1 < n_adj ? ee + 1 : n_adj - 1];
-          JjtLoad L2;
-          jjt_issue(L2, en2, STl, Sul);
-          float* vp = reinterpret_cast<float*>(Svl + en.y);
-          *vp += dot(jjt_combine(L, en.x), g);
-          L = L2, en = en2;
-        }
-      }
-    }
-    for (int i = 0; i < n_feat; ++i) {
+    // phase 0: dihedral records, (u_cos, u_sin) -> u_phi = -sin u_cos + cos u_sin (d cos = -sin d phi, d sin = cos d phi)
+    const int n_rec = poisoned ? 0 : n_feat;
+    for (int i = q; i < n_rec; i += W) {
       const int4 fi = s_fi[i];
       if (fi.x != CVF_FEAT_DIHEDRAL) continue;
       const float* sp = reinterpret_cast<const float*>(STl + fi.z);
-      float* vp = reinterpret_cast<float*>(Svl + fi.y);
-      const float vphi = vp[0];
-      vp[0] = -sp[9 * 32] * vphi, vp[32] = sp[8 * 32] * vphi;
+      float* up = reinterpret_cast<float*>(Sul + fi.y);
+      up[0] = fmaf(sp[8 * 32], up[32], -sp[9 * 32] * up[0]);
     }
-    __syncwarp();
-    for (int r = lane >> 3; r < d_r; r += 4)
-      *reinterpret_cast<float4*>(Un + (size_t)r * P.Bp + c4) = *reinterpret_cast<const float4*>(Sv + r * 32 + c4);
-    P.Dq[(size_t)n * P.Bp + t * 32 + lane] = D;
+    named_barrier(bar_id, bar_n);
+    // phase 1: per-atom gradients
+    float D = 0.0f;
+    for (int c = q; c < nc; c += W) {
+      int e = s_start[c];
+      const int e_end = s_start[c + 1];
+      int4 enA = s_adj[e];
+      JjtLoad LA;
+      jjt_issue(LA, enA, STl);
+      float uA = *reinterpret_cast<const float*>(Sul + enA.y);
+      cvf_v3 g = v3(0.f, 0.f, 0.f);
+      for (; e < e_end; ++e) {
+        const int4 enB = s_adj[e + 1 < n_adj ? e + 1 : n_adj - 1];
+        JjtLoad LB;
+        jjt_issue(LB, enB, STl);
+        const float uB = *reinterpret_cast<const float*>(Sul + enB.y);
+        g = g + uA * jjt_combine(LA, enA.x);
+        LA = LB, enA = enB, uA = uB;
+      }
+      const cvf_v3 dg = v3(s_dg[3 * c], s_dg[3 * c + 1], s_dg[3 * c + 2]);
+      D = fmaf(dg.x * g.x, g.x, fmaf(dg.y * g.y, g.y, fmaf(dg.z * g.z, g.z, D)));
+      float* gp = reinterpret_cast<float*>(Sgl + 128 * 3 * c);
+      gp[0] = dg.x * g.x, gp[32] = dg.y * g.y, gp[64] = dg.z * g.z;
+    }
+    named_barrier(bar_id, bar_n);
+    // phase 2: vhat per record, in place of u
+    for (int i = q; i < n_rec; i += W) {
+      const int4 fi = s_fi[i];
+      float* up = reinterpret_cast<float*>(Sul + fi.y);
+      int e = s_rstart[i];
+      const int e_end = s_rstart[i + 1];
+      if (fi.x == CVF_FEAT_POSITION) {
+        if (e < e_end) {
+          const float* gp = reinterpret_cast<const float*>(Sgl + s_radj[e].y);
+          up[0] = gp[0], up[32] = gp[32], up[64] = gp[64];
+        }
+        continue;
+      }
+      const float u = up[0];
+      float v = 0.0f;
+      if (fi.w >= 0) {
+        v = *reinterpret_cast<const float*>(STl + fi.w) * u;
+        D = fmaf(v, u, D);
+      }
+      for (; e < e_end; ++e) {
+        const int4 en = s_radj[e];
+        JjtLoad L;
+        jjt_issue(L, en, STl);
+        const float* gp = reinterpret_cast<const float*>(Sgl + en.y);
+        v += dot(jjt_combine(L, en.x), v3(gp[0], gp[32], gp[64]));
+      }
+      if (fi.x == CVF_FEAT_DIHEDRAL) {
+        const float* sp = reinterpret_cast<const float*>(STl + fi.z);
+        up[0] = -sp[9 * 32] * v, up[32] = sp[8 * 32] * v;
+      } else {
+        up[0] = v;
+      }
+    }
+    Sd[q * 32 + lane] = D;
+    named_barrier(bar_id, bar_n);
+    for (int r = 4 * q + (lane >> 3); r < d_r; r += 4 * W)
+      *reinterpret_cast<float4*>(Un + (size_t)r * P.Bp + c4) = *reinterpret_cast<const float4*>(Su + r * 32 + c4);
+    if (q == 0) {
+      float Dt = Sd[lane];
+      for (int w = 1; w < W; ++w) Dt += Sd[w * 32 + lane];
+      P.Dq[(size_t)n * P.Bp + t * 32 + lane] = poisoned ? __int_as_float(0x7fc00000) : Dt;
+    }
   }
 }
 
@@ -1366,9 +1428,15 @@ static int prep_feat_groups(int n_atoms, int n_feat) {
     if (prep_feat_smem_bytes(g, n_atoms, n_feat) <= (size_t)max_smem_optin()) return g;
   return 0;
 }
-static size_t jjt_smem_bytes(int k, int d_r, int n_used, int n_feat, int n_adj, int n_st) {
-  return (size_t)(((n_used + 1 + 3) & ~3) + ((n_used + 3) & ~3)) * 4 + (size_t)((n_adj > 0 ? n_adj : 1) + n_feat) * 16 +
-         (size_t)((3 * n_used + 3) & ~3) * 4 + (size_t)(n_st + kStConstRows) * 32 * 4 + (size_t)k * 2 * d_r * 32 * 4;
+static int n_shared_of(const cvf_preproc* pp) {
+  const int v = pp->n_shared_atoms;
+  return v < 0 ? 0 : v > pp->n_used ? pp->n_used : v;
+}
+static int jjt_warps_per_net(int k) { return k <= 3 ? 4 : k <= 6 ? 2 : 1; }   // at most 12 warps per CTA
+static size_t jjt_smem_bytes(int k, int d_r, int n_shared, int n_feat, int n_adj, int n_st) {
+  const int W = jjt_warps_per_net(k), cap = n_adj > 0 ? n_adj : 1;
+  return (size_t)(((n_shared + 1 + 3) & ~3) + ((n_shared + 3) & ~3) + ((n_feat + 1 + 3) & ~3)) * 4 + (size_t)(2 * cap + n_feat) * 16 +
+         (size_t)((3 * n_shared + 3) & ~3) * 4 + (size_t)(n_st + kStConstRows) * 32 * 4 + (size_t)k * (d_r + 3 * n_shared + W) * 32 * 4;
 }
 
 static bool supported_shape(const NetPlan& np, Shape* s) {
@@ -1399,7 +1467,7 @@ bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k) {
     if (c[0] * 3 + c[1] + c[2] + c[3] * 2 != pp->d_r) return false;
     d_r = tile_rows = pp->d_r;
     if (fast::prep_feat_groups(pp->n_atoms, pp->n_feat) == 0) return false;
-    if (fast::jjt_smem_bytes(k, d_r, pp->n_used, pp->n_feat, fast::n_adj_of(c), fast::n_st_of(c, pp->n_self_records)) > cap) return false;
+    if (fast::jjt_smem_bytes(k, d_r, fast::n_shared_of(pp), pp->n_feat, fast::n_adj_of(c), fast::n_st_of(c, pp->n_self_records)) > cap) return false;
   } else if (pp->kind == 1) {
     if (!pp->positions_only || !pp->used_identity || pp->n_align < 3 || pp->diag != nullptr || pp->n_used != pp->n_atoms) return false;
     d_r = 3 * pp->n_atoms;
@@ -1429,11 +1497,12 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   P->tile_rows = P->kind == 1 ? P->d_rp : P->d_r;
   P->n_atoms = pp->kind == 1 ? pp->n_atoms : 0;
   P->n_align = pp->kind == 1 ? pp->n_align : 0;
-  P->n_used = P->n_feat = P->n_st = P->n_adj = P->n_self = 0;
+  P->n_used = P->n_feat = P->n_st = P->n_adj = P->n_self = P->n_shared = 0;
   P->used_atoms = P->feat = nullptr;
   if (P->kind == 2) {
     P->n_used = pp->n_used, P->n_feat = pp->n_feat;
     P->n_self = pp->n_self_records < 0 ? 0 : pp->n_self_records;
+    P->n_shared = n_shared_of(pp);
     P->n_st = n_st_of(pp->n_feat_by_type, pp->n_self_records), P->n_adj = n_adj_of(pp->n_feat_by_type);
     P->used_atoms = pp->used_atoms, P->feat = pp->feat;
   }
@@ -1509,14 +1578,16 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
   CVF_LAUNCH(K_FAST_PASS1, stream, pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out));
   CVF_CUDA(cudaGetLastError());
   if (P.kind == 2) {
-    const size_t smemj = jjt_smem_bytes(P.k, P.d_r, P.n_used, P.n_feat, P.n_adj, P.n_st);
+    const int W = jjt_warps_per_net(P.k);
+    const size_t smemj = jjt_smem_bytes(P.k, P.d_r, P.n_shared, P.n_feat, P.n_adj, P.n_st);
     CVF_CUDA(cudaFuncSetAttribute(jjt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemj));
     long long per_sm = (long long)(228 * 1024) / (long long)(smemj + 1024);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 32 / P.k) per_sm = 32 / P.k;
+    if (per_sm > 64 / (P.k * W)) per_sm = 64 / (P.k * W);
+    if (per_sm < 1) per_sm = 1;
     long long gj = (long long)sm_count() * per_sm;
     if (P.Bp / 32 < gj) gj = P.Bp / 32;
-    CVF_LAUNCH(K_FAST_JJT, stream, jjt_kernel<<<(int)gj, 32 * P.k, smemj, stream>>>(P));
+    CVF_LAUNCH(K_FAST_JJT, stream, jjt_kernel<<<(int)gj, 32 * P.k * W, smemj, stream>>>(P, W));
     CVF_CUDA(cudaGetLastError());
   }
   return 0;

@@ -65,6 +65,9 @@ typedef struct cvf_preproc {
                                  read by a POSITION record never counts): their contribution through those atoms is a per-frame
                                  scalar ("self term") that the feature-Jacobian kernel keeps as one more stencil row.  Sizing
                                  hint only: a smaller value costs speed, not correctness; a larger one costs scratch */
+  int32_t n_shared_atoms;     /* used atoms read by more than one record or by a POSITION record: the atoms whose gradient the
+                                 feature-Jacobian kernel accumulates across records (sizes its shared memory; the kernel checks
+                                 the value against the record list and poisons its output with NaN if it is too small) */
 } cvf_preproc;
 
 /* Linear+activation chain built by nn.create_sequential_nn (nn.py:29-59).  For nn.AutoEncoder the
