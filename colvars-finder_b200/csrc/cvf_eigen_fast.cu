@@ -143,7 +143,7 @@ __host__ __device__ inline int geo_floats_of(int drp) { return 2 * drp + 8; }
 // that no other record reads: m = sum over those atoms of stencil . (a stencil), so that their whole contribution is
 // vhat_f += m u_f, D += m u_f^2 and they stay out of the CSR.  jjt_kernel appends 5 constant rows (0,0,1,0,0) to its staged
 // tile: a position record is three pairs whose "stencils" are the unit vectors found there.
-// adj kinds: 1 +stencil, 2 -stencil, 3 angle apex -(s + s'), 4 dihedral p1, 5 dihedral p2.
+// adj kinds: 1 stencil times the sign in the fourth field, 3 angle apex -(s + s'), 4 dihedral p1, 5 dihedral p2.
 constexpr int kTabHdr = 4, kFinfoInts = 12;
 __host__ __device__ inline int tab_finfo() { return kTabHdr; }
 __host__ __device__ inline int tab_adj_start(int n_feat) { return kTabHdr + kFinfoInts * n_feat; }
@@ -224,7 +224,7 @@ __device__ void build_feature_tables(const FastPlan& P) {
         else if (type == CVF_FEAT_ANGLE) kind = j == 1 ? 3 : 1, srj = sr_i + (j == 2 ? 3 : 0);
         else kind = j == 0 || j == 3 ? 1 : (j == 1 ? 4 : 5), srj = sr_i + (j == 3 ? 3 : 0);
         int* e = radj + 4 * racc++;
-        e[0] = kind, e[1] = 128 * 3 * reads[rec[1 + j]], e[2] = 128 * srj, e[3] = 0;
+        e[0] = kind == 2 ? 1 : kind, e[1] = 128 * 3 * reads[rec[1 + j]], e[2] = 128 * srj, e[3] = __float_as_int(kind == 2 ? -1.0f : 1.0f);
       }
     }
     rstart[P.n_feat] = racc;
@@ -236,7 +236,7 @@ __device__ void build_feature_tables(const FastPlan& P) {
     if (type == CVF_FEAT_POSITION) {
       for (int c = 0; c < 3; ++c) {
         int* e = adj + 4 * slot[rec[1]]++;
-        e[0] = 1, e[1] = 128 * (fo_i + c), e[2] = 128 * (sr + 2 - c), e[3] = 0;
+        e[0] = 1, e[1] = 128 * (fo_i + c), e[2] = 128 * (sr + 2 - c), e[3] = __float_as_int(1.0f);
       }
       continue;
     }
@@ -247,7 +247,7 @@ __device__ void build_feature_tables(const FastPlan& P) {
       else if (type == CVF_FEAT_ANGLE) kind = j == 1 ? 3 : 1, srj = sr_i + (j == 2 ? 3 : 0);
       else kind = j == 0 || j == 3 ? 1 : (j == 1 ? 4 : 5), srj = sr_i + (j == 3 ? 3 : 0);
       int* e = adj + 4 * slot[rec[1 + j]]++;
-      e[0] = kind, e[1] = 128 * fo_i, e[2] = 128 * srj, e[3] = 0;
+      e[0] = kind == 2 ? 1 : kind, e[1] = 128 * fo_i, e[2] = 128 * srj, e[3] = __float_as_int(kind == 2 ? -1.0f : 1.0f);
     }
   }
 }
@@ -508,9 +508,8 @@ __device__ __forceinline__ void jjt_issue(JjtLoad& L, const int4 en, const char*
     if (en.x >= 4) L.p = sp[192], L.q = sp[224];
   }
 }
+// stencil of kinds >= 3 (kind 1 is s0 times the pair's sign, applied by the caller to the scalar factor)
 __device__ __forceinline__ cvf_v3 jjt_combine(const JjtLoad& L, int kind) {
-  if (kind == 1) return L.s0;
-  if (kind == 2) return v3(-L.s0.x, -L.s0.y, -L.s0.z);
   float c0 = -1.0f, c1 = -1.0f;
   if (kind == 4) c0 = -1.0f - L.p, c1 = L.q;
   if (kind == 5) c0 = L.p, c1 = -1.0f - L.q;
@@ -603,7 +602,8 @@ __global__ void __launch_bounds__(384, 2) jjt_kernel(const FastPlan P, int W) {
         JjtLoad LB;
         jjt_issue(LB, enB, STl);
         const float uB = *reinterpret_cast<const float*>(Sul + enB.y);
-        g = g + uA * jjt_combine(LA, enA.x);
+        if (enA.x == 1) g = g + (__int_as_float(enA.w) * uA) * LA.s0;
+        else g = g + uA * jjt_combine(LA, enA.x);
         LA = LB, enA = enB, uA = uB;
       }
       const cvf_v3 dg = v3(s_dg[3 * c], s_dg[3 * c + 1], s_dg[3 * c + 2]);
@@ -636,7 +636,9 @@ __global__ void __launch_bounds__(384, 2) jjt_kernel(const FastPlan P, int W) {
         JjtLoad L;
         jjt_issue(L, en, STl);
         const float* gp = reinterpret_cast<const float*>(Sgl + en.y);
-        v += dot(jjt_combine(L, en.x), v3(gp[0], gp[32], gp[64]));
+        const cvf_v3 gv = v3(gp[0], gp[32], gp[64]);
+        if (en.x == 1) v = fmaf(__int_as_float(en.w), dot(L.s0, gv), v);
+        else v += dot(jjt_combine(L, en.x), gv);
       }
       if (fi.x == CVF_FEAT_DIHEDRAL) {
         const float* sp = reinterpret_cast<const float*>(STl + fi.z);
