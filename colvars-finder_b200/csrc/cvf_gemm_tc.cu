@@ -108,8 +108,9 @@ __device__ __forceinline__ void tc_load(Stage4& r, const float* __restrict__ P, 
           v.w = 0.f;
         }
       }
-    } else {         // (k = idx / 32, 4 consecutive rows)
-      const int idx = tid + 256 * i, k = k0 + (idx >> 5), row = row0 + 4 * (idx & 31);
+    } else {         // 4 consecutive rows at one k; a warp covers 16 k x 8 rows (see tc_store)
+      const int lane = tid & 31, wq = (tid >> 5) + 8 * (i >> 1);
+      const int k = k0 + (lane & 15) + 16 * (i & 1), row = row0 + 4 * ((lane >> 4) + 2 * wq);
       if (k < k1 && row < nrows) {
         v = __ldg(reinterpret_cast<const float4*>(P + (size_t)k * ld + row));
         if (row + 3 >= nrows) {
@@ -137,7 +138,11 @@ __device__ __forceinline__ void tc_store(uint8_t* hi_tile, uint8_t* lo_tile, con
       *reinterpret_cast<float4*>(hi_tile + o) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(lo_tile + o) = make_float4(l[0], l[1], l[2], l[3]);
     } else {
-      const int idx = tid + 256 * i, k = idx >> 5, row = 4 * (idx & 31);
+      // transposing store.  Lanes of a warp differ in k & 15 and in the parity of the row quad, so for each of the four
+      // components the 32 scalar stores fall into 32 different banks: word = 4 * ((k >> 2) ^ (row & 7)) + (k & 3) modulo 32
+      // takes every value once (k & 3, (k >> 2) & 3 and the row & 4 bit that the XOR moves into bit 2 of the chunk).
+      const int lane = tid & 31, wq = (tid >> 5) + 8 * (i >> 1);
+      const int k = (lane & 15) + 16 * (i & 1), row = 4 * ((lane >> 4) + 2 * wq);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t o = sw_off(row + c, k >> 2) + 4 * (k & 3);
