@@ -50,17 +50,23 @@ WORKLOADS = {
     "c4": ("166-atom chain EigenFunctionTask, generator loss, k=3, 45 distances + 18 dihedrals (d_r=81), "
            "nets [81,20,20,20,1]", 1996, 128500),
     "c5": ("1000-atom AutoEncoderTask step on position features (d_r=3000), enc [3000,512,512,2], dec [2,512,512,3000]; "
-           "layer-wise fp32 SIMT products (no tensor-core path yet)", 12004, 21590016),
+           "layer-wise products on tcgen05 tensor cores (3 x TF32 split, fp32 accumulation in tensor memory)", 12004, 21590016),
 }
 METRIC = "train-step frames/sec"
 # fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
 KERNEL_FLOPS = {
     ("c3", "fast_pass2a"): 45240, ("c3", "fast_pass1"): 25680, ("c3", "fast_pass2b(dW1)"): 15840,
     ("c1", "fast_pass2a"): 5080, ("c1", "fast_pass1"): 1760,
+    ("c4", "fast_pass2a"): 48720, ("c4", "fast_pass1"): 29160, ("c4", "fast_pass2b(dW1)"): 19440,
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture under profiles/ (per frame x frames of that run
-# is NOT extrapolated: null unless the capture used this configuration)
-KERNEL_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture of this command under profiles/
+# (r01_ncu_c3_summary.txt); keyed by (workload, kernel, frames per launch) and not extrapolated to other sizes
+KERNEL_TRAFFIC = {
+    ("c3", "fast_pass2a", 1 << 22): 7.090627e9 + 7.657184e9,
+    ("c3", "fast_pass1", 1 << 22): 1.309251e9 + 4.319722e9,
+    ("c3", "fast_pass2b(dW1)", 1 << 22): 6.717460e9 + 0.277013e9,
+    ("c3", "fast_prep", 1 << 22): 1.107347e9 + 1.259367e9,
+}
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -447,7 +453,7 @@ def main():
                 "ms_per_step": float(ms_e2e) / K},
         "gpu_launches": launches_timed * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": KERNEL_TRAFFIC.get((args.workload, dom_name)), "kernel": dom_name, "kernel_ms": kern_ms,
+                     "traffic": KERNEL_TRAFFIC.get((args.workload, dom_name, args.frames)), "kernel": dom_name, "kernel_ms": kern_ms,
                      "kernel_share_of_step": prof[dom_name][0] / K / step_kernel_ms, "peak_source": peak_src,
                      "note": "this path is fp32-FMA bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
         "roofline_fp32": {"bound": "fp32_fma", "peak": fma_peak, "unit": "TFLOP/s",
@@ -459,6 +465,22 @@ def main():
                               "frac": dom_flops * args.frames / (kern_ms * 1e-3) / 1e12 / fma_peak}},
         "kernels": {k_: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k_, v in sorted(prof.items())},
     }
+    if args.workload == "c5":
+        # the layer products run on the tensor cores as three TF32 passes: the fp32-equivalent ceiling is the measured dense
+        # bf16 rate / 2 (TF32 runs at half the bf16 rate) / 3 (passes)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16 = float(json.load(f)["bf16_tflops_sustained"])
+            src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32) / 3 (split passes)"
+        except Exception:
+            bf16, src = 1379.4, "fallback 1379.4 TF/s bf16 / 2 / 3"
+        peak = bf16 / 6.0
+        out["roofline"] = {"bound": "tensor", "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s", "frac": step_tflops / peak,
+                           "traffic": None, "kernel": "ae_step (tcgen05 3xTF32 products + transposes, whole step)",
+                           "kernel_ms": kern_ms, "kernel_share_of_step": prof[dom_name][0] / K / step_kernel_ms,
+                           "peak_source": src,
+                           "note": "achieved = algorithmic fp32 flops of the step (6P per frame) per second; tensor-pipe active "
+                                   "cycles per product kernel are in profiles/"}
     if not args.no_cpu_baseline:
         fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, 5, 1)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",

@@ -8,8 +8,10 @@
 //   * operands: both tiles are staged K-major ([row][32 k] = 128-byte rows) in the canonical 128-byte-swizzled layout the
 //     UMMA shared-memory descriptor expects (8-row groups of 1024 bytes, 16-byte chunk index XOR row mod 8); the staging threads
 //     transpose on the fly when the global operand is contiguous along the other dimension;
-//   * one thread issues the MMAs (M = 128, N = 128, K = 8 per instruction; 12 per stage), completion is tracked with
-//     tcgen05.commit on an mbarrier per stage; the 256 threads stage block i+1 while the tensor core works on block i;
+//   * a ninth warp does nothing but issue the MMAs (one thread; M = 128, N = 128, K = 8 per instruction; 12 per stage) as the
+//     stages fill (mbarrier per stage, 256 arrivals) and commit them (tcgen05.commit on a second mbarrier per stage, which
+//     returns the stage); three stages, and the staging threads' global loads run two blocks ahead of their stores, so load
+//     latency, staging and the tensor core overlap;
 //   * the 128 x 128 fp32 accumulator lives in 128 columns of tensor memory and is read back with tcgen05.ld (32 lanes x 32
 //     columns per warp instruction) for the fused epilogue (bias / tanh / multiplication by 1 - act^2).
 #include <stdint.h>
@@ -23,7 +25,7 @@ namespace wide {
 constexpr int TM = 128, TN = 128, TK = 32;            // CTA tile; TK fp32 = one 128-byte swizzle row
 constexpr int kTileBytes = TM * TK * 4;               // 16 KB per operand tile
 constexpr int kStageBytes = 4 * kTileBytes;           // Ahi, Alo, Bhi, Blo
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr uint32_t kTmemCols = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -47,6 +49,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (done) return;
   }
   __trap();
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: start address, stride between 8-row groups 1024 B,
@@ -153,9 +159,10 @@ __device__ __forceinline__ void tc_store(uint8_t* hi_tile, uint8_t* lo_tile, con
   }
 }
 
-__global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const Gemm g) {
+__global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_done[kStages];
+  __shared__ __align__(8) uint64_t mma_done[kStages];   // tensor core has finished reading the stage
+  __shared__ __align__(8) uint64_t full[kStages];       // the 256 staging threads have filled the stage
   __shared__ uint32_t tmem_base_slot;
   // 1024-byte aligned operand area (the swizzle pattern is a function of the absolute address bits)
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -165,7 +172,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const Gemm g) {
   const int n_blocks = (kend - kbeg + TK - 1) / TK;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&mma_done[s], 1);
+    for (int s = 0; s < kStages; ++s) mbar_init(&mma_done[s], 1), mbar_init(&full[s], 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -179,50 +186,69 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const Gemm g) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_slot;
 
-  Stage4 ra, rb;
-  if (n_blocks > 0) {
-    tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg, kend, tid);
-    tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg, kend, tid);
-  }
-  uint32_t phase[kStages] = {0, 0};
-  for (int blk = 0; blk < n_blocks; ++blk) {
-    const int s = blk % kStages;
-    uint8_t* st = tiles + (size_t)s * kStageBytes;
-    // the MMAs that last read this stage (block blk - kStages) must have finished
-    if (blk >= kStages) {
-      mbar_wait(&mma_done[s], phase[s]);
-      phase[s] ^= 1;
+  // Warp-specialised pipeline.  Warps 0-7 (256 threads) stage: their global loads run two k-blocks ahead of their staging
+  // stores (two register sets, alternating), and the stores run up to three blocks ahead of the tensor core (three
+  // shared-memory stages, handed over through the `full` mbarriers).  Warp 8 only issues the MMAs of every filled stage and
+  // commits them to `mma_done`, which hands the stage back.
+  uint32_t phase[kStages] = {0, 0, 0};
+  if (warp < 8) {
+    Stage4 ra0, rb0, ra1, rb1;
+    if (n_blocks > 0) {
+      tc_load(ra0, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg, kend, tid);
+      tc_load(rb0, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg, kend, tid);
     }
-    tc_store(st, st + kTileBytes, ra, g.a_kcontig, tid);
-    tc_store(st + 2 * kTileBytes, st + 3 * kTileBytes, rb, g.b_kcontig, tid);
-    if (blk + 1 < n_blocks) {   // next block's global loads are in flight during this block's MMAs
-      tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + (blk + 1) * TK, kend, tid);
-      tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + (blk + 1) * TK, kend, tid);
+    if (n_blocks > 1) {
+      tc_load(ra1, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + TK, kend, tid);
+      tc_load(rb1, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + TK, kend, tid);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + kTileBytes, b_hi = a_hi + 2 * kTileBytes, b_lo = a_hi + 3 * kTileBytes;
-#pragma unroll
-      for (int kk = 0; kk < TK / 8; ++kk) {
-        const uint32_t ko = kk * 32;   // 8 TF32 = 32 bytes along K inside the swizzle row
-        umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_hi + ko), (blk | kk) != 0);
-        umma_tf32(tmem_d, umma_desc(a_lo + ko), umma_desc(b_hi + ko), 1);
-        umma_tf32(tmem_d, umma_desc(a_hi + ko), umma_desc(b_lo + ko), 1);
+    auto body = [&](int blk, Stage4& ra, Stage4& rb) {
+      const int s = blk % kStages;
+      uint8_t* st = tiles + (size_t)s * kStageBytes;
+      // the MMAs that last read this stage (block blk - kStages) must have finished
+      if (blk >= kStages) {
+        mbar_wait(&mma_done[s], phase[s]);
+        phase[s] ^= 1;
       }
-      umma_commit(&mma_done[s]);
+      tc_store(st, st + kTileBytes, ra, g.a_kcontig, tid);
+      tc_store(st + 2 * kTileBytes, st + 3 * kTileBytes, rb, g.b_kcontig, tid);
+      if (blk + 2 < n_blocks) {
+        tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + (blk + 2) * TK, kend, tid);
+        tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + (blk + 2) * TK, kend, tid);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(&full[s]);
+    };
+    for (int blk = 0; blk < n_blocks; blk += 2) {
+      body(blk, ra0, rb0);
+      if (blk + 1 < n_blocks) body(blk + 1, ra1, rb1);
+    }
+  } else {
+    uint32_t fphase[kStages] = {0, 0, 0};
+    for (int blk = 0; blk < n_blocks; ++blk) {
+      const int s = blk % kStages;
+      mbar_wait(&full[s], fphase[s]);
+      fphase[s] ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(tiles + (size_t)s * kStageBytes);
+        const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + kTileBytes), db_hi = umma_desc(a_hi + 2 * kTileBytes),
+                       db_lo = umma_desc(a_hi + 3 * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < TK / 8; ++kk) {
+          const uint64_t ko = (uint64_t)(kk * 32 >> 4);   // 8 TF32 = 32 bytes along K inside the swizzle row (address field: >> 4)
+          umma_tf32(tmem_d, da_hi + ko, db_hi + ko, (blk | kk) != 0);
+          umma_tf32(tmem_d, da_lo + ko, db_hi + ko, 1);
+          umma_tf32(tmem_d, da_hi + ko, db_lo + ko, 1);
+        }
+        umma_commit(&mma_done[s]);
+      }
+      __syncwarp();
     }
   }
-  // wait for the last commit of every stage that was used
-  if (n_blocks > 0) {
+  // the last commit covers every MMA issued before it
+  if (warp < 8 && n_blocks > 0) {
     const int last = (n_blocks - 1) % kStages;
     mbar_wait(&mma_done[last], phase[last]);
-    if (n_blocks > 1) {
-      const int prev = (n_blocks - 2) % kStages;
-      if (prev != last) mbar_wait(&mma_done[prev], phase[prev]);
-    }
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(256, 1) tc_gemm_kernel(const Gemm g) {
   float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
   const int row = m0 + 32 * (warp & 3) + lane;
 #pragma unroll 1
-  for (int cb = 0; cb < 2; ++cb) {
+  for (int cb = 0; cb < (warp < 8 ? 2 : 0); ++cb) {
     const int col0 = 64 * (warp >> 2) + 32 * cb;
     uint32_t v[32];
     if (n_blocks > 0) {
@@ -294,7 +320,7 @@ int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM, splits);
-  CVF_LAUNCH(K_AE_STEP, stream, tc_gemm_kernel<<<grid, 256, smem, stream>>>(g));
+  CVF_LAUNCH(K_AE_STEP, stream, tc_gemm_kernel<<<grid, 288, smem, stream>>>(g));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
