@@ -51,6 +51,8 @@ WORKLOADS = {
            "nets [81,20,20,20,1]", 1996, 128500),
     "c5": ("1000-atom AutoEncoderTask step on position features (d_r=3000), enc [3000,512,512,2], dec [2,512,512,3000]; "
            "layer-wise products on tcgen05 tensor cores (3 x TF32 split, fp32 accumulation in tensor memory)", 12004, 21590016),
+    "c2p": ("alanine-dipeptide AutoEncoderTask pre-pass (core.py:635): Kabsch alignment of every frame onto the reference, "
+            "22 atoms, aligned positions out (one pass over the trajectory, HBM-bound)", 528, 1500),
 }
 METRIC = "train-step frames/sec"
 # fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
@@ -138,6 +140,15 @@ def build_workload(name, n_frames, dev, seed, lr=1e-3):
     FakeTrajectory = bd.SyntheticTrajectory
     torch.manual_seed(2026)
     tmp = f"/tmp/cvf_bench_{os.getpid()}"
+    if name == "c2p":
+        base = bd.DIPEPTIDE_NM * 10.0
+        X = bd.frames(base, n_frames, dev, seed)
+        w = torch.ones(n_frames, device=dev)
+        align = utils.Align(base, list(range(22))).to(dev)
+
+        def step(Xb, wb):
+            return align(Xb)[0, 0, 0]
+        return step, X, w, None
     if name in ("c3", "c2"):
         base = bd.DIPEPTIDE_NM * 10.0
         X = bd.frames(base, n_frames, dev, seed)
@@ -205,6 +216,18 @@ def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(2026)
+    if name == "c2p":
+        base = ref_torch.DIPEPTIDE_NM * 10.0
+        X = torch.as_tensor(ref_torch.synth_frames(base, n_frames, seed=seed))
+        pp = ref_torch.Preprocess(ref_torch.Align(base, list(range(22))), None)
+        times = []
+        with torch.no_grad():
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                pp(X)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+        return n_frames * steps / sum(times), 1e3 * sum(times) / steps, cores
     if name == "c5":
         X = torch.randn(n_frames, 3000)
         w = torch.ones(n_frames)
@@ -283,7 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))   # c2p: the HBM-bound alignment pre-pass alone
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 2^22; 2^16 for c5)")
     ap.add_argument("--cpu-frames", type=int, default=None, help="frames per step of the CPU sample (default 100000; 4096 for c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -455,7 +478,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": KERNEL_TRAFFIC.get((args.workload, dom_name, args.frames)), "kernel": dom_name, "kernel_ms": kern_ms,
                      "kernel_share_of_step": prof[dom_name][0] / K / step_kernel_ms, "peak_source": peak_src,
-                     "note": "this path is fp32-FMA bound, not HBM bound (SURVEY 8d): see roofline_fp32"},
+                     "note": ("HBM-bound kernel: algorithmic bytes = frame read + aligned frame written" if args.workload == "c2p" else
+                              "this path is fp32-FMA bound, not HBM bound (SURVEY 8d): see roofline_fp32")},
         "roofline_fp32": {"bound": "fp32_fma", "peak": fma_peak, "unit": "TFLOP/s",
                           "peak_source": "cvf_fma_probe measured in this run",
                           "step": {"achieved": step_tflops, "frac": step_tflops / fma_peak, "flops_per_frame": flops_per_frame},

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _ops
+from . import utils as _utils
 from .nn import AutoEncoder, EigenFunctions
 
 
@@ -118,6 +119,29 @@ class TrainingTask(ABC):
                 np.savetxt('%s/%d_' % (d, idx) + name.replace('.', '_') + '.txt', param.detach().cpu().numpy())
         if self.verbose:
             print(f'  trained model saved at:\n\t{d}/model.pt')
+        # TorchScript export of the collective variables (reference core.py:210-227): scripted_cv_gpu.pt / scripted_cv_cpu.pt.
+        # The pre-processing layers of this package are exported as their stock-torch restatement (utils.scriptable), so the
+        # files load in libtorch (PLUMED, Colvars) without libcvf.
+        cv = self.colvar_model()
+        if isinstance(cv, torch.nn.Sequential) and len(cv) == 2:
+            cv = torch.nn.Sequential(_utils.scriptable(cv[0]).to(self.device), cv[1])
+        try:
+            if self.device.type == 'cuda':
+                torch.jit.script(cv).save(f'{d}/scripted_cv_gpu.pt')
+                if self.verbose:
+                    print(f'  script (GPU) model for CVs saved at:\n\t{d}/scripted_cv_gpu.pt\n', flush=True)
+                torch.jit.script(copy.deepcopy(cv).to('cpu')).save(f'{d}/scripted_cv_cpu.pt')
+            else:
+                torch.jit.script(cv).save(f'{d}/scripted_cv_cpu.pt')
+            if self.verbose:
+                print(f'  script (CPU) model for CVs saved at:\n\t{d}/scripted_cv_cpu.pt\n', flush=True)
+        except Exception as exc:   # a user-supplied pp_layer that TorchScript cannot compile: the reference would raise here
+            raise RuntimeError(f"TorchScript export of the collective-variable model failed: {exc}") from exc
+
+    def _cv_preprocessing(self):
+        """pp_layer as the first stage of colvar_model(): a bare utils.Align returns [B,N,3] frames, the networks take [B,3N]."""
+        pp = self.preprocessing_layer
+        return _utils.Preprocessing(pp, None) if isinstance(pp, _utils.Align) else pp
 
     def _shard(self, n):
         return _ops.shard_range(n, self._rank, self._world)
@@ -190,7 +214,7 @@ class EigenFunctionTask(TrainingTask):
     def colvar_model(self):
         if self._cvec is None:
             self._cvec = torch.arange(self.k)
-        return torch.nn.Sequential(self.preprocessing_layer, self.get_reordered_eigenfunctions(self.model, self._cvec))
+        return torch.nn.Sequential(self._cv_preprocessing(), self.get_reordered_eigenfunctions(self.model, self._cvec))
 
     def reg_model(self):
         return None
@@ -298,7 +322,7 @@ class AutoEncoderTask(TrainingTask):
         self._ctx = _ops.AEContext(self.model, self.device)
 
     def colvar_model(self):
-        return torch.nn.Sequential(self.preprocessing_layer, self.model.encoder)
+        return torch.nn.Sequential(self._cv_preprocessing(), self.model.encoder)
 
     def reg_model(self):
         return None

@@ -16,6 +16,7 @@ import os
 
 import numpy as np
 import torch
+from typing import List
 
 from . import _lib
 
@@ -201,3 +202,101 @@ class Preprocessing(torch.nn.Module):
             _lib.check(_lib.lib().cvf_features_fwd(x.data_ptr(), x.shape[0], spec.struct_ptr(), out.data_ptr(),
                                                    _stream_ptr()), "cvf_features_fwd")
         return out
+
+
+# ------------------------------------------------------------------------------------------ TorchScript export
+# save_model (reference core.py:212-227) writes torch.jit.script(Sequential(pp_layer, cv)) for use OUTSIDE this package
+# (PLUMED / Colvars load scripted_cv_{cpu,gpu}.pt through libtorch).  The training step never calls these modules: they are the
+# same maps r(x) as the CUDA kernels, restated with stock torch ops so that the exported file has no dependency on libcvf.
+class _ScriptAlign(torch.nn.Module):
+    def __init__(self, ref_pos, align_idx):
+        super().__init__()
+        self.register_buffer("ref_pos", ref_pos.detach().clone().to(torch.float32))
+        self.register_buffer("align_idx", align_idx.detach().clone().to(torch.long))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        xa = x.index_select(1, self.align_idx)
+        c = xa.mean(1, keepdim=True)
+        h = torch.matmul((xa - c).transpose(1, 2), self.ref_pos.to(x.dtype))
+        u, s, vh = torch.linalg.svd(h)
+        d = torch.sign(torch.linalg.det(torch.matmul(u, vh))).detach()
+        diag = torch.ones_like(s)
+        diag[:, 2] = d
+        rot = torch.matmul(u * diag.unsqueeze(1), vh)
+        return torch.matmul(x - c, rot)
+
+
+class _ScriptFeatures(torch.nn.Module):
+    def __init__(self, features):
+        super().__init__()
+        groups = {"position": [], "bond": [], "angle": [], "dihedral": []}
+        src = []                                   # (group, column inside the group's block) of every output column
+        for t, atoms in features:
+            if t == "position":
+                for a in atoms:
+                    j = len(groups[t])
+                    groups[t].append([a])
+                    src += [(0, 3 * j), (0, 3 * j + 1), (0, 3 * j + 2)]
+            elif t == "dihedral":
+                j = len(groups[t])
+                groups[t].append(atoms)
+                src += [(3, 2 * j), (3, 2 * j + 1)]
+            else:
+                j = len(groups[t])
+                groups[t].append(atoms)
+                src.append((1 if t == "bond" else 2, j))
+        widths = [3 * len(groups["position"]), len(groups["bond"]), len(groups["angle"]), 2 * len(groups["dihedral"])]
+        offs = [0, widths[0], widths[0] + widths[1], widths[0] + widths[1] + widths[2]]
+        self.register_buffer("perm", torch.tensor([offs[g] + c for g, c in src], dtype=torch.long))
+        for name, width in (("position", 1), ("bond", 2), ("angle", 3), ("dihedral", 4)):
+            t = torch.tensor(groups[name], dtype=torch.long).reshape(-1, width)
+            self.register_buffer(name + "_idx", t)
+
+    def forward(self, y: torch.Tensor) -> torch.Tensor:
+        b = y.shape[0]
+        parts: List[torch.Tensor] = []
+        parts.append(y.index_select(1, self.position_idx[:, 0]).reshape(b, -1))
+        p0 = y.index_select(1, self.bond_idx[:, 0])
+        p1 = y.index_select(1, self.bond_idx[:, 1])
+        parts.append(torch.linalg.norm(p1 - p0, dim=2))
+        a0 = y.index_select(1, self.angle_idx[:, 0])
+        a1 = y.index_select(1, self.angle_idx[:, 1])
+        a2 = y.index_select(1, self.angle_idx[:, 2])
+        u = a0 - a1
+        v = a2 - a1
+        parts.append((u * v).sum(2) / (torch.linalg.norm(u, dim=2) * torch.linalg.norm(v, dim=2)))
+        d0 = y.index_select(1, self.dihedral_idx[:, 0])
+        d1 = y.index_select(1, self.dihedral_idx[:, 1])
+        d2 = y.index_select(1, self.dihedral_idx[:, 2])
+        d3 = y.index_select(1, self.dihedral_idx[:, 3])
+        r12 = d1 - d0
+        r23 = d2 - d1
+        r34 = d3 - d2
+        n1 = torch.cross(r12, r23, dim=2)
+        n2 = torch.cross(r23, r34, dim=2)
+        den = torch.sqrt((n1 * n1).sum(2) * (n2 * n2).sum(2))
+        cs = (n1 * n2).sum(2) / den
+        sn = (n1 * r34).sum(2) * torch.linalg.norm(r23, dim=2) / den
+        parts.append(torch.stack([cs, sn], dim=2).reshape(b, -1))
+        return torch.cat(parts, dim=1).index_select(1, self.perm)
+
+
+class _ScriptFlatten(torch.nn.Module):
+    def forward(self, y: torch.Tensor) -> torch.Tensor:
+        return y.reshape(y.shape[0], -1)
+
+
+def scriptable(pp_layer):
+    """A torch.jit.script-able module computing the same r(x) as ``pp_layer`` with stock torch ops (used by save_model for the
+    exported collective-variable file).  Modules that are not defined in this package are returned unchanged."""
+    if isinstance(pp_layer, Align):
+        return torch.nn.Sequential(_ScriptAlign(pp_layer.ref_pos, pp_layer.align_idx), _ScriptFlatten())
+    if isinstance(pp_layer, FeatureMap):
+        return _ScriptFeatures(pp_layer.features)
+    if isinstance(pp_layer, Preprocessing):
+        mods = []
+        if pp_layer.align is not None:
+            mods.append(_ScriptAlign(pp_layer.align.ref_pos, pp_layer.align.align_idx))
+        mods.append(_ScriptFlatten() if pp_layer.feature_mapper is None else _ScriptFeatures(pp_layer.feature_mapper.features))
+        return torch.nn.Sequential(*mods)
+    return pp_layer

@@ -682,3 +682,33 @@ def test_save_model_and_unsupported(tmp_path):
     with pytest.raises(RuntimeError, match="Tanh"):
         core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1, torch.nn.ReLU()), str(tmp_path), 1.0,
                                [1.0], device=DEV, verbose=False)
+
+
+@pytest.mark.gpu
+def test_save_model_exports_scripted_collective_variables(tmp_path):
+    """save_model writes scripted_cv_gpu.pt / scripted_cv_cpu.pt (reference core.py:212-227); the exported module -- stock torch
+    ops only -- reproduces colvar_model(), which runs the CUDA pre-processing kernels."""
+    from colvarsfinder import core, nn, utils
+    heavy = [1, 4, 5, 6, 8, 10, 14, 15, 16, 18]
+    feats = [("bond", [1, 4]), ("angle", [4, 6, 8]), ("dihedral", [4, 6, 8, 14]), ("position", [8]), ("dihedral", [6, 8, 14, 16])]
+    X = ref_torch.synth_frames(BASE, 300, seed=11)
+    w = ref_torch.boltzmann_weights(300, seed=12)
+    for pp, d_r in ((utils.Align(BASE, list(range(22))), 66),
+                    (utils.Preprocessing(utils.Align(BASE[heavy], heavy), utils.FeatureMap(feats)), 9)):
+        torch.manual_seed(3)
+        out_dir = tmp_path / f"d{d_r}"
+        model = nn.EigenFunctions([d_r, 20, 20, 20, 1], 2)
+        task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64), dt=1.0), pp, model, str(out_dir), 20.0, [1.0, 0.5], k=2,
+                                      device=DEV, verbose=False, debug_mode=False)
+        task.save_model(0)
+        Xd = torch.as_tensor(X, device=DEV)
+        want = task.colvar_model()(Xd)
+        got_gpu = torch.jit.load(str(out_dir / "latest" / "scripted_cv_gpu.pt"))(Xd)
+        got_cpu = torch.jit.load(str(out_dir / "latest" / "scripted_cv_cpu.pt"))(torch.as_tensor(X))
+        assert want.shape == (300, 2)
+        assert torch.allclose(got_gpu, want, atol=2e-5, rtol=1e-4), (got_gpu - want).abs().max()
+        assert torch.allclose(got_cpu, want.cpu(), atol=2e-5, rtol=1e-4), (got_cpu - want.cpu()).abs().max()
+        # the task still trains after the export (the parameters must still alias the flat buffer the kernels read)
+        loss = task.loss_func(task._traj, task._weights, None, None)[0]
+        loss.backward()
+        assert all(p.grad is not None for p in model.parameters())

@@ -217,3 +217,34 @@ def test_shard_ranges_cover_everything():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_scriptable_preprocessing_matches_oracle_and_round_trips(tmp_path):
+    """utils.scriptable(): the stock-torch restatement of Align / FeatureMap / Preprocessing that save_model exports
+    (reference core.py:212-227) agrees with the oracle's pre-processing layer and survives torch.jit.script + save + load."""
+    import torch
+    from colvarsfinder import utils
+    from oracle import ref_torch
+    base = ref_torch.DIPEPTIDE_NM * 10.0
+    heavy = [1, 4, 5, 6, 8, 10, 14, 15, 16, 18]
+    feats = [("bond", [1, 4]), ("position", [4, 8]), ("angle", [4, 6, 8]), ("dihedral", [4, 6, 8, 14]), ("bond", [10, 18]),
+             ("dihedral", [6, 8, 14, 16])]
+    X = torch.as_tensor(ref_torch.synth_frames(base, 64, seed=5))
+    cases = [
+        (utils.Align(base, list(range(22))), ref_torch.Preprocess(ref_torch.Align(base, list(range(22))), None)),
+        (utils.Preprocessing(utils.Align(base[heavy], heavy), utils.FeatureMap(feats)),
+         ref_torch.Preprocess(ref_torch.Align(base[heavy], heavy), ref_torch.FeatureMap(feats))),
+        (utils.FeatureMap(feats), ref_torch.Preprocess(None, ref_torch.FeatureMap(feats))),
+    ]
+    for i, (pp, oracle_pp) in enumerate(cases):
+        mod = utils.scriptable(pp)
+        want = oracle_pp(X.double()).float()
+        got = mod(X)
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, atol=2e-5, rtol=1e-5), (i, (got - want).abs().max())
+        path = str(tmp_path / f"pp{i}.pt")
+        torch.jit.script(mod).save(path)
+        again = torch.jit.load(path)(X)
+        assert torch.equal(again, got)
+    ident = torch.nn.Identity()
+    assert utils.scriptable(ident) is ident
