@@ -106,11 +106,14 @@ class Align(torch.nn.Module):
         print('\natom indices used for alignment: \n', self.align_idx.cpu().numpy())
         print('\npositions of reference state used in aligment:\n', self.ref_pos.cpu().numpy())
 
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """Aligned frames; ``out`` (optional, [B,N,3] float32 on the same device) receives them without an allocation."""
         x = _require_cuda_f32(x, "Align")
         if x.dim() != 3 or x.shape[2] != 3:
             raise RuntimeError(f"Align expects [B,N,3], got {tuple(x.shape)}")
-        y = torch.empty_like(x)
+        if out is not None and (out.shape != x.shape or out.dtype != torch.float32 or out.device != x.device or not out.is_contiguous()):
+            raise RuntimeError("Align: out must be a contiguous float32 tensor of the input's shape on the input's device")
+        y = torch.empty_like(x) if out is None else out
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().cvf_align_fwd(x.data_ptr(), x.shape[0], x.shape[1], self.align_idx.data_ptr(),
                                                 self.align_idx.numel(), self.ref_pos.data_ptr(), y.data_ptr(), None,

@@ -50,7 +50,7 @@ __device__ __forceinline__ void align_frame_inplace(float* fr, int n_atoms, cons
 }
 
 // Thread per frame, tile of `tile_f` frames staged in shared memory (frame-major, stride = 3N floats).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 align_tile_kernel(const float* __restrict__ x, long long B, int n_atoms, const int32_t* __restrict__ aidx, int n_align,
                   const float* __restrict__ ref, float* __restrict__ y, float* __restrict__ R_out, float* __restrict__ c_out,
                   int tile_f, int use_tma) {

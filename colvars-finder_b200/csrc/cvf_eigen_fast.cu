@@ -321,7 +321,7 @@ __global__ void pack_kernel(const FastPlan P, const float* __restrict__ params) 
 
 // ------------------------------------------------------------------------------------------------ prep
 // kind 1: Kabsch per frame (thread per frame on a coalesced shared-memory tile), frame-minor output.
-__global__ void __launch_bounds__(128) prep_align_kernel(const FastPlan P, const float* __restrict__ x) {
+__global__ void __launch_bounds__(128, 6) prep_align_kernel(const FastPlan P, const float* __restrict__ x) {
   extern __shared__ __align__(16) float st[];
   const int tid = threadIdx.x;
   const int fl = 3 * P.n_atoms, S = fl | 1;   // odd stride: conflict-free column access
@@ -1560,7 +1560,9 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
   } else if (P.kind == 1) {
     const size_t smem = (size_t)(128 * ((3 * P.n_atoms) | 1) + 6 * 128) * sizeof(float);
     CVF_CUDA(cudaFuncSetAttribute(prep_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long grid = (long long)sm_count() * 4;
+    long long per_sm = (long long)(228 * 1024) / (long long)(smem + 1024);
+    per_sm = per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm;
+    long long grid = (long long)sm_count() * per_sm;
     if (P.Bp / 128 < grid) grid = P.Bp / 128;
     CVF_LAUNCH(K_FAST_PREP, stream, prep_align_kernel<<<(int)grid, 128, smem, stream>>>(P, x));
   } else {
