@@ -264,33 +264,6 @@ __global__ void zero_doubles_kernel(double* p, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.0;
 }
 
-// out[c][r] = in[r][c] (r < rows, c < cols) through 32 x 32 shared-memory tiles: the tensor-core kernel stages K-contiguous
-// operands four times faster than operands it has to transpose, so the products whose K is the frame index (weight gradients)
-// or the output index (back-propagated deltas) get transposed copies of their operands first -- an HBM-speed pass that costs a
-// few percent of the product it feeds.
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols,
-                                                        float* __restrict__ out, long long ld_out) {
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int tiles_c = (cols + 31) / 32;
-  const long long n_tiles = (long long)((rows + 31) / 32) * tiles_c;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int r0 = (int)(t / tiles_c) * 32, c0 = (int)(t % tiles_c) * 32;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r0 + ty + 8 * j, c = c0 + tx;
-      tile[ty + 8 * j][tx] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : 0.0f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = c0 + ty + 8 * j, r = r0 + tx;
-      if (c < cols && r < rows) out[(size_t)c * ld_out + r] = tile[tx][ty + 8 * j];
-    }
-    __syncthreads();
-  }
-}
-
 static inline int round4(int v) { return (v + 3) & ~3; }
 
 struct WidePlan {
@@ -302,9 +275,11 @@ struct WidePlan {
   size_t act_floats_per_frame;   // sum over layers 0..L of ld
   size_t delta_floats_per_frame; // 2 * max ld (ping-pong)
   size_t dw_max_floats;          // largest padded weight-gradient block
-  size_t wt_off[kMaxLayers];     // transposed weights [in][round4(out)] (tensor-core path)
-  size_t wt_floats;
-  size_t trans_floats_per_frame; // 2 * max ld: transposed delta and activation of the layer whose weight gradient is formed
+  // tensor-core path: tile images (cvf_gemm.cuh) of the weights as the B operand of the forward products (wf) and of the
+  // back-propagation products (wb), and per frame the floats of the two operand images of a weight-gradient product
+  size_t wf_off[kMaxLayers], wb_off[kMaxLayers];
+  size_t wimg_floats;
+  size_t img_floats_per_frame;
 };
 
 static void make_plan(const NetPlan& np, WidePlan* P) {
@@ -329,10 +304,16 @@ static void make_plan(const NetPlan& np, WidePlan* P) {
   }
   P->w_floats = wf;
   P->delta_floats_per_frame = 2 * (size_t)maxld;
-  P->trans_floats_per_frame = 2 * (size_t)maxld;
-  size_t wt = 0;
-  for (int l = 0; l < np.L; ++l) P->wt_off[l] = wt, wt += (size_t)np.dims[l] * round4(np.dims[l + 1]);
-  P->wt_floats = wt;
+  size_t wi = 0;
+  int maxrows = 0;
+  for (int l = 0; l < np.L; ++l) {
+    P->wf_off[l] = wi, wi += tile_image_floats(np.dims[l + 1], np.dims[l]);
+    P->wb_off[l] = wi, wi += tile_image_floats(np.dims[l], np.dims[l + 1]);
+    if (np.dims[l + 1] > maxrows) maxrows = np.dims[l + 1];
+    if (np.dims[l] + 1 > maxrows) maxrows = np.dims[l] + 1;
+  }
+  P->wimg_floats = wi;
+  P->img_floats_per_frame = 2 * (size_t)((maxrows + 127) / 128 * 128) * 2;   // two operands, hi + lo, rows padded to the tile
 }
 
 constexpr int kMaxSplits = 32;
@@ -360,8 +341,8 @@ size_t wide_ae_workspace_bytes(const NetPlan& np, long long B) {
   wide::make_plan(np, &P);
   long long chunk = B < 32768 ? B : 32768;
   chunk = (chunk + 127) / 128 * 128;
-  const size_t per_frame = (P.act_floats_per_frame + P.delta_floats_per_frame + P.trans_floats_per_frame) * sizeof(float);
-  return 8192 + (P.w_floats + P.wt_floats) * sizeof(float) + (size_t)wide::kMaxSplits * P.dw_max_floats * sizeof(float) +
+  const size_t per_frame = (P.act_floats_per_frame + P.delta_floats_per_frame + P.img_floats_per_frame) * sizeof(float);
+  return 8192 + (P.w_floats + P.wimg_floats) * sizeof(float) + (size_t)wide::kMaxSplits * P.dw_max_floats * sizeof(float) +
          (size_t)chunk * per_frame + (size_t)sm_count() * 8 * 2 * sizeof(double);
 }
 
@@ -381,13 +362,13 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   };
   double* part = (double*)take((size_t)sm_count() * 8 * 2 * sizeof(double));
   float* Wp = (float*)take(P.w_floats * sizeof(float));
-  float* WT = (float*)take(P.wt_floats * sizeof(float));
+  float* Wimg = (float*)take(P.wimg_floats * sizeof(float));
   float* dWp = (float*)take((size_t)kMaxSplits * P.dw_max_floats * sizeof(float));
   if (off >= ws_bytes) {
     set_error("workspace too small for the layer-wise autoencoder path: %zu bytes", ws_bytes);
     return CVF_E_WORKSPACE;
   }
-  const size_t per_frame = (P.act_floats_per_frame + P.delta_floats_per_frame + P.trans_floats_per_frame) * sizeof(float);
+  const size_t per_frame = (P.act_floats_per_frame + P.delta_floats_per_frame + P.img_floats_per_frame) * sizeof(float);
   long long chunk = (long long)((ws_bytes - off - 2048) / per_frame);
   chunk = chunk / 128 * 128;
   if (chunk > 32768) chunk = 32768;
@@ -403,8 +384,8 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   }
   float* dbuf = (float*)take((size_t)chunk * P.delta_floats_per_frame * sizeof(float));
   float* delta[2] = {dbuf, dbuf + (size_t)chunk * (P.delta_floats_per_frame / 2)};
-  float* tbuf = (float*)take((size_t)chunk * P.trans_floats_per_frame * sizeof(float));
-  float* trans[2] = {tbuf, tbuf + (size_t)chunk * (P.trans_floats_per_frame / 2)};
+  float* ibuf = (float*)take((size_t)chunk * P.img_floats_per_frame * sizeof(float));
+  float* opimg[2] = {ibuf, ibuf + (size_t)chunk * (P.img_floats_per_frame / 2)};
   const bool tc = g_wide_mode == 0;
 
   for (int l = 0; l < L; ++l) {
@@ -413,12 +394,14 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
                pad_weights_kernel<<<(n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256, 256, 0, stream>>>(params + P.gw_off[l], P.dims[l + 1],
                                                                                                      P.dims[l], Wp + P.w_off[l], P.ld[l]));
   }
-  if (tc && grad_out) {
-    for (int l = 1; l < L; ++l) {   // W_l^T for the back-propagation products (layer 0 has none)
-      const long long nt = (long long)((P.dims[l + 1] + 31) / 32) * ((P.dims[l] + 31) / 32);
-      CVF_LAUNCH(K_AE_STEP, stream,
-                 transpose_kernel<<<(int)(nt > 2048 ? 2048 : nt), 256, 0, stream>>>(Wp + P.w_off[l], P.ld[l], P.dims[l + 1], P.dims[l],
-                                                                                   WT + P.wt_off[l], cvf::round4(P.dims[l + 1])));
+  if (tc) {   // weight images: B operand of the forward products and (layers >= 1, training only) of the back-propagation products
+    for (int l = 0; l < L; ++l) {
+      int e = launch_tile_image(Wp + P.w_off[l], P.ld[l], 1, P.dims[l + 1], P.dims[l], Wimg + P.wf_off[l], stream);
+      if (e) return e;
+      if (grad_out && l >= 1) {
+        e = launch_tile_image(Wp + P.w_off[l], P.ld[l], 0, P.dims[l], P.dims[l + 1], Wimg + P.wb_off[l], stream);
+        if (e) return e;
+      }
     }
   }
   if (grad_out) CVF_LAUNCH(K_AE_STEP, stream, zero_doubles_kernel<<<64, 256, 0, stream>>>(grad_out, np.n_params));
@@ -446,6 +429,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
       g.M = M, g.N = P.dims[l + 1], g.K = P.dims[l], g.k_per_split = g.K;
       g.epi = P.act[l] ? EPI_BIAS_TANH : EPI_BIAS;
       g.bias = params + P.gb_off[l];
+      if (tc) g.b_img = Wimg + P.wf_off[l], g.b_img_kblocks = (P.dims[l] + 31) / 32;
       int e = launch_gemm(g, 1, stream);
       if (e) return e;
     }
@@ -475,15 +459,12 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         memset(&g, 0, sizeof(g));
         g.A = dcur, g.lda = cur_ld, g.a_kcontig = 0;          // Aop[i][f] = delta[f][i]
         g.B = acts[l], g.ldb = P.ld[l], g.b_kcontig = 0;      // Bop[f][j] = A_l[f][j]
-        if (tc) {   // frame-contiguous copies of both operands
-          const long long Mp = cvf::round4(M);
-          const long long nta = (long long)((M + 31) / 32) * ((rows + 31) / 32), ntb = (long long)((M + 31) / 32) * ((cols + 31) / 32);
-          CVF_LAUNCH(K_AE_STEP, stream,
-                     transpose_kernel<<<(int)(nta > 8192 ? 8192 : nta), 256, 0, stream>>>(dcur, cur_ld, M, rows, trans[0], Mp));
-          CVF_LAUNCH(K_AE_STEP, stream,
-                     transpose_kernel<<<(int)(ntb > 8192 ? 8192 : ntb), 256, 0, stream>>>(acts[l], P.ld[l], M, cols, trans[1], Mp));
-          g.A = trans[0], g.lda = Mp, g.a_kcontig = 1;
-          g.B = trans[1], g.ldb = Mp, g.b_kcontig = 1;
+        if (tc) {   // both operands as tile images over the frames (split, transposed and swizzled once, read by bulk copies)
+          int e = launch_tile_image(dcur, cur_ld, 0, rows, M, opimg[0], stream);
+          if (e) return e;
+          e = launch_tile_image(acts[l], P.ld[l], 0, cols, M, opimg[1], stream);
+          if (e) return e;
+          g.a_img = opimg[0], g.b_img = opimg[1], g.a_img_kblocks = g.b_img_kblocks = (M + 31) / 32;
         }
         g.C = dWp, g.ldc = P.ld[l], g.c_split_stride = (long long)rows * P.ld[l];
         g.M = rows, g.N = cols, g.K = M, g.k_per_split = kps;
@@ -504,7 +485,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         memset(&g, 0, sizeof(g));
         g.A = dcur, g.lda = cur_ld, g.a_kcontig = 1;                    // Aop[f][i] = delta[f][i]
         g.B = Wp + P.w_off[l], g.ldb = P.ld[l], g.b_kcontig = 0;        // Bop[i][j] = W[i][j]
-        if (tc) g.B = WT + P.wt_off[l], g.ldb = cvf::round4(P.dims[l + 1]), g.b_kcontig = 1;   // W^T[j][i]
+        if (tc) g.b_img = Wimg + P.wb_off[l], g.b_img_kblocks = (P.dims[l + 1] + 31) / 32;
         g.C = dnext, g.ldc = P.ld[l];
         g.M = M, g.N = P.dims[l], g.K = P.dims[l + 1], g.k_per_split = g.K;
         g.epi = P.act[l - 1] ? EPI_MUL_OM : EPI_NONE;

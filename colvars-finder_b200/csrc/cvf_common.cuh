@@ -25,10 +25,12 @@ int check_cuda(cudaError_t e, const char* what);
 int sm_count();
 int max_smem_optin();
 
-#define CVF_CUDA(call)                                   \
-  do {                                                   \
-    int _e = cvf::check_cuda((call), #call);             \
-    if (_e) return _e;                                   \
+#define CVF_STR2(x) #x
+#define CVF_STR(x) CVF_STR2(x)
+#define CVF_CUDA(call)                                                          \
+  do {                                                                          \
+    int _e = cvf::check_cuda((call), #call " at " __FILE__ ":" CVF_STR(__LINE__)); \
+    if (_e) return _e;                                                          \
   } while (0)
 
 // Launch accounting (cvf_api.cu): every kernel launch of the library goes through CVF_LAUNCH, which counts it and, while

@@ -24,11 +24,22 @@ struct Gemm {
   int epi;
   const float* bias;   // [N]
   const float* act;    // EPI_MUL_OM: [M][ldc] activations A with C *= 1 - A^2
+  // Tensor-core path only: operand "tile images".  An image holds the operand already split into TF32 hi / lo parts and laid
+  // out exactly as the kernel's shared-memory stage wants it (K-major 128 x 32 tiles, 128-byte swizzle, zero padded):
+  // image[(row_tile * kblocks + k_block) * 8192 floats] = hi tile (4096 floats) | lo tile, k_block counted from K = 0.  A stage
+  // is then filled by one 1-D bulk asynchronous copy (TMA) per operand instead of through registers.  NULL = stage from A / B.
+  const float* a_img;
+  const float* b_img;
+  int a_img_kblocks, b_img_kblocks;
 };
 
 // cvf_gemm_tc.cu: the same product on the 5th-generation tensor cores; grid = (ceil(N/128), ceil(M/128), splits), k_per_split
 // a multiple of 32 when splits > 1
 int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream);
+// floats of the image of an operand with `rows` rows and K columns
+inline size_t tile_image_floats(int rows, int K) { return (size_t)((rows + 127) / 128) * ((K + 31) / 32) * 8192; }
+// builds the image of Xop[row][k] = kcontig ? X[row * ld + k] : X[k * ld + row]
+int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K, float* img, cudaStream_t stream);
 
 }  // namespace wide
 }  // namespace cvf

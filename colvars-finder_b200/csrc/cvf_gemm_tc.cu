@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: start address, stride between 8-row groups 1024 B,
 // descriptor version 1 (sm_100), layout type SWIZZLE_128B
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -191,15 +200,18 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
   // shared-memory stages, handed over through the `full` mbarriers).  Warp 8 only issues the MMAs of every filled stage and
   // commits them to `mma_done`, which hands the stage back.
   uint32_t phase[kStages] = {0, 0, 0};
+  // image of this CTA's row tile of each operand (k-block 0), or null
+  const float* a_img = g.a_img ? g.a_img + (size_t)blockIdx.y * g.a_img_kblocks * (2 * kTileBytes / 4) : nullptr;
+  const float* b_img = g.b_img ? g.b_img + (size_t)blockIdx.x * g.b_img_kblocks * (2 * kTileBytes / 4) : nullptr;
   if (warp < 8) {
     Stage4 ra0, rb0, ra1, rb1;
     if (n_blocks > 0) {
-      tc_load(ra0, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg, kend, tid);
-      tc_load(rb0, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg, kend, tid);
+      if (!a_img) tc_load(ra0, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg, kend, tid);
+      if (!b_img) tc_load(rb0, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg, kend, tid);
     }
     if (n_blocks > 1) {
-      tc_load(ra1, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + TK, kend, tid);
-      tc_load(rb1, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + TK, kend, tid);
+      if (!a_img) tc_load(ra1, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + TK, kend, tid);
+      if (!b_img) tc_load(rb1, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + TK, kend, tid);
     }
     auto body = [&](int blk, Stage4& ra, Stage4& rb) {
       const int s = blk % kStages;
@@ -209,11 +221,17 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
         mbar_wait(&mma_done[s], phase[s]);
         phase[s] ^= 1;
       }
-      tc_store(st, st + kTileBytes, ra, g.a_kcontig, tid);
-      tc_store(st + 2 * kTileBytes, st + 3 * kTileBytes, rb, g.b_kcontig, tid);
+      if (tid == 0 && (a_img || b_img)) {   // operands that come as tile images: one bulk copy each, counted in bytes on `full`
+        const int kb = kbeg / TK + blk;
+        mbar_expect_tx(&full[s], (uint32_t)((a_img ? 2 : 0) + (b_img ? 2 : 0)) * kTileBytes);
+        if (a_img) bulk_g2s(st, a_img + (size_t)kb * (2 * kTileBytes / 4), 2 * kTileBytes, &full[s]);
+        if (b_img) bulk_g2s(st + 2 * kTileBytes, b_img + (size_t)kb * (2 * kTileBytes / 4), 2 * kTileBytes, &full[s]);
+      }
+      if (!a_img) tc_store(st, st + kTileBytes, ra, g.a_kcontig, tid);
+      if (!b_img) tc_store(st + 2 * kTileBytes, st + 3 * kTileBytes, rb, g.b_kcontig, tid);
       if (blk + 2 < n_blocks) {
-        tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + (blk + 2) * TK, kend, tid);
-        tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + (blk + 2) * TK, kend, tid);
+        if (!a_img) tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + (blk + 2) * TK, kend, tid);
+        if (!b_img) tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + (blk + 2) * TK, kend, tid);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&full[s]);
@@ -312,6 +330,36 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
   }
 }
 
+// One CTA per (row tile, k-block): the same load / split / swizzled store as the product kernel's staging, into shared memory,
+// then the finished 32 KB image (hi tile | lo tile) goes out as coalesced 16-byte stores.
+__global__ void __launch_bounds__(256) tile_image_kernel(const float* __restrict__ X, long long ld, int kcontig, int rows, int K,
+                                                         int kblocks, float* __restrict__ img) {
+  __shared__ __align__(1024) uint8_t buf[2 * kTileBytes];
+  const int tid = threadIdx.x;
+  const long long n_items = (long long)((rows + TM - 1) / TM) * kblocks;
+  for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int rt = (int)(it / kblocks), kb = (int)(it - (long long)rt * kblocks);
+    Stage4 r;
+    tc_load(r, X, ld, kcontig, rt * TM, rows, kb * TK, K, tid);
+    __syncthreads();   // the previous item's copy-out has finished reading buf
+    tc_store(buf, buf + kTileBytes, r, kcontig, tid);
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(img + (size_t)it * (2 * kTileBytes / 4));
+    const float4* src = reinterpret_cast<const float4*>(buf);
+#pragma unroll
+    for (int i = 0; i < 2 * kTileBytes / 16 / 256; ++i) dst[tid + 256 * i] = src[tid + 256 * i];
+  }
+}
+
+int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K, float* img, cudaStream_t stream) {
+  const int kblocks = (K + TK - 1) / TK;
+  const long long n_items = (long long)((rows + TM - 1) / TM) * kblocks;
+  const int grid = (int)(n_items > 148 * 16 ? 148 * 16 : n_items);
+  CVF_LAUNCH(K_AE_STEP, stream, tile_image_kernel<<<grid, 256, 0, stream>>>(X, ld, kcontig, rows, K, kblocks, img));
+  CVF_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream) {
   const size_t smem = (size_t)kStages * kStageBytes + 1024;
   static bool configured = false;
@@ -321,7 +369,14 @@ int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream) {
   }
   dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM, splits);
   CVF_LAUNCH(K_AE_STEP, stream, tc_gemm_kernel<<<grid, 288, smem, stream>>>(g));
-  CVF_CUDA(cudaGetLastError());
+  {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("tc_gemm_kernel launch failed: grid (%u,%u,%u), %zu B shared memory, M %d N %d K %d: %s", grid.x, grid.y, grid.z, smem,
+                g.M, g.N, g.K, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
   return 0;
 }
 
