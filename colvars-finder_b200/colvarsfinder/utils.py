@@ -64,6 +64,28 @@ class WeightedTrajectory:
             self.weights = np.ones(self.n_frames)
 
 
+def calc_weights(csv_filename, sampling_beta, sys_beta, traj_weight_filename='weights.txt', energy_col_idx=1):
+    """Weights of trajectory data from an energy column of a CSV file (reference utils.py:354-417):
+    v_i = exp(-(beta_sys - beta_sim) (V_i - mean V)) / mean, written one per line to ``traj_weight_filename``.
+    Host-side data preparation (the file feeds ``WeightedTrajectory(weight_filename=...)``); same arguments, prints and
+    output file as the reference."""
+    import pandas as pd
+    print('\n=============Calculate Weights============')
+    print(f'Reading potential from: {csv_filename}')
+    vec = pd.read_csv(csv_filename)
+    vec.rename(columns={vec.columns[0]: 'Time'}, inplace=True)
+    print('\nWhole data:\n', vec.head(8))
+    energy_col_name = vec.columns[energy_col_idx]
+    print('\nUse {:d}th column to reweight, name: {}'.format(energy_col_idx, energy_col_name))
+    energy = vec[energy_col_name].to_numpy(dtype=np.float64)
+    print(f'\nsampling beta={sampling_beta}, system beta={sys_beta}')
+    nonnormalized = np.exp(-(sys_beta - sampling_beta) * (energy - energy.mean()))
+    weights = pd.DataFrame(nonnormalized / np.mean(nonnormalized), columns=['weight'])
+    print('\nWeight:\n', weights.head(8), '\n\nSummary of weights:\n', weights.describe())
+    weights.to_csv(traj_weight_filename, header=False, index=False)
+    print(f'weights saved to: {traj_weight_filename}')
+
+
 def _stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 

@@ -248,3 +248,23 @@ def test_scriptable_preprocessing_matches_oracle_and_round_trips(tmp_path):
         assert torch.equal(again, got)
     ident = torch.nn.Identity()
     assert utils.scriptable(ident) is ident
+
+
+def test_calc_weights_matches_reference_golden(tmp_path, capsys):
+    """utils.calc_weights against the weights file the unmodified reference wrote for the same CSV (oracle/gen_golden_weights.py)."""
+    import os
+    from colvarsfinder import utils
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "calc_weights.npz"))
+    csv = tmp_path / "state.csv"
+    with open(csv, "w") as f:
+        f.write('#"Time (ps)","Potential Energy (kJ/mole)","Total Energy (kJ/mole)"\n')
+        for t, a, b in zip(g["time"], g["pot"], g["tot"]):
+            f.write(f"{float(t)!r},{float(a)!r},{float(b)!r}\n")
+    for tag in ("a", "b"):
+        b_sim, b_sys, col = g[f"args_{tag}"]
+        out = tmp_path / f"w_{tag}.txt"
+        utils.calc_weights(str(csv), float(b_sim), float(b_sys), traj_weight_filename=str(out), energy_col_idx=int(col))
+        got = np.loadtxt(out)
+        np.testing.assert_allclose(got, g[f"weights_{tag}"], rtol=1e-12, atol=0)
+        assert abs(got.mean() - 1.0) < 1e-12
+    assert "Calculate Weights" in capsys.readouterr().out
