@@ -35,6 +35,8 @@ _P, _I64, _I32, _D, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size
 SYMBOLS = {
     "cvf_version": (C.c_int, []),
     "cvf_last_error_string": (C.c_char_p, []),
+    "cvf_sizeof_preproc": (_SZ, []),
+    "cvf_sizeof_mlp": (_SZ, []),
     "cvf_mlp_param_count": (_I64, [C.POINTER(Mlp)]),
     "cvf_align_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "cvf_features_fwd": (C.c_int, [_P, _I64, C.POINTER(Preproc), _P, _P]),
@@ -73,6 +75,8 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
+        if handle.cvf_sizeof_preproc() != C.sizeof(Preproc) or handle.cvf_sizeof_mlp() != C.sizeof(Mlp):
+            raise RuntimeError(f"{LIB_PATH} was built against a different include/cvf.h (struct sizes differ): rebuild it")
         _lib = handle
     return _lib
 

@@ -132,3 +132,5 @@ extern "C" int cvf_fma_probe(float* sink, int32_t iters, double* flops_out, void
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
+extern "C" size_t cvf_sizeof_preproc(void) { return sizeof(cvf_preproc); }
+extern "C" size_t cvf_sizeof_mlp(void) { return sizeof(cvf_mlp); }

@@ -1271,15 +1271,25 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 // fp32 sums to its own fp64 block of that network (one owner per address: deterministic).
 constexpr int kRun = 16;
 
+// half of stage_rows: of the row quads 0, 1, 2, ... warp `h` of a pair takes the even (h = 0) or odd (h = 1) ones
+__device__ __forceinline__ void stage_rows_half(float* dst, const float* src, int nrows, long long Bp, int lane, int h) {
+  const int c4 = 4 * (lane & 7);
+#pragma unroll 4
+  for (int r = (lane >> 3) + 4 * h; r < nrows; r += 8) cp_async16(dst + r * kRowPad + c4, src + (size_t)r * Bp + c4);
+}
+
+// Two warps share one pair of staging buffers: each issues half of the copies of a tile and multiplies half of its frames, so
+// the shared memory that held four independent warps holds eight and the dependency stalls of one are covered by the others.
 template <int H, int TI>
 __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* __restrict__ part2) {
   extern __shared__ __align__(16) float sm[];
   constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
+  const int pair = warp >> 1, h = warp & 1, npairs = nw >> 1;
   const int drp = P.d_rp, d_r = P.d_r, nig = drp / TI, k = P.k, blk = H * d_r;
   const int rows_per_buf = 2 * drp + 2 * H;
-  float* buf0 = sm + (size_t)warp * 2 * rows_per_buf * RP;   // two staging buffers per warp: r | vhat | s_1, scale G_1
-  for (int i = tid; i < nw * 2 * rows_per_buf * RP; i += nt) sm[i] = 0.0f;
+  float* buf0 = sm + (size_t)pair * 2 * rows_per_buf * RP;   // two staging buffers per pair: r | vhat | s_1, scale G_1
+  for (int i = tid; i < npairs * 2 * rows_per_buf * RP; i += nt) sm[i] = 0.0f;
   double* part = part2 + ((size_t)blockIdx.x * nw + warp) * (size_t)(k * blk);   // [k][H * d_r]
   for (int i = lane; i < k * blk; i += 32) part[i] = 0.0;
   __syncthreads();
@@ -1287,16 +1297,16 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* _
   const bool active = og < TQ && ig < nig;
   const long long n_tiles = P.Bp / 32;
   const long long n_runs = (n_tiles + kRun - 1) / kRun, n_items = n_runs * k;
-  const long long stride = (long long)gridDim.x * nw;
-  // the warp's tiles form one sequence (item q, tile t inside its run); tile i + 1 is staged while tile i is multiplied
+  const long long stride = (long long)gridDim.x * npairs;
+  // the pair's tiles form one sequence (item q, tile t inside its run); tile i + 1 is staged while tile i is multiplied
   auto stage = [&](int b, int n, long long t) {
     float* R = buf0 + (size_t)b * rows_per_buf * RP;
-    stage_rows(R, P.Y + t * 32, d_r, P.Bp, lane);
-    stage_rows(R + drp * RP, P.U + ((size_t)n * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
-    stage_rows(R + 2 * drp * RP, P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, 2 * H, P.Bp, lane);
+    stage_rows_half(R, P.Y + t * 32, d_r, P.Bp, lane, h);
+    stage_rows_half(R + drp * RP, P.U + ((size_t)n * drp) * P.Bp + t * 32, d_r, P.Bp, lane, h);
+    stage_rows_half(R + 2 * drp * RP, P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, 2 * H, P.Bp, lane, h);
     cp_async_commit();
   };
-  long long q = (long long)blockIdx.x * nw + warp;
+  long long q = (long long)blockIdx.x * npairs + pair;
   int cur = 0;
   if (q < n_items) stage(0, (int)(q % k), (q / k) * kRun);
   for (; q < n_items; q += stride) {
@@ -1308,27 +1318,27 @@ __global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* _
 #pragma unroll
       for (int i = 0; i < TI; ++i) acc[j][i] = make_float2(0.f, 0.f);
     for (long long t = t0; t < t1; ++t) {
-      // successor of (q, t) in this warp's sequence
+      // successor of (q, t) in this pair's sequence
       long long tn = t + 1, qn = q;
       if (tn >= t1) qn = q + stride, tn = (qn / k) * kRun;
-      __syncwarp();   // every lane has finished reading the buffer that is staged next
+      named_barrier(1 + pair, 64);   // both warps have finished reading the buffer that is staged next
       if (qn < n_items) {
         stage(cur ^ 1, (int)(qn % k), tn);
         cp_async_wait_group<1>();
       } else {
         cp_async_wait_all();
       }
-      __syncwarp();
+      named_barrier(1 + pair, 64);   // both halves of the current tile have landed
       const float* R = buf0 + (size_t)cur * rows_per_buf * RP;
       if (active)
         outer_tile<4, TI>(acc, R + (2 * drp + og) * RP, R + ig * RP, R + (2 * drp + H + og) * RP, R + (drp + ig) * RP, TQ * RP,
-                          nig * RP, 0, 32);
+                          nig * RP, 16 * h, 16 * h + 16);
       cur ^= 1;
     }
-    // fp32 sums of the run -> this warp's fp64 block of network n, transposed through the X rows of the buffer just used so
-    // that the additions are coalesced (those rows are restaged before their next use)
-    __syncwarp();
-    float* T = buf0 + (size_t)(cur ^ 1) * rows_per_buf * RP;
+    // fp32 sums of the run -> this warp's fp64 block of network n, transposed through its half of the buffer just used so that
+    // the additions are coalesced (the buffer is restaged, after the pair's next barrier, before its next use)
+    named_barrier(1 + pair, 64);
+    float* T = buf0 + (size_t)(cur ^ 1) * rows_per_buf * RP + (size_t)h * (rows_per_buf * RP / 2);
     if (active) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -1387,11 +1397,13 @@ static int pass2_warps(int k, int img2_floats, int geo_floats, int drp, int H, i
     if (pass2_smem_bytes(k, img2_floats, geo_floats, drp, H, NH, wv) <= (size_t)max_smem_optin()) return wv;
   return 0;
 }
-static size_t dw1_smem_bytes(int warps, int drp, int H) { return (size_t)warps * 2 * (2 * drp + 2 * H) * kRowPad * sizeof(float); }
-// warps of a pass-2b CTA (two staging buffers each): as many as fit (<= 8); 0 if fewer than 2 fit
+static size_t dw1_smem_bytes(int warps, int drp, int H) { return (size_t)(warps / 2) * 2 * (2 * drp + 2 * H) * kRowPad * sizeof(float); }
+// warps of a pass-2b CTA (pairs of warps share two staging buffers): as many as fit (<= 8); 0 if no pair fits, or if a
+// warp's half of a buffer cannot hold the [H][d_r] block it transposes through it
 static int dw1_warps(int k, int drp, int H) {
   (void)k;
-  for (int wv = kP2MaxWarps; wv >= 2; --wv)
+  if ((size_t)H * drp > (size_t)(2 * drp + 2 * H) * kRowPad / 2) return 0;
+  for (int wv = kP2MaxWarps; wv >= 2; wv -= 2)
     if (dw1_smem_bytes(wv, drp, H) <= (size_t)max_smem_optin()) return wv;
   return 0;
 }
@@ -1651,8 +1663,9 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   const int warps_b = dw1_warps(k, P.d_rp, H);
   const size_t smem3 = dw1_smem_bytes(warps_b, P.d_rp, H);
   const long long n_items = (n_tiles + kRun - 1) / kRun * k;
+  const int pairs_b = warps_b / 2;
   long long grid_b = sm_count();
-  if ((n_items + warps_b - 1) / warps_b < grid_b) grid_b = (n_items + warps_b - 1) / warps_b;
+  if ((n_items + pairs_b - 1) / pairs_b < grid_b) grid_b = (n_items + pairs_b - 1) / pairs_b;
   const int ti = dw1_cols_per_lane(P.d_rp, H);
 #define CVF_DW1(TI_)                                                                                                       \
   do {                                                                                                                     \

@@ -80,6 +80,9 @@ typedef struct cvf_mlp {
 
 int cvf_version(void);
 const char* cvf_last_error_string(void);
+/* sizeof(cvf_preproc) / sizeof(cvf_mlp) as this library was compiled: lets a binding check its own struct layout */
+size_t cvf_sizeof_preproc(void);
+size_t cvf_sizeof_mlp(void);
 
 /* number of float parameters of one chain, in torch's parameters() order: W1[out,in], b1[out], W2, b2, ... */
 int64_t cvf_mlp_param_count(const cvf_mlp* net);
