@@ -64,26 +64,29 @@ KERNEL_FLOPS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture of this command under profiles/
 # (r01_ncu_c3_summary.txt); keyed by (workload, kernel, frames per launch) and not extrapolated to other sizes
 KERNEL_TRAFFIC = {
-    ("c3", "fast_pass2a", 1 << 22): 7.090627e9 + 7.657184e9,
-    ("c3", "fast_pass1", 1 << 22): 1.309251e9 + 4.319722e9,
-    ("c3", "fast_pass2b(dW1)", 1 << 22): 6.717460e9 + 0.277013e9,
-    ("c3", "fast_prep", 1 << 22): 1.107347e9 + 1.259367e9,
+    ("c3", "fast_pass2a", 1 << 22): 7.090671e9 + 7.656838e9,
+    ("c3", "fast_pass1", 1 << 22): 1.309395e9 + 4.320238e9,
+    ("c3", "fast_pass2b(dW1)", 1 << 22): 7.168490e9 + 0.552433e9,
+    ("c3", "fast_prep", 1 << 22): 1.115100e9 + 1.265860e9,
 }
 
 
 # ------------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The sampler is started before
+    the warm-up steps (nvidia-smi needs ~0.1 s to start) and `mark()` / `stop()` bracket the timed region; only samples read
+    inside the bracket count.  If the region was too short for one, the samples of the warm-up steps (same load) are used and
+    the result says so."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_mark = index, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -93,9 +96,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
 
     def stop(self):
+        t_end = time.perf_counter()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -103,8 +110,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t_mark if self.t_mark is not None else 0.0
+        inside = [r for t, r in self.rows if t0 <= t <= t_end + 0.05]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than one sampling period)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
@@ -114,7 +126,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -356,6 +368,7 @@ def main():
     entry.build()
     from colvarsfinder import _lib
 
+    sampler = ClockSampler(local).start() if rank == 0 else None   # started early: nvidia-smi takes a while to deliver its first row
     step, X, w, task = build_workload(args.workload, args.frames, dev, seed=2026 + rank)
     W = max(args.warmup, 3)
     K = args.steps
@@ -370,7 +383,8 @@ def main():
         step(X, w)
     barrier()
     _lib.profile_read(reset=True)      # launch counters to zero: the timed region is counted exactly
-    sampler = ClockSampler(local).start() if rank == 0 else None
+    if sampler:
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
