@@ -371,6 +371,119 @@ def test_eigen_fast_feature_path_matches_oracle(name, B, tmp_path):
     assert abs(float(res[0][0][0]) - float(res[1][0][0])) <= (5e-5 if B > 2 else 5e-4) * abs(float(res[1][0][0]))
 
 
+def _feature_task(tmp_path, base, feats, align_idx, dims, k, X, w, diag=None, lag_tau=0, dt=1.0, eig_w=None):
+    from colvarsfinder import core, nn, utils
+    fmap = utils.FeatureMap(feats)
+    pp = fmap if align_idx is None else utils.Preprocessing(utils.Align(base[align_idx], align_idx), fmap)
+    nets = _random_nets(dims, k, seed=sum(dims) + k)
+    model = nn.EigenFunctions(dims, k)
+    with torch.no_grad():
+        for i in range(k):
+            for p, v in zip(model.eigen_funcs[i].parameters(), nets[i]):
+                p.copy_(torch.as_tensor(v))
+    eig_w = eig_w or [1.0, 0.6, 0.3, 0.2, 0.15, 0.1, 0.05][:k]
+    task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64), dt=dt), pp, model, str(tmp_path), 20.0, eig_w,
+                                  diag_coeff=None if diag is None else torch.as_tensor(diag), lag_tau=lag_tau, k=k, device=DEV,
+                                  verbose=False, debug_mode=False)
+    return task, model, nets, eig_w
+
+
+@pytest.mark.parametrize("dims_k", [([9, 16, 16, 16, 1], 1), ([9, 32, 32, 32, 1], 2), ([9, 20, 20, 1], 4), ([9, 20, 20, 20, 1], 7)])
+def test_eigen_fast_feature_path_network_shapes(dims_k, tmp_path):
+    """Every instantiated network shape of the thread-private kernels on a feature map, and every warps-per-network setting of
+    the J diag(a) J^T kernel (k = 1..3: four warps, k = 4..6: two, k = 7, 8: one)."""
+    dims, k = dims_k
+    feats = [("bond", [1, 4]), ("angle", [4, 6, 8]), ("dihedral", [4, 6, 8, 14]), ("position", [8]), ("dihedral", [6, 8, 14, 16])]
+    B = 333
+    X = ref_torch.synth_frames(BASE, B, seed=21)
+    w = ref_torch.boltzmann_weights(B, seed=22)
+    task, model, nets, eig_w = _feature_task(tmp_path, BASE, feats, None, dims, k, X, w)
+    assert task._ctx.fast_path
+    out = task.loss_func(task._traj, task._weights, None, None)
+    out[0].backward()
+    comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, cf.Preproc(feats=feats), 20.0, eig_w)
+    assert list(out[4].cpu().numpy()) == list(comb["cvec"])
+    assert abs(float(out[0]) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
+    np.testing.assert_allclose(out[1].cpu().numpy(), comb["eig"], rtol=2e-4)
+    for i in range(k):
+        for p, g in zip(model.eigen_funcs[i].parameters(), g64[i]):
+            if np.abs(g).max() < 1e-9 * abs(comb["loss"]):
+                continue
+            assert C.rel_l2(p.grad.cpu().numpy(), g) < 2e-3
+
+
+def test_eigen_feature_path_determinism_and_additivity(tmp_path):
+    """C4 records on 2^18 frames of the 166-atom chain: two runs give bit-identical losses and gradients (every sum of the
+    feature kernels has one owner), and the fp64 batch sums of a batch equal the sum over two unequal parts."""
+    base = ref_torch.chain_structure(166, seed=2026)
+    n = 1 << 18
+    X = ref_torch.synth_frames(base, n, seed=9)
+    w = ref_torch.boltzmann_weights(n, seed=9)
+    task, model, nets, eig_w = _feature_task(tmp_path, base, _c4_records(), list(range(0, 160, 4)), [81, 20, 20, 20, 1], 3, X, w)
+    assert task._ctx.fast_path and task._ctx.spec.alignment_elided
+    outs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        out = task.loss_func(task._traj, task._weights)
+        out[0].backward()
+        outs.append((out[0].clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()))
+    assert torch.isfinite(outs[0][0]) and torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ctx, Xd, wd = task._ctx, task._traj, task._weights
+    _, s_all = ctx.stats(Xd, wd)
+    h = n // 2 + 77
+    _, s1 = ctx.stats(Xd[:h].contiguous(), wd[:h].contiguous())
+    _, s2 = ctx.stats(Xd[h:].contiguous(), wd[h:].contiguous())
+    torch.testing.assert_close(s1 + s2, s_all, rtol=1e-12, atol=0)
+    # a slice against the oracle (which goes through the alignment and its Jacobian)
+    ppo = cf.Preproc(align_idx=list(range(0, 160, 4)), ref=base[list(range(0, 160, 4))], feats=_c4_records())
+    _, _, S = cf.eigen_loss_and_grads(X[:1500], w[:1500], nets, ppo, 20.0, eig_w)
+    _, s_small = ctx.stats(Xd[:1500].contiguous(), wd[:1500].contiguous())
+    np.testing.assert_allclose(s_small.cpu().numpy()[-3:], S["SD"], rtol=1e-4)
+
+
+def test_eigen_lag_loss_on_feature_path(tmp_path):
+    """Transfer-operator branch with a feature map as pre-processing: both forward passes and both backward passes run on the
+    feature kernels (the lagged batch uses the second scratch slot)."""
+    feats = [("bond", [1, 4]), ("dihedral", [4, 6, 8, 14]), ("angle", [6, 8, 14]), ("dihedral", [6, 8, 14, 16]), ("bond", [10, 18])]
+    lag, B, k, dims = 2, 600, 2, [7, 20, 20, 20, 1]
+    X = ref_torch.synth_frames(BASE, B + lag, seed=51)
+    w = ref_torch.boltzmann_weights(B + lag, seed=52)
+    task, model, nets, eig_w = _feature_task(tmp_path, BASE, feats, None, dims, k, X, w, lag_tau=1.0, dt=0.5)
+    assert task.lag_idx == lag and task._ctx.fast_path
+    Xd, wd = task._traj, task._weights
+    out = task.loss_func(Xd[:-lag].contiguous(), wd[:-lag].contiguous(), Xd[lag:].contiguous(), wd[lag:].contiguous())
+    out[0].backward()
+    tn = [[torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in net] for net in nets]
+    Xt, wt = torch.tensor(X, dtype=torch.float64), torch.tensor(w, dtype=torch.float64)
+    ppo = ref_torch.Preprocess(None, ref_torch.FeatureMap(feats)).double()
+    ref = ref_torch.eigen_loss(Xt[:-lag], wt[:-lag], tn, ppo, 20.0, eig_w, X_lagged=Xt[lag:], weight_lagged=wt[lag:], lag_time=1.0)
+    ref[0].backward()
+    assert abs(float(out[0]) - float(ref[0])) <= 2e-5 * abs(float(ref[0]))
+    assert list(out[4].cpu().numpy()) == [int(v) for v in ref[4]]
+    for i in range(k):
+        for p, t in zip(model.eigen_funcs[i].parameters(), tn[i]):
+            g64 = t.grad.numpy()
+            if np.abs(g64).max() < 1e-9 * abs(float(ref[0])):
+                continue
+            assert C.rel_l2(p.grad.cpu().numpy(), g64) < 2e-4
+
+
+def test_eigen_feature_descriptor_too_small_poisons_instead_of_overrunning(tmp_path):
+    """The three sizing fields of cvf_preproc are a contract: with n_shared_atoms understated the table builder refuses the
+    record list and the Dirichlet sums come out NaN -- no out-of-bounds write, no silent wrong answer."""
+    feats = [("bond", [1, 4]), ("bond", [4, 8]), ("bond", [1, 8]), ("dihedral", [4, 6, 8, 14])]
+    X = ref_torch.synth_frames(BASE, 200, seed=3)
+    w = ref_torch.boltzmann_weights(200, seed=3)
+    task, model, nets, eig_w = _feature_task(tmp_path, BASE, feats, None, [5, 20, 20, 20, 1], 1, X, w)
+    assert task._ctx.fast_path and task._ctx.spec.struct.n_shared_atoms == 3
+    good = task.loss_func(task._traj, task._weights)[0]
+    assert torch.isfinite(good)
+    task._ctx.spec.struct.n_shared_atoms = 1
+    task._ctx._ws.clear()
+    bad = task.loss_func(task._traj, task._weights)[0]
+    assert torch.isnan(bad)
+
+
 def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
     """Size-independent property at BASELINE scale (2^20 frames of C3): the fp64 batch sums of a batch equal the sum over
     its halves, and the gradient sums of pass 2 (at fixed coefficients) are additive too."""
