@@ -58,7 +58,7 @@ METRIC = "train-step frames/sec"
 # fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
 KERNEL_FLOPS = {
     ("c3", "fast_pass2a"): 45240, ("c3", "fast_pass1"): 25680, ("c3", "fast_pass2b(dW1)"): 15840,
-    ("c1", "fast_pass2a"): 5080, ("c1", "fast_pass1"): 1760,
+    ("c1", "fast_pass2a"): 5240, ("c1", "fast_pass1"): 1760,
     ("c4", "fast_pass2a"): 48720, ("c4", "fast_pass1"): 29160, ("c4", "fast_pass2b(dW1)"): 19440,
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture of this command under profiles/

@@ -996,8 +996,9 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   float* rows0 = reinterpret_cast<float*>(comb + n_comb + (n_comb & 1));
   float* Zr = rows0 + (size_t)warp * rows_per_warp * RP;   // [NH][2H] A_l | T_l
   float* Xr = Zr + 2 * NH * H * RP;                        // [2H]     s_l | G_l; flush buffer
-  float* Sr = Zr;                                          // [drp]    r staged for layer 1
-  float* Su = Zr + drp * RP;                               // [drp]    u staged for layer 1
+  const bool inline_dw1 = drp == 12;                       // pass2_inline_dw1(): r and vhat keep rows of their own
+  float* Sr = inline_dw1 ? Xr + 2 * H * RP : Zr;           // [drp]    r staged for layer 1
+  float* Su = Sr + drp * RP;                               // [drp]    u staged for layer 1
   float* Sj = Zr + 2 * drp * RP;                           // [12]     alignment-Jacobian vectors staged for layer 1
   for (int n = 0; n < k; ++n)
     for (int i = tid; i < P.img2_floats; i += nt) wsm[n * P.img2_floats + i] = P.img[(size_t)n * P.img_floats + i];
@@ -1110,7 +1111,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       }
       // vhat rows -> global memory (in place of u), 16 bytes per lane, before the Z rows take over the staging area
       __syncwarp();
-      store_rows(Ut, Su, d_r, P.Bp, lane);
+      if (!inline_dw1) store_rows(Ut, Su, d_r, P.Bp, lane);
       float a[H], tg[H];   // A_l, T_l = (1 - A_l^2) zdot_l of the current layer
 #pragma unroll
       for (int j = 0; j < HP; ++j) {
@@ -1248,7 +1249,39 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll
           for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = scale * gl[o];
           __syncwarp();
-          store_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, Xr, 2 * H, P.Bp, lane);
+          if (!inline_dw1) {
+            store_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, Xr, 2 * H, P.Bp, lane);
+          } else {
+            // dW_1 [H][d_r <= 12] here: the same half-warp product as the hidden layers, 12 columns
+            const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
+            float2 acc[TQ][3];
+#pragma unroll
+            for (int j = 0; j < TQ; ++j)
+#pragma unroll
+              for (int i = 0; i < 3; ++i) acc[j][i] = make_float2(0.f, 0.f);
+            outer_tile<TQ, 3>(acc, Xr + og * RP, Sr + ig * RP, Xr + (H + og) * RP, Su + ig * RP, 4 * RP, 4 * RP, 16 * half,
+                              16 * half + 16);
+            float r1[TQ][3];
+#pragma unroll
+            for (int j = 0; j < TQ; ++j)
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                r1[j][i] = acc[j][i].x + acc[j][i].y;
+                r1[j][i] += __shfl_xor_sync(0xffffffffu, r1[j][i], 16);
+              }
+            __syncwarp();   // every lane has finished reading the X rows
+            if (half == 0) {
+#pragma unroll
+              for (int j = 0; j < TQ; ++j)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                  const int col = 4 * i + ig;
+                  if (col < d_r) Xr[(4 * j + og) * d_r + col] = r1[j][i];
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < H * d_r; e += 32) atomicAdd(pn + P.gw_off[0] + e, (double)Xr[e]);
+          }
         }
       }
     }
@@ -1382,9 +1415,12 @@ struct Shape {
 static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int tile_rows) {
   return ((size_t)k * img_floats + geo_floats + (size_t)tile_rows * kP1Frames) * sizeof(float);
 }
+// Pass 2a forms the first layer's weight gradient itself when the input is at most 12 wide (2-d / 3-d model systems): r and
+// vhat then stay in 24 rows of their own behind the X rows, and pass 2b (one 12-column group for 5 of 32 lanes) is not launched.
+static bool pass2_inline_dw1(int drp) { return drp == 12; }
 static int pass2_rows_per_warp(int drp, int H, int NH) {
   const int need = 2 * NH * H + 2 * H, stage = 2 * drp + 12;
-  return need > stage ? need : stage;
+  return (need > stage ? need : stage) + (pass2_inline_dw1(drp) ? 2 * drp : 0);
 }
 static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH, int warps) {
   const int n_comb = 2 * k + k * k;
@@ -1454,6 +1490,7 @@ static size_t jjt_smem_bytes(int k, int d_r, int n_shared, int n_feat, int n_adj
 }
 
 static bool supported_shape(const NetPlan& np, Shape* s) {
+  s->H = s->NH = 0;
   if (np.L < 2) return false;
   const int H = np.dims[1];
   for (int l = 1; l < np.L; ++l)
@@ -1659,6 +1696,7 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   const int n_part = k * np.n_params;
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, nw * n_part, 0, n_part, grad_out));
   CVF_CUDA(cudaGetLastError());
+  if (pass2_inline_dw1(P.d_rp)) return 0;   // pass 2a has formed the first layer's weight gradient itself
   // pass 2b: the first layer's weight gradient
   const int warps_b = dw1_warps(k, P.d_rp, H);
   const size_t smem3 = dw1_smem_bytes(warps_b, P.d_rp, H);
