@@ -53,6 +53,85 @@ def _split(n, test_ratio, draws):
     return tr, te
 
 
+class _GraphedStep:
+    """One training iteration -- loss, backward, optimizer step -- replayed as a CUDA graph.
+
+    The loops of the reference (core.py:498-522, 699-712) run many small steps: at the notebook batch sizes (1 000 - 20 000
+    states) an iteration is about twenty kernel launches worth 0.1 ms of GPU time behind 0.6 - 0.9 ms of Python, autograd and
+    launch overhead.  After WARMUP eager iterations the iteration is captured once -- capture records the launches, it does not
+    run them -- and every later iteration is a device-to-device copy of the mini-batch into static buffers plus one graph
+    launch.  Every iteration, eager or replayed, is a real training step on its own mini-batch, so the sequence of parameter
+    updates is exactly the one of the eager loop.  Any failure to capture falls back to the eager loop.
+
+    ``step_fn(*batch) -> tuple of tensors``: evaluates the loss, calls backward(), returns what the loop logs."""
+
+    WARMUP = 3
+    MIN_STEPS = 200      # capture costs about as much as 50 - 100 eager iterations: shorter runs stay eager
+
+    def __init__(self, task, step_fn, contexts, planned_steps):
+        self.task, self.step_fn, self.contexts = task, step_fn, contexts
+        opt = task.optimizer
+        ok_opt = isinstance(opt, torch.optim.SGD) or (isinstance(opt, torch.optim.Adam) and
+                                                      all(g.get('capturable', False) for g in opt.param_groups))
+        self.enabled = (getattr(task, 'use_cuda_graph', True) and os.environ.get('CVF_CUDA_GRAPH', '1') != '0'
+                        and task._world == 1 and ok_opt and
+                        planned_steps >= int(os.environ.get('CVF_CUDA_GRAPH_MIN_STEPS', self.MIN_STEPS)))
+        self.eager_steps, self.replays = 0, 0
+        self.graph, self.static_in, self.static_out, self._keep = None, None, None, None
+        self.shapes = None
+
+    def _eager(self, batch):
+        self.task.optimizer.zero_grad(set_to_none=True)
+        outs = self.step_fn(*batch)
+        self.task.optimizer.step()
+        self.eager_steps += 1
+        return outs
+
+    def __call__(self, *batch):
+        if not self.enabled or self.eager_steps < self.WARMUP:
+            return self._eager(batch)
+        shapes = tuple(None if t is None else tuple(t.shape) for t in batch)
+        if self.graph is None:
+            try:
+                self.static_in = [None if t is None else t.detach().clone() for t in batch]
+                self.task.optimizer.zero_grad(set_to_none=True)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = self.step_fn(*self.static_in)
+                    self.task.optimizer.step()
+                self.graph, self.static_out, self.shapes = graph, outs, shapes
+                # the graph writes into the scratch buffers that existed at capture: keep them alive even if a context later
+                # grows its scratch for a larger batch
+                self._keep = []
+                for c in self.contexts:
+                    self._keep += [w['buf'] for w in getattr(c, '_ws', {}).values() if w]
+                    if getattr(c, 'workspace', None) is not None:
+                        self._keep.append(c.workspace)
+            except Exception as exc:   # capture is an optimisation: any failure means the eager loop
+                self.enabled, self.graph = False, None
+                if self.task.verbose:
+                    print(f'[Info] CUDA-graph capture of the training step failed ({exc}); continuing with the eager loop', flush=True)
+                torch.cuda.synchronize()
+                return self._eager(batch)
+        elif shapes != self.shapes:
+            return self._eager_after_graph(batch)
+        else:
+            for dst, src in zip(self.static_in, batch):
+                if dst is not None:
+                    dst.copy_(src)
+        self.graph.replay()
+        self.replays += 1
+        return tuple(o.clone() for o in self.static_out)
+
+    def _eager_after_graph(self, batch):
+        # a batch of another size: run it eagerly on gradients of its own (the graph owns the static .grad tensors)
+        saved = [p.grad for g in self.task.optimizer.param_groups for p in g['params']]
+        outs = self._eager(batch)
+        for p, g in zip([p for gr in self.task.optimizer.param_groups for p in gr['params']], saved):
+            p.grad = g
+        return outs
+
+
 class TrainingTask(ABC):
     """Common state of the training tasks (reference core.py:60-249)."""
 
@@ -97,7 +176,8 @@ class TrainingTask(ABC):
             elif self.verbose:
                 print(f'model file not found: {self.load_model_filename}')
         if self.optimizer_name.lower() == 'adam':
-            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.learning_rate)
+            # capturable: the step count lives on the device, so that optimizer.step() can be part of a CUDA graph (_GraphedStep)
+            self.optimizer = torch.optim.Adam(self.model.parameters(), lr=self.learning_rate, capturable=True)
         else:
             self.optimizer = torch.optim.SGD(self.model.parameters(), lr=self.learning_rate)
 
@@ -260,16 +340,21 @@ class EigenFunctionTask(TrainingTask):
             print("Test set:\n\t%d data, %d iterations per epoch, %d iterations in total." %
                   (len(idx_test), n_it_test, n_it_test * self.num_epochs), flush=True)
         loss_names = ['loss', 'eigen_non_penalty', 'eigen_penalty'] + ['eig_%d' % (i + 1) for i in range(self.k)]
+
+        def one_step(X, weight, Xl, wl):
+            loss, eig_vals, non_penalty_loss, penalty, cvec = self.loss_func(X, weight, Xl, wl)
+            loss.backward()
+            return torch.cat([torch.stack([loss.detach(), non_penalty_loss, penalty]), eig_vals]), cvec
+
+        graphed = self._graphed_step = _GraphedStep(self, one_step, [self._ctx], n_it_train * self.num_epochs)
         for epoch in range(self.num_epochs):
             self.model.train()
             train_rows = []
             loss = None
             for X, weight, Xl, wl in self._epoch_batches(X_train, w_train, bs_train, Xl_train, wl_train):
-                self.optimizer.zero_grad(set_to_none=True)
-                loss, eig_vals, non_penalty_loss, penalty, self._cvec = self.loss_func(X, weight, Xl, wl)
-                loss.backward()
-                train_rows.append(torch.cat([torch.stack([loss.detach(), non_penalty_loss, penalty]), eig_vals]))
-                self.optimizer.step()
+                row, self._cvec = graphed(X, weight, Xl, wl)      # zero_grad, loss_func, backward, optimizer.step
+                train_rows.append(row)
+                loss = row[0]
             if self.save_model_every_step > 0 and epoch % self.save_model_every_step == self.save_model_every_step - 1:
                 self.save_model(epoch)
                 if loss is not None and loss < min_loss:
@@ -349,16 +434,19 @@ class AutoEncoderTask(TrainingTask):
                   (len(idx_train), n_it_train, n_it_train * self.num_epochs), flush=True)
             print("Test set:\n\t%d data, %d iterations per epoch, %d iterations in total." %
                   (len(idx_test), n_it_test, n_it_test * self.num_epochs), flush=True)
+        def one_step(X, weight):
+            loss = self.weighted_MSE_loss(X, weight)
+            loss.backward()
+            return (loss.detach(),)
+
+        graphed = self._graphed_step = _GraphedStep(self, one_step, [self._ctx], n_it_train * self.num_epochs)
         for epoch in range(self.num_epochs):
             self.model.train()
             train_loss = []
             loss = None
             for s in range(0, X_train.shape[0] - bs_train + 1, bs_train):
-                self.optimizer.zero_grad(set_to_none=True)
-                loss = self.weighted_MSE_loss(X_train[s:s + bs_train], w_train[s:s + bs_train])
-                loss.backward()
-                train_loss.append(loss.detach())
-                self.optimizer.step()
+                loss, = graphed(X_train[s:s + bs_train], w_train[s:s + bs_train])   # zero_grad, loss, backward, optimizer.step
+                train_loss.append(loss)
             if self.save_model_every_step > 0 and epoch % self.save_model_every_step == self.save_model_every_step - 1:
                 self.save_model(epoch)
                 if loss is not None and loss < min_loss:

@@ -825,3 +825,43 @@ def test_save_model_exports_scripted_collective_variables(tmp_path):
         loss = task.loss_func(task._traj, task._weights, None, None)[0]
         loss.backward()
         assert all(p.grad is not None for p in model.parameters())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["eigen", "eigen_lag", "ae"])
+def test_train_loop_cuda_graph_replays_the_eager_steps(kind, tmp_path, monkeypatch):
+    """train() replays its iteration as a CUDA graph after three eager iterations (core._GraphedStep).  Every iteration is a real
+    step on its own mini-batch, so the per-iteration log and the final parameters must equal those of the eager loop
+    (CVF_CUDA_GRAPH=0) bit for bit -- the kernels are deterministic and the graph launches the same ones."""
+    from colvarsfinder import core, nn
+    n = 2600
+    rng = np.random.default_rng(12)
+    X = np.cumsum(rng.normal(scale=0.2, size=(n, 2)), 0).astype(np.float32)
+    X -= X.mean(0)
+    w = ref_torch.boltzmann_weights(n, seed=13)
+    results = []
+    monkeypatch.setenv("CVF_CUDA_GRAPH_MIN_STEPS", "1")
+    for graph in ("1", "0"):
+        monkeypatch.setenv("CVF_CUDA_GRAPH", graph)
+        torch.manual_seed(5)
+        np.random.seed(6)
+        traj = FakeTrajectory(X.astype(np.float64), w.astype(np.float64), dt=0.1)
+        if kind == "ae":
+            model = nn.AutoEncoder([2, 8, 1], [1, 8, 2])
+            task = core.AutoEncoderTask(traj, torch.nn.Identity(), model, str(tmp_path / graph), learning_rate=0.01, batch_size=250,
+                                        num_epochs=3, test_ratio=0.2, save_model_every_step=0, device=DEV, verbose=False,
+                                        debug_mode=False)
+        else:
+            model = nn.EigenFunctions([2, 20, 20, 20, 1], 2)
+            task = core.EigenFunctionTask(traj, torch.nn.Identity(), model, str(tmp_path / graph), 10.0, [1.0, 0.5],
+                                          lag_tau=0.2 if kind == "eigen_lag" else 0, learning_rate=0.01, k=2, batch_size=250,
+                                          num_epochs=3, test_ratio=0.2, save_model_every_step=0, device=DEV, verbose=False,
+                                          debug_mode=False)
+        task.train()
+        gs = task._graphed_step
+        assert (gs.replays > 0) == (graph == "1") and gs.eager_steps + gs.replays == 3 * (2080 // 250)
+        hist = torch.cat([l[0].reshape(len(l[0]), -1) for l in task.loss_list])
+        results.append((hist, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu(), task.train_loss_df.to_numpy()))
+    assert torch.equal(results[0][0], results[1][0])
+    assert torch.equal(results[0][1], results[1][1])
+    assert np.array_equal(results[0][2], results[1][2])
