@@ -18,6 +18,7 @@ from __future__ import annotations
 import copy
 import itertools
 import os
+import time
 from abc import ABC, abstractmethod
 
 import numpy as np
@@ -66,10 +67,10 @@ class _GraphedStep:
     ``step_fn(*batch) -> tuple of tensors``: evaluates the loss, calls backward(), returns what the loop logs."""
 
     WARMUP = 3
-    MIN_STEPS = 200      # capture costs about as much as 50 - 100 eager iterations: shorter runs stay eager
+    MIN_STEPS = 100      # capture costs 2 - 100 ms, i.e. up to about 100 eager iterations: shorter runs stay eager
 
-    def __init__(self, task, step_fn, contexts, planned_steps):
-        self.task, self.step_fn, self.contexts = task, step_fn, contexts
+    def __init__(self, task, step_fn, contexts, planned_steps, train=True):
+        self.task, self.step_fn, self.contexts, self.train = task, step_fn, contexts, train   # train=False: evaluation only
         opt = task.optimizer
         ok_opt = isinstance(opt, torch.optim.SGD) or (isinstance(opt, torch.optim.Adam) and
                                                       all(g.get('capturable', False) for g in opt.param_groups))
@@ -81,9 +82,11 @@ class _GraphedStep:
         self.shapes = None
 
     def _eager(self, batch):
-        self.task.optimizer.zero_grad(set_to_none=True)
+        if self.train:
+            self.task.optimizer.zero_grad(set_to_none=True)
         outs = self.step_fn(*batch)
-        self.task.optimizer.step()
+        if self.train:
+            self.task.optimizer.step()
         self.eager_steps += 1
         return outs
 
@@ -93,13 +96,26 @@ class _GraphedStep:
         shapes = tuple(None if t is None else tuple(t.shape) for t in batch)
         if self.graph is None:
             try:
+                _t0 = time.perf_counter()
                 self.static_in = [None if t is None else t.detach().clone() for t in batch]
-                self.task.optimizer.zero_grad(set_to_none=True)
+                if self.train:
+                    self.task.optimizer.zero_grad(set_to_none=True)
+                # capture_begin / capture_end on a side stream by hand: torch.cuda.graph() would also empty the allocator's
+                # cache first, which costs up to a second when gigabytes of trajectory temporaries are cached
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    outs = self.step_fn(*self.static_in)
-                    self.task.optimizer.step()
+                cur, side = torch.cuda.current_stream(), torch.cuda.Stream(device=self.task.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    graph.capture_begin()
+                    try:
+                        outs = self.step_fn(*self.static_in)
+                        if self.train:
+                            self.task.optimizer.step()
+                    finally:
+                        graph.capture_end()
+                cur.wait_stream(side)
                 self.graph, self.static_out, self.shapes = graph, outs, shapes
+                self.capture_seconds = time.perf_counter() - _t0
                 # the graph writes into the scratch buffers that existed at capture: keep them alive even if a context later
                 # grows its scratch for a larger batch
                 self._keep = []
@@ -125,6 +141,8 @@ class _GraphedStep:
 
     def _eager_after_graph(self, batch):
         # a batch of another size: run it eagerly on gradients of its own (the graph owns the static .grad tensors)
+        if not self.train:
+            return self._eager(batch)
         saved = [p.grad for g in self.task.optimizer.param_groups for p in g['params']]
         outs = self._eager(batch)
         for p, g in zip([p for gr in self.task.optimizer.param_groups for p in gr['params']], saved):
@@ -346,7 +364,12 @@ class EigenFunctionTask(TrainingTask):
             loss.backward()
             return torch.cat([torch.stack([loss.detach(), non_penalty_loss, penalty]), eig_vals]), cvec
 
+        def one_eval(X, weight, Xl, wl):
+            loss, eig_vals, non_penalty_loss, penalty, _ = self.loss_func(X, weight, Xl, wl)
+            return (torch.cat([torch.stack([loss.detach(), non_penalty_loss, penalty]), eig_vals]),)
+
         graphed = self._graphed_step = _GraphedStep(self, one_step, [self._ctx], n_it_train * self.num_epochs)
+        graphed_test = self._graphed_eval = _GraphedStep(self, one_eval, [self._ctx], n_it_test * self.num_epochs, train=False)
         for epoch in range(self.num_epochs):
             self.model.train()
             train_rows = []
@@ -365,8 +388,7 @@ class EigenFunctionTask(TrainingTask):
                     self.plot_class.plot(self.colvar_model(), epoch=epoch)
             test_rows = []
             for X, weight, Xl, wl in self._epoch_batches(X_test, w_test, bs_test, Xl_test, wl_test):
-                loss_t, eig_vals, non_penalty_loss, penalty, _ = self.loss_func(X, weight, Xl, wl)
-                test_rows.append(torch.cat([torch.stack([loss_t.detach(), non_penalty_loss, penalty]), eig_vals]))
+                test_rows.append(graphed_test(X, weight, Xl, wl)[0])
             # one device->host transfer per epoch for the whole log
             tr = torch.stack(train_rows).cpu() if train_rows else torch.zeros(0, 3 + self.k)
             te = torch.stack(test_rows).cpu() if test_rows else torch.zeros(0, 3 + self.k)
@@ -439,7 +461,11 @@ class AutoEncoderTask(TrainingTask):
             loss.backward()
             return (loss.detach(),)
 
+        def one_eval(X, weight):
+            return (self.weighted_MSE_loss(X, weight).detach(),)
+
         graphed = self._graphed_step = _GraphedStep(self, one_step, [self._ctx], n_it_train * self.num_epochs)
+        graphed_test = self._graphed_eval = _GraphedStep(self, one_eval, [self._ctx], n_it_test * self.num_epochs, train=False)
         for epoch in range(self.num_epochs):
             self.model.train()
             train_loss = []
@@ -457,7 +483,7 @@ class AutoEncoderTask(TrainingTask):
                     self.plot_class.plot(self.colvar_model(), epoch=epoch)
             self.model.eval()
             with torch.no_grad():
-                test_loss = [self.weighted_MSE_loss(X_test[s:s + bs_test], w_test[s:s + bs_test])
+                test_loss = [graphed_test(X_test[s:s + bs_test], w_test[s:s + bs_test])[0]
                              for s in range(0, X_test.shape[0] - bs_test + 1, bs_test)]
             tr = torch.stack(train_loss).cpu() if train_loss else torch.zeros(0)
             te = torch.stack(test_loss).cpu() if test_loss else torch.zeros(0)

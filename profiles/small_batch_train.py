@@ -30,9 +30,12 @@ def run(kind, graph):
     with contextlib.redirect_stdout(io.StringIO()):
         task.train()
     torch.cuda.synchronize(); t1 = time.perf_counter()
+    tr0 = time.perf_counter()
     steps = task._graphed_step.eager_steps + task._graphed_step.replays
     print(kind, "graph" if graph == "1" else "eager", "train() %.3f s" % (t1 - t0), steps, "steps", "%.0f us/step incl. test loop" % ((t1 - t0) / steps * 1e6),
-          "replays", task._graphed_step.replays, "final loss", float(task.train_loss_df["loss"].iloc[-1]), flush=True)
+          "replays", task._graphed_step.replays, "capture s", round(getattr(task._graphed_step, "capture_seconds", 0.0), 3), round(getattr(task._graphed_eval, "capture_seconds", 0.0), 3), "final loss", float(task.train_loss_df["loss"].iloc[-1]), flush=True)
+import gc
 for kind in ("c1", "c3"):
-    for graph in ("0", "0", "1", "1"):     # the first run of a kind also pays one-time costs (module loading, allocator growth)
+    for graph in ("0", "0", "1", "1", "1"):     # the first run of a kind also pays one-time costs (module loading, allocator growth)
         run(kind, graph)
+        t0 = time.perf_counter(); gc.collect(); torch.cuda.synchronize(); print("   teardown s", round(time.perf_counter() - t0, 3), flush=True)
