@@ -16,7 +16,7 @@ namespace cvf {
 
 struct AePlan {
   NetPlan net;
-  int F, FS, FB, nthreads;
+  int F, FS, FB, nthreads, ctas_per_sm;
   int a_row[kMaxLayers + 1];   // activations A_0 (input) .. A_L (output)
   int s_row[kMaxLayers + 1];   // adjoints of z_l, l = 1..L
   int row_w, row_err;
@@ -213,7 +213,8 @@ static int ae_plan(const cvf_mlp* net, AePlan* P) {
   }
   const size_t cap = (size_t)max_smem_optin();
   static const int Fs[3] = {128, 64, 32};
-  for (int c = 0; c < 3; ++c) {
+  int c = 0;
+  for (; c < 3; ++c) {
     if (ae_layout(P, Fs[c]) <= cap) break;
     if (c == 2) {
       set_error("autoencoder state does not fit shared memory (%zu B at 32 frames, %zu available)", P->smem_bytes, cap);
@@ -221,6 +222,15 @@ static int ae_plan(const cvf_mlp* net, AePlan* P) {
     }
   }
   P->nthreads = 384;
+  P->ctas_per_sm = 1;
+  // Two CTAs of half the frames and half the threads per SM instead of one: the phases of the row engine end in CTA-wide
+  // barriers, and a second, independent CTA fills the issue slots the first one leaves while it waits at them.
+  if (c < 2 && 2 * (ae_layout(P, Fs[c + 1]) + 1024) <= (size_t)228 * 1024) {
+    P->nthreads = 192;
+    P->ctas_per_sm = 2;
+  } else {
+    ae_layout(P, Fs[c]);
+  }
   return 0;
 }
 
@@ -243,7 +253,7 @@ extern "C" size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B) {
   const int path = ae_path(net, &P);
   if (path < 0 || B < 1) return 0;
   if (path == 0) return wide_ae_workspace_bytes(P.net, B);
-  return (size_t)(2 + P.net.n_params) * sizeof(double) * (size_t)sm_count();
+  return (size_t)(2 + P.net.n_params) * sizeof(double) * (size_t)sm_count() * 2;
 }
 
 extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
@@ -260,7 +270,7 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
   const bool grad = grad_out != nullptr;
   const int n_part = 2 + (grad ? P.net.n_params : 0);
   const long long n_tiles = (B + P.F - 1) / P.F;
-  int grid = sm_count();
+  int grid = sm_count() * P.ctas_per_sm;
   if (n_tiles < grid) grid = (int)n_tiles;
   if ((size_t)grid * n_part * sizeof(double) > workspace_bytes) {
     set_error("workspace too small: %zu < %zu", workspace_bytes, (size_t)grid * n_part * sizeof(double));
