@@ -494,8 +494,7 @@ __global__ void __launch_bounds__(512) prep_feat_kernel(const FastPlan P, const 
 //            goes to the network's per-atom gradient rows;
 //   phase 2, record-major (a warp takes every W-th record): vhat_f = m u_f + sum over the record's atoms of stencil . (a g),
 //            written in place of u_f.
-// Every sum has one owner and a fixed order: the result is deterministic.  The pair streams are read through a one-ahead
-// register pipeline.  vhat replaces u in P.U.
+// Every sum has one owner and a fixed order: the result is deterministic.  vhat replaces u in P.U.
 struct JjtLoad {
   cvf_v3 s0, s1;
   float p, q;
@@ -590,21 +589,19 @@ __global__ void __launch_bounds__(384, 2) jjt_kernel(const FastPlan P, int W) {
     // phase 1: per-atom gradients
     float D = 0.0f;
     for (int c = q; c < nc; c += W) {
-      int e = s_start[c];
       const int e_end = s_start[c + 1];
-      int4 enA = s_adj[e];
-      JjtLoad LA;
-      jjt_issue(LA, enA, STl);
-      float uA = *reinterpret_cast<const float*>(Sul + enA.y);
       cvf_v3 g = v3(0.f, 0.f, 0.f);
-      for (; e < e_end; ++e) {
-        const int4 enB = s_adj[e + 1 < n_adj ? e + 1 : n_adj - 1];
-        JjtLoad LB;
-        jjt_issue(LB, enB, STl);
-        const float uB = *reinterpret_cast<const float*>(Sul + enB.y);
-        if (enA.x == 1) g = g + (__int_as_float(enA.w) * uA) * LA.s0;
-        else g = g + uA * jjt_combine(LA, enA.x);
-        LA = LB, enA = enB, uA = uB;
+      for (int e = s_start[c]; e < e_end; ++e) {
+        const int4 en = s_adj[e];
+        const float u = *reinterpret_cast<const float*>(Sul + en.y);
+        if (en.x == 1) {
+          const float* sp = reinterpret_cast<const float*>(STl + en.z);
+          g = g + (__int_as_float(en.w) * u) * v3(sp[0], sp[32], sp[64]);
+        } else {
+          JjtLoad L;
+          jjt_issue(L, en, STl);
+          g = g + u * jjt_combine(L, en.x);
+        }
       }
       const cvf_v3 dg = v3(s_dg[3 * c], s_dg[3 * c + 1], s_dg[3 * c + 2]);
       D = fmaf(dg.x * g.x, g.x, fmaf(dg.y * g.y, g.y, fmaf(dg.z * g.z, g.z, D)));
@@ -633,12 +630,16 @@ __global__ void __launch_bounds__(384, 2) jjt_kernel(const FastPlan P, int W) {
       }
       for (; e < e_end; ++e) {
         const int4 en = s_radj[e];
-        JjtLoad L;
-        jjt_issue(L, en, STl);
         const float* gp = reinterpret_cast<const float*>(Sgl + en.y);
         const cvf_v3 gv = v3(gp[0], gp[32], gp[64]);
-        if (en.x == 1) v = fmaf(__int_as_float(en.w), dot(L.s0, gv), v);
-        else v += dot(jjt_combine(L, en.x), gv);
+        if (en.x == 1) {
+          const float* sp = reinterpret_cast<const float*>(STl + en.z);
+          v = fmaf(__int_as_float(en.w), dot(v3(sp[0], sp[32], sp[64]), gv), v);
+        } else {
+          JjtLoad L;
+          jjt_issue(L, en, STl);
+          v += dot(jjt_combine(L, en.x), gv);
+        }
       }
       if (fi.x == CVF_FEAT_DIHEDRAL) {
         const float* sp = reinterpret_cast<const float*>(STl + fi.z);
