@@ -9,6 +9,7 @@ import bench_data as bd
 dev = torch.device("cuda", 0)
 def run(kind, graph):
     os.environ["CVF_CUDA_GRAPH"] = graph
+    os.environ["CVF_CUDA_GRAPH_MIN_STEPS"] = "1"
     torch.manual_seed(0); np.random.seed(0)
     if kind == "c1":
         n, bs = 100000, 1000
