@@ -64,10 +64,10 @@ KERNEL_FLOPS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture of this command under profiles/
 # (r01_ncu_c3_summary.txt); keyed by (workload, kernel, frames per launch) and not extrapolated to other sizes
 KERNEL_TRAFFIC = {
-    ("c3", "fast_pass2a", 1 << 22): 7.090671e9 + 7.656838e9,
-    ("c3", "fast_pass1", 1 << 22): 1.309395e9 + 4.320238e9,
-    ("c3", "fast_pass2b(dW1)", 1 << 22): 7.168490e9 + 0.552433e9,
-    ("c3", "fast_prep", 1 << 22): 1.115100e9 + 1.265860e9,
+    ("c3", "fast_pass2a", 1 << 22): 7.082898e9 + 7.657857e9,
+    ("c3", "fast_pass1", 1 << 22): 1.309537e9 + 4.322941e9,
+    ("c3", "fast_pass2b(dW1)", 1 << 22): 7.147142e9 + 0.550824e9,
+    ("c3", "fast_prep", 1 << 22): 1.115355e9 + 1.264251e9,
 }
 
 
@@ -368,7 +368,8 @@ def main():
     entry.build()
     from colvarsfinder import _lib
 
-    sampler = ClockSampler(local).start() if rank == 0 else None   # started early: nvidia-smi takes a while to deliver its first row
+    # started early: nvidia-smi takes a while to deliver its first row (CVF_BENCH_CLOCKS=0 switches the sampling off)
+    sampler = ClockSampler(local).start() if rank == 0 and os.environ.get("CVF_BENCH_CLOCKS", "1") != "0" else None
     step, X, w, task = build_workload(args.workload, args.frames, dev, seed=2026 + rank)
     W = max(args.warmup, 3)
     K = args.steps
