@@ -23,6 +23,7 @@ Weak scaling: every rank keeps `--frames` frames (default 2^22, 1.1 GB > L2) res
 from __future__ import annotations
 
 import argparse
+import gc
 import ctypes as C
 import json
 import os
@@ -386,12 +387,17 @@ def main():
     _lib.profile_read(reset=True)      # launch counters to zero: the timed region is counted exactly
     if sampler:
         sampler.mark()
+    # the launch queue is empty at this point: a pause of the host (a full garbage collection takes tens of milliseconds in a
+    # process with torch loaded) would leave the GPU idle for as long, so collect now and keep the collector off while timing
+    gc.collect()
+    gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
         loss = step(X, w)
     e1.record()
     barrier()
+    gc.enable()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -440,11 +446,14 @@ def main():
 
     e2e_loop(2)
     barrier()
+    gc.collect()
+    gc.disable()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     e2e_loop(K)
     t1.record()
     barrier()
+    gc.enable()
     ms_e2e = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(ms_e2e, op=torch.distributed.ReduceOp.MAX)
