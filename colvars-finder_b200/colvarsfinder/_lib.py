@@ -53,6 +53,7 @@ SYMBOLS = {
     "cvf_ae_workspace_bytes": (_SZ, [C.POINTER(Mlp), _I64]),
     "cvf_ae_step": (C.c_int, [_P, _P, _I64, C.POINTER(Mlp), _P, _P, _P, _P, _SZ, _P]),
     "cvf_ae_set_wide_path": (C.c_int, [_I32]),
+    "cvf_ae_set_fast_path": (C.c_int, [_I32]),
     "cvf_fma_probe": (C.c_int, [_P, _I32, C.POINTER(_D), _P]),
     "cvf_profile_enable": (C.c_int, [_I32]),
     "cvf_profile_num_kernels": (_I32, []),

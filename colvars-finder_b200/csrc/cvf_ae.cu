@@ -14,6 +14,13 @@
 
 namespace cvf {
 
+// cvf_ae_fast.cu: thread-private kernels for the notebook-sized chain  [d,20,20,20,2] + [2,10,10,d]
+bool fast_ae_supported(const NetPlan& np);
+size_t fast_ae_workspace_bytes(const NetPlan& np, long long B);
+int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long B, const float* params, double* sums_out,
+                 double* grad_out, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int fast_ae_set_mode(int mode);
+
 struct AePlan {
   NetPlan net;
   int F, FS, FB, nthreads, ctas_per_sm;
@@ -253,7 +260,12 @@ extern "C" size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B) {
   const int path = ae_path(net, &P);
   if (path < 0 || B < 1) return 0;
   if (path == 0) return wide_ae_workspace_bytes(P.net, B);
-  return (size_t)(2 + P.net.n_params) * sizeof(double) * (size_t)sm_count() * 2;
+  const size_t general = (size_t)(2 + P.net.n_params) * sizeof(double) * (size_t)sm_count() * 2;
+  if (fast_ae_supported(P.net)) {
+    const size_t fast = fast_ae_workspace_bytes(P.net, B);
+    return fast > general ? fast : general;
+  }
+  return general;
 }
 
 extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
@@ -267,6 +279,7 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
     return CVF_E_ARG;
   }
   if (path == 0) return wide_ae_step(P.net, feat, w, B, params, sums_out, grad_out, workspace, workspace_bytes, stream);
+  if (fast_ae_supported(P.net)) return fast_ae_step(P.net, feat, w, B, params, sums_out, grad_out, workspace, workspace_bytes, stream);
   const bool grad = grad_out != nullptr;
   const int n_part = 2 + (grad ? P.net.n_params : 0);
   const long long n_tiles = (B + P.F - 1) / P.F;
@@ -296,6 +309,14 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
 extern "C" int cvf_ae_set_wide_path(int32_t mode) {
   if (wide_ae_set_mode(mode)) {
     set_error("cvf_ae_set_wide_path: mode must be 0 (tensor cores) or 1 (fp32 SIMT)");
+    return CVF_E_ARG;
+  }
+  return 0;
+}
+
+extern "C" int cvf_ae_set_fast_path(int32_t mode) {
+  if (cvf::fast_ae_set_mode(mode)) {
+    cvf::set_error("cvf_ae_set_fast_path: mode must be 0 (auto) or 1 (general kernels)");
     return CVF_E_ARG;
   }
   return 0;

@@ -717,6 +717,41 @@ def test_ae_loss_matches_oracle_ragged_sizes(B, tmp_path):
         assert C.rel_l2(g, go) < 2e-5
 
 
+@pytest.mark.parametrize("d", [30, 66, 71])
+@pytest.mark.parametrize("B", [3, 700, 20000])
+def test_ae_fast_and_general_kernels_match_oracle(B, d, tmp_path):
+    """The notebook-sized chain [d,20,20,20,2] + [2,10,10,d] (examples/dipeptide/main.ipynb:434 uses d = 30) on the thread-private
+    kernels (cvf_ae_fast.cu) and, with cvf_ae_set_fast_path(1), on the general row-engine kernel: both against the fp64 oracle,
+    and against each other."""
+    from colvarsfinder import _lib, core, nn
+    rng = np.random.default_rng(B + d)
+    torch.manual_seed(B + d)
+    e_dims, d_dims = [d, 20, 20, 20, 2], [2, 10, 10, d]
+    enc = [p.numpy() for p in ref_torch.init_mlp_params(e_dims)]
+    dec = [p.numpy() for p in ref_torch.init_mlp_params(d_dims)]
+    F = rng.normal(scale=1.5, size=(B, d)).astype(np.float32)
+    w = ref_torch.boltzmann_weights(B, seed=B)
+    lo, genc, gdec = cf.ae_loss_and_grads(F, w, enc, dec)
+    res = {}
+    for mode in (0, 1):
+        _lib.check(_lib.lib().cvf_ae_set_fast_path(mode), "cvf_ae_set_fast_path")
+        try:
+            task, model = _ae_task(dict(e_dims=e_dims, d_dims=d_dims, enc=enc, dec=dec, F=F, w=w), tmp_path)
+            loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+            loss.backward()
+            with torch.no_grad():
+                l_eval = task.weighted_MSE_loss(task._feature_traj, task._weights)
+        finally:
+            _lib.lib().cvf_ae_set_fast_path(0)
+        assert torch.equal(l_eval, loss.detach())
+        assert abs(float(loss) - lo) <= 1e-5 * abs(lo), (mode, float(loss), lo)
+        got = [p.grad.cpu().numpy() for p in model.encoder.parameters()] + [p.grad.cpu().numpy() for p in model.decoder.parameters()]
+        for i, (g, go) in enumerate(zip(got, genc + gdec)):
+            assert C.rel_l2(g, go) < 2e-5, (mode, i, C.rel_l2(g, go))
+        res[mode] = float(loss)
+    assert abs(res[0] - res[1]) <= 2e-6 * abs(res[1])
+
+
 @pytest.mark.parametrize("mode", ["tensor_cores", "simt"])
 @pytest.mark.parametrize("B", [130, 1000, 33000])
 def test_ae_wide_layers_match_oracle(B, mode, tmp_path):
