@@ -61,6 +61,7 @@ KERNEL_FLOPS = {
     ("c3", "fast_pass2a"): 45240, ("c3", "fast_pass1"): 25680, ("c3", "fast_pass2b(dW1)"): 15840,
     ("c1", "fast_pass2a"): 5240, ("c1", "fast_pass1"): 1760,
     ("c4", "fast_pass2a"): 48720, ("c4", "fast_pass1"): 29160, ("c4", "fast_pass2b(dW1)"): 19440,
+    ("c2", "ae_fast_main"): 9120, ("c2", "ae_fast_dw"): 6176,   # forward P + delta sweep (P - first layer); weight + bias products
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture of this command under profiles/
 # (r01_ncu_c3_summary.txt); keyed by (workload, kernel, frames per launch) and not extrapolated to other sizes

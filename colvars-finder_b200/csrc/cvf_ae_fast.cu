@@ -140,10 +140,22 @@ __global__ void __launch_bounds__(128) prep_kernel(const Plan P, const float* __
   const long long n_tiles = P.Bp / 128;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long f0 = tile * 128;
-    for (int i = tid; i < 128 * d; i += 128) {
-      const int f = i / d, j = i - f * d;
-      const long long fr = min(f0 + f, P.B - 1);
-      st[f * S + j] = __ldg(feat + (size_t)fr * d + j);
+    if (f0 + 128 <= P.B) {
+      // contiguous tile: element i = tid + 128 m belongs to frame i / d; (frame, feature) advance incrementally
+      const float* src = feat + (size_t)f0 * d;
+      const int df = 128 / d, dj = 128 - df * d;
+      int f = tid / d, j = tid - f * d;
+      for (int i = tid; i < 128 * d; i += 128) {
+        st[f * S + j] = __ldg(src + i);
+        f += df, j += dj;
+        if (j >= d) j -= d, ++f;
+      }
+    } else {
+      for (int i = tid; i < 128 * d; i += 128) {
+        const int f = i / d, j = i - f * d;
+        const long long fr = min(f0 + f, P.B - 1);
+        st[f * S + j] = __ldg(feat + (size_t)fr * d + j);
+      }
     }
     __syncthreads();
     for (int r = 0; r < d; ++r) P.R[(size_t)r * P.Bp + f0 + tid] = st[tid * S + r];
@@ -637,7 +649,7 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
     set_error("workspace too small for the autoencoder fast path: %zu < %zu", ws_bytes, need);
     return CVF_E_WORKSPACE;
   }
-  CVF_LAUNCH(K_AE_STEP, stream, (pack_kernel<20, 2, 10><<<7, 256, 0, stream>>>(P, params)));
+  CVF_LAUNCH(K_FAST_PACK, stream, (pack_kernel<20, 2, 10><<<7, 256, 0, stream>>>(P, params)));
   CVF_CUDA(cudaGetLastError());
   {
     const size_t smem = (size_t)128 * (P.d | 1) * sizeof(float);
@@ -646,7 +658,7 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
     per_sm = per_sm < 1 ? 1 : per_sm > 8 ? 8 : per_sm;
     long long grid = (long long)sm_count() * per_sm;
     if (P.Bp / 128 < grid) grid = P.Bp / 128;
-    CVF_LAUNCH(K_AE_STEP, stream, prep_kernel<<<(int)grid, 128, smem, stream>>>(P, feat));
+    CVF_LAUNCH(K_AE_FAST_PREP, stream, prep_kernel<<<(int)grid, 128, smem, stream>>>(P, feat));
     CVF_CUDA(cudaGetLastError());
   }
   int grid_main = sm_count();
@@ -654,7 +666,7 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
     const size_t smem = main_smem(P.img_floats, P.d);
     CVF_CUDA(cudaFuncSetAttribute(main_kernel<20, 2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (P.Bp / kTile < grid_main) grid_main = (int)(P.Bp / kTile);
-    CVF_LAUNCH(K_AE_STEP, stream, (main_kernel<20, 2, 10><<<grid_main, kThreads, smem, stream>>>(P, w, grad_out ? 1 : 0)));
+    CVF_LAUNCH(K_AE_FAST_MAIN, stream, (main_kernel<20, 2, 10><<<grid_main, kThreads, smem, stream>>>(P, w, grad_out ? 1 : 0)));
     CVF_CUDA(cudaGetLastError());
   }
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<1, 32, 0, stream>>>(P.part_loss, grid_main, 2, 0, 2, sums_out));
@@ -666,7 +678,7 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   const long long n_items = (P.Bp / 32 + kRun - 1) / kRun * P.n_types;
   long long grid = sm_count();
   if ((n_items + pairs - 1) / pairs < grid) grid = (n_items + pairs - 1) / pairs;
-  CVF_LAUNCH(K_AE_STEP, stream, dw_kernel<<<(int)grid, 64 * pairs, smem, stream>>>(P));
+  CVF_LAUNCH(K_AE_FAST_DW, stream, dw_kernel<<<(int)grid, 64 * pairs, smem, stream>>>(P));
   CVF_CUDA(cudaGetLastError());
   CVF_LAUNCH(K_REDUCE, stream,
              reduce_partials_kernel<<<(P.n_params + 127) / 128, 128, 0, stream>>>(P.part_dw, (int)grid, 2 * pairs * P.n_params, 0,
