@@ -3,7 +3,7 @@
 // eigenfunction fast path (cvf_eigen_fast.cu) around what the SM sustains:
 //
 //   prep   : the caller's [B][d] features -> frame-minor rows R[0..d) (row = feature, column = frame)
-//   main   : forward through the seven layers and the reverse sweep of the deltas, THREAD-PRIVATELY (two frames per
+//   main   : forward through the seven layers and the reverse sweep of the deltas, THREAD-PRIVATELY (two CTAs per SM, two frames per
 //            thread so that every weight fetched from shared memory feeds two FFMA2, activations in registers, no barrier
 //            between layers); the activations a_1..a_6 and the deltas delta_1..delta_7 go to frame-minor rows of R, the
 //            weighted squared error to fp64 partial sums
@@ -22,8 +22,8 @@ namespace aefast {
 typedef unsigned long long u64;
 constexpr int kRP = 36;        // floats per 32-frame operand row in shared memory (16-byte aligned, bank skew 4 per row)
 constexpr int kRun = 16;       // tiles of 32 frames per work item of the dw kernel
-constexpr int kTile = 512;     // frames per tile of the main kernel
-constexpr int kThreads = 256;
+constexpr int kTile = 256;     // frames per tile of the main kernel: two CTAs per SM, so that one computes while the other
+constexpr int kThreads = 128;  // waits for its (single-buffered) tile
 constexpr int kMaxTypes = 4;
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -215,7 +215,7 @@ __device__ __forceinline__ void unpack2(float (&a)[2][N], const float2 (&z)[2][N
 }
 
 template <int E, int EC, int G>
-__global__ void __launch_bounds__(kThreads, 1) main_kernel(const Plan P, const float* __restrict__ w, int grad) {
+__global__ void __launch_bounds__(kThreads, 2) main_kernel(const Plan P, const float* __restrict__ w, int grad) {
   extern __shared__ __align__(16) float sm[];
   __shared__ double red[2][kThreads / 32];
   typedef Img<E, EC, G> I;
@@ -235,6 +235,15 @@ __global__ void __launch_bounds__(kThreads, 1) main_kernel(const Plan P, const f
       st4(tile + r * F + 4 * c4, __ldg(reinterpret_cast<const float4*>(P.R + (size_t)r * P.Bp + f0) + c4));
     }
     __syncthreads();
+    {
+      // pull the next tile into L2 while this one is worked on
+      const long long tn = t + gridDim.x;
+      if (tn < n_tiles)
+        for (int i = tid; i < d * (F / 32); i += kThreads) {
+          const int r = i / (F / 32), c = i - r * (F / 32);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(P.R + (size_t)r * P.Bp + tn * F + 32 * c));
+        }
+    }
     float wf[2];
     wf[0] = col < P.B ? __ldg(w + col) : 0.0f;
     wf[1] = col + 1 < P.B ? __ldg(w + col + 1) : 0.0f;
@@ -604,7 +613,7 @@ static size_t make_plan(Plan* P, const NetPlan& np, long long B, void* workspace
     off += (bytes + 255) & ~(size_t)255;
     return p;
   };
-  P->part_loss = (double*)take((size_t)sm_count() * 2 * sizeof(double));
+  P->part_loss = (double*)take((size_t)sm_count() * 2 * 2 * sizeof(double));
   P->part_dw = (double*)take((size_t)sm_count() * 8 * P->n_params * sizeof(double));
   P->img = (float*)take((size_t)P->img_floats * sizeof(float));
   P->R = (float*)take((size_t)P->n_rows * P->Bp * sizeof(float));
@@ -661,7 +670,7 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
     CVF_LAUNCH(K_AE_FAST_PREP, stream, prep_kernel<<<(int)grid, 128, smem, stream>>>(P, feat));
     CVF_CUDA(cudaGetLastError());
   }
-  int grid_main = sm_count();
+  int grid_main = 2 * sm_count();
   {
     const size_t smem = main_smem(P.img_floats, P.d);
     CVF_CUDA(cudaFuncSetAttribute(main_kernel<20, 2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
