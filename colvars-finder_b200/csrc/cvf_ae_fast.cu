@@ -1,5 +1,5 @@
 // cvf_ae_fast.cu -- AutoEncoderTask.weighted_MSE_loss + backward (reference core.py:652-666, 708) for the notebook-sized
-// autoencoder  encoder [d, E, E, E, e] / decoder [e, G, G, d]  (examples/dipeptide/main.ipynb:434), organised like the
+// autoencoder  encoder [d, 20, 20, 20, e] / decoder [e, 10, 10, d], e = 1, 2, 3  (examples/dipeptide/main.ipynb:434), organised like the
 // eigenfunction fast path (cvf_eigen_fast.cu) around what the SM sustains:
 //
 //   prep   : the caller's [B][d] features -> frame-minor rows R[0..d) (row = feature, column = frame)
@@ -558,7 +558,7 @@ static bool shape_ok(const NetPlan& np, int* E, int* EC, int* G) {
     if (np.act[l] != want_act[l]) return false;
   if (dm[0] != dm[7] || dm[1] != dm[2] || dm[2] != dm[3] || dm[5] != dm[6]) return false;
   *E = dm[1], *EC = dm[4], *G = dm[5];
-  return *E == 20 && *EC == 2 && *G == 10 && dm[0] >= 1 && dm[0] <= 72;
+  return *E == 20 && *EC >= 1 && *EC <= 3 && *G == 10 && dm[0] >= 1 && dm[0] <= 72;   // the instantiated shapes
 }
 
 static size_t main_smem(int img_floats, int d) { return ((size_t)img_floats + (size_t)d * kTile) * sizeof(float); }
@@ -575,7 +575,11 @@ static size_t make_plan(Plan* P, const NetPlan& np, long long B, void* workspace
   P->n_rows = row;
   for (int l = 0; l < np.L; ++l) P->gw_off[l] = np.gw_off[l], P->gb_off[l] = np.gb_off[l];
   P->n_params = np.n_params;
-  P->img_floats = Img<20, 2, 10>::floats(P->d, P->drp);
+  {
+    const int ec = np.dims[4];
+    P->img_floats = ec == 1 ? Img<20, 1, 10>::floats(P->d, P->drp) : ec == 2 ? Img<20, 2, 10>::floats(P->d, P->drp)
+                                                                           : Img<20, 3, 10>::floats(P->d, P->drp);
+  }
   // pack the layers into types: largest first, first type with room
   int order[kMaxLayers], lanes[kMaxLayers + 1];
   for (int l = 1; l <= np.L; ++l) lanes[l] = ((np.dims[l] + 3) / 4) * ((np.dims[l - 1] + 11) / 12), order[l - 1] = l;
@@ -658,7 +662,14 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
     set_error("workspace too small for the autoencoder fast path: %zu < %zu", ws_bytes, need);
     return CVF_E_WORKSPACE;
   }
-  CVF_LAUNCH(K_FAST_PACK, stream, (pack_kernel<20, 2, 10><<<7, 256, 0, stream>>>(P, params)));
+  const int ec = np.dims[4];
+#define CVF_AE_FAST_SHAPE(CALL) \
+  do {                          \
+    if (ec == 1) { CALL(20, 1, 10); } else if (ec == 2) { CALL(20, 2, 10); } else { CALL(20, 3, 10); } \
+  } while (0)
+#define CVF_AE_PACK(E_, EC_, G_) CVF_LAUNCH(K_FAST_PACK, stream, (pack_kernel<E_, EC_, G_><<<7, 256, 0, stream>>>(P, params)))
+  CVF_AE_FAST_SHAPE(CVF_AE_PACK);
+#undef CVF_AE_PACK
   CVF_CUDA(cudaGetLastError());
   {
     const size_t smem = (size_t)128 * (P.d | 1) * sizeof(float);
@@ -673,9 +684,15 @@ int fast_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   int grid_main = 2 * sm_count();
   {
     const size_t smem = main_smem(P.img_floats, P.d);
-    CVF_CUDA(cudaFuncSetAttribute(main_kernel<20, 2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (P.Bp / kTile < grid_main) grid_main = (int)(P.Bp / kTile);
-    CVF_LAUNCH(K_AE_FAST_MAIN, stream, (main_kernel<20, 2, 10><<<grid_main, kThreads, smem, stream>>>(P, w, grad_out ? 1 : 0)));
+#define CVF_AE_MAIN(E_, EC_, G_)                                                                                                  \
+  do {                                                                                                                            \
+    CVF_CUDA(cudaFuncSetAttribute(main_kernel<E_, EC_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    CVF_LAUNCH(K_AE_FAST_MAIN, stream, (main_kernel<E_, EC_, G_><<<grid_main, kThreads, smem, stream>>>(P, w, grad_out ? 1 : 0))); \
+  } while (0)
+    CVF_AE_FAST_SHAPE(CVF_AE_MAIN);
+#undef CVF_AE_MAIN
+#undef CVF_AE_FAST_SHAPE
     CVF_CUDA(cudaGetLastError());
   }
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<1, 32, 0, stream>>>(P.part_loss, grid_main, 2, 0, 2, sums_out));

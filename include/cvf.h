@@ -154,7 +154,7 @@ int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net
                 double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* testing / profiling switch for chains that fit shared memory: 0 = the thread-private kernels (cvf_ae_fast.cu) when the chain
- * is encoder [d,20,20,20,2] + decoder [2,10,10,d], d <= 72 (default); 1 = always the general row-engine kernel */
+ * is encoder [d,20,20,20,e] + decoder [e,10,10,d], e = 1..3, d <= 72 (default); 1 = always the general row-engine kernel */
 int cvf_ae_set_fast_path(int32_t mode);
 
 /* Products of the layer-wise autoencoder path: 0 = tcgen05 tensor cores, fp32 operands split into two TF32 terms and three

@@ -717,16 +717,16 @@ def test_ae_loss_matches_oracle_ragged_sizes(B, tmp_path):
         assert C.rel_l2(g, go) < 2e-5
 
 
-@pytest.mark.parametrize("d", [30, 66, 71])
+@pytest.mark.parametrize("d,e", [(30, 2), (66, 2), (71, 2), (30, 1), (66, 3)])
 @pytest.mark.parametrize("B", [3, 700, 20000])
-def test_ae_fast_and_general_kernels_match_oracle(B, d, tmp_path):
-    """The notebook-sized chain [d,20,20,20,2] + [2,10,10,d] (examples/dipeptide/main.ipynb:434 uses d = 30) on the thread-private
+def test_ae_fast_and_general_kernels_match_oracle(B, d, e, tmp_path):
+    """The notebook-sized chain [d,20,20,20,e] + [e,10,10,d] (examples/dipeptide/main.ipynb:434 uses d = 30, e = 2) on the thread-private
     kernels (cvf_ae_fast.cu) and, with cvf_ae_set_fast_path(1), on the general row-engine kernel: both against the fp64 oracle,
     and against each other."""
     from colvarsfinder import _lib, core, nn
     rng = np.random.default_rng(B + d)
     torch.manual_seed(B + d)
-    e_dims, d_dims = [d, 20, 20, 20, 2], [2, 10, 10, d]
+    e_dims, d_dims = [d, 20, 20, 20, e], [e, 10, 10, d]
     enc = [p.numpy() for p in ref_torch.init_mlp_params(e_dims)]
     dec = [p.numpy() for p in ref_torch.init_mlp_params(d_dims)]
     F = rng.normal(scale=1.5, size=(B, d)).astype(np.float32)
@@ -737,7 +737,10 @@ def test_ae_fast_and_general_kernels_match_oracle(B, d, tmp_path):
         _lib.check(_lib.lib().cvf_ae_set_fast_path(mode), "cvf_ae_set_fast_path")
         try:
             task, model = _ae_task(dict(e_dims=e_dims, d_dims=d_dims, enc=enc, dec=dec, F=F, w=w), tmp_path)
+            _lib.profile_read(reset=True)
             loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+            launched = _lib.profile_read(reset=True)
+            assert (launched["ae_fast_main"][2] > 0) == (mode == 0) and (launched["ae_step"][2] > 0) == (mode == 1)
             loss.backward()
             with torch.no_grad():
                 l_eval = task.weighted_MSE_loss(task._feature_traj, task._weights)
