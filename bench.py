@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import argparse
 import gc
+import signal
 import ctypes as C
 import json
 import os
@@ -80,15 +81,18 @@ class ClockSampler:
     inside the bracket count.  If the region was too short for one, the samples of the warm-up steps (same load) are used and
     the result says so."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # SM clock and the throttle-reason BITMASK only: every extra field is another driver query, and a query can hold up kernel
+    # dispatch for milliseconds (visible on steps made of a hundred launches).  Bits: 0x4 sw_power_cap, 0x8 hw_slowdown,
+    # 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown (nvml.h nvmlClocksEventReason*).
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.t_mark = index, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -101,12 +105,28 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def mark(self):
+        """Start of the timed region.  The sampler is paused until `resume()`: an NVML query can hold up this process's kernel
+        launches for milliseconds, which is invisible once the launch queue is a step deep but not while it is being filled
+        from empty right after the barrier."""
         self.t_mark = time.perf_counter()
+        if self.proc is not None:
+            try:
+                self.proc.send_signal(signal.SIGSTOP)
+            except Exception:
+                pass
+
+    def resume(self):
+        if self.proc is not None:
+            try:
+                self.proc.send_signal(signal.SIGCONT)
+            except Exception:
+                pass
 
     def stop(self):
         t_end = time.perf_counter()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.resume()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -122,8 +142,9 @@ class ClockSampler:
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
+                mask = int(r[3], 16) if r[3].lower().startswith("0x") else 0
+                for name, bit in self.BITS:
+                    if mask & bit:
                         reasons.add(name)
             except Exception:
                 pass
@@ -394,8 +415,10 @@ def main():
     gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
+    for i in range(K):
         loss = step(X, w)
+        if sampler and i == min(1, K - 1):
+            sampler.resume()      # the queue now holds a step or two of GPU work
     e1.record()
     barrier()
     gc.enable()
