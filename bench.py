@@ -16,6 +16,10 @@ Weak scaling: every rank keeps `--frames` frames (default 2^22, 1.1 GB > L2) res
             = SURVEY 8d's per-frame figure x frames, against the measured HBM peak.  `roofline_fp32` puts the kernel and
             the whole step against the fp32 FMA peak measured in the same run (cvf_fma_probe), which is the roofline
             that actually binds this path; `kernels` lists every kernel's share of the step.
+`scaling_strong` (N-GPU runs of C1-C4): the same step on SURVEY 8d's fixed global batch of 2^23 frames split over the ranks.
+`dp_parity` (N > 1): before the timed region, one common batch is run once on a single rank's worth of code (collectives off)
+            and once sharded over the ranks with the NCCL all-reduces; loss, eigenvalues and gradients must agree.
+`native`  : source hash stamped into libcvf_sm100.so and whether it equals the hash of the sources next to it.
 `cpu_baseline` / `--impl reference`: oracle/ref_torch.py (restatement of the reference's PyTorch path; /root/reference does
             not exist on the GPU box) on the host cores, on a bounded sample of the same workload.  Only these two legs
             import oracle/.
@@ -64,14 +68,20 @@ KERNEL_FLOPS = {
     ("c4", "fast_pass2a"): 48720, ("c4", "fast_pass1"): 29160, ("c4", "fast_pass2b(dW1)"): 19440,
     ("c2", "ae_fast_main"): 9120, ("c2", "ae_fast_dw"): 6176,   # forward P + delta sweep (P - first layer); weight + bias products
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` capture of this command under profiles/
-# (r01_ncu_c3_summary.txt); keyed by (workload, kernel, frames per launch) and not extrapolated to other sizes
-KERNEL_TRAFFIC = {
-    ("c3", "fast_pass2a", 1 << 22): 7.082898e9 + 7.657857e9,
-    ("c3", "fast_pass1", 1 << 22): 1.309537e9 + 4.322941e9,
-    ("c3", "fast_pass2b(dW1)", 1 << 22): 7.147142e9 + 0.550824e9,
-    ("c3", "fast_prep", 1 << 22): 1.115355e9 + 1.264251e9,
-}
+def measured_traffic(workload, kernel, frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel`, from the `ncu --set full` capture of this very
+    command that profiles/ncu_traffic.py condensed into profiles/ncu_traffic.json -- used only when the capture was taken at
+    the same workload, frame count and source hash as the running library; None otherwise (no stale constants)."""
+    try:
+        import __graft_entry__ as entry
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tab = json.load(f)
+        if tab.get("source_hash") != entry.library_hash() or tab.get("workload") != workload or tab.get("frames") != frames:
+            return None, "no ncu capture of this build (profiles/ncu_traffic.json is of another source hash / size)"
+        v = tab["kernels"].get(kernel)
+        return (None, "kernel not in the capture") if v is None else (float(v), f"ncu --set full capture {tab.get('capture')}")
+    except Exception as exc:
+        return None, f"no capture table ({type(exc).__name__})"
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -246,7 +256,7 @@ def build_workload(name, n_frames, dev, seed, lr=1e-3):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
+def cpu_reference_run(name, n_frames, steps, warmup, seed=7, dataloader_steps=0):
     """The reference's PyTorch path (oracle/ref_torch.py restatement: autograd through torch.linalg.svd, double
     backward, Adam) on the host cores.  Returns (frames/s, ms/step, cores)."""
     from oracle import ref_torch
@@ -318,7 +328,63 @@ def cpu_reference_run(name, n_frames, steps, warmup, seed=7):
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
+    if dataloader_steps > 0 and name in ("c1", "c3", "c4"):
+        # (ii) of SURVEY 8d: the same step fed by the reference's loader (core.py:470-475: TensorDataset + default collate,
+        # shuffle=False, drop_last=True), batch size = the sample
+        ds = torch.utils.data.TensorDataset(X.repeat((dataloader_steps,) + (1,) * (X.dim() - 1)), w.repeat(dataloader_steps),
+                                            torch.arange(n_frames * dataloader_steps))
+        loader = torch.utils.data.DataLoader(dataset=ds, batch_size=n_frames, drop_last=True, shuffle=False)
+        t0 = time.perf_counter()
+        for Xb, wb, _ in loader:
+            opt.zero_grad(set_to_none=True)
+            Xr = Xb.clone().requires_grad_()
+            loss = ref_torch.eigen_loss(Xr, wb, nets, pp, 20.0, eig_w)[0]
+            loss.backward()
+            opt.step()
+        cpu_reference_run.dataloader_fps = n_frames * dataloader_steps / (time.perf_counter() - t0)
     return n_frames * steps / total, 1e3 * total / steps, cores
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU checks
+def _loss_and_grads(task, X, w):
+    from colvarsfinder import core
+    task.optimizer.zero_grad(set_to_none=True)
+    if isinstance(task, core.EigenFunctionTask):
+        out = task.loss_func(X, w, None, None)
+        loss, eig = out[0], out[1].double()
+    else:
+        loss, eig = task.weighted_MSE_loss(X, w), torch.zeros(1, dtype=torch.float64, device=X.device)
+    loss.backward()
+    g = torch.cat([p.grad.reshape(-1) for p in task.model.parameters()]).double()
+    task.optimizer.zero_grad(set_to_none=True)
+    return loss.detach().double(), eig, g
+
+
+def dp_parity_check(task, X, w, rank, world, frames=1 << 18):
+    """N ranks on shards of ONE common batch (NCCL all-reduce of batch sums and gradient sums) against the same batch on one
+    rank (collectives off): loss, eigenvalues, gradients.  Outside the timed region; parameters are not updated."""
+    import torch.distributed as dist
+    from colvarsfinder import _ops
+    n = min(frames, X.shape[0])
+    n -= n % (512 * world)
+    Xc, wc = X[:n].clone(), w[:n].clone()
+    dist.broadcast(Xc, 0)
+    dist.broadcast(wc, 0)
+    with _ops.no_collectives():
+        l1, e1, g1 = _loss_and_grads(task, Xc, wc)
+    lo, hi = _ops.shard_range(n, rank, world)
+    l2, e2, g2 = _loss_and_grads(task, Xc[lo:hi].contiguous(), wc[lo:hi].contiguous())
+    res = {"frames": n, "loss_rel": float((l1 - l2).abs() / l1.abs()),
+           "eig_rel_max": float(((e1 - e2).abs() / e1.abs().clamp_min(1e-300)).max()),
+           "grad_rel_l2": float((g1 - g2).norm() / g1.norm())}
+    worst = torch.tensor([res["loss_rel"], res["eig_rel_max"], res["grad_rel_l2"]], dtype=torch.float64, device=X.device)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    res.update(loss_rel=float(worst[0]), eig_rel_max=float(worst[1]), grad_rel_l2=float(worst[2]))
+    # fp32 sums inside a 512-frame tile are identical (shard boundaries are tile boundaries); only the fp64 order differs
+    res["ok"] = bool(worst[0] < 1e-6 and worst[1] < 1e-6 and worst[2] < 1e-6)
+    if not res["ok"]:
+        raise SystemExit(f"data-parallel parity check failed: {res}")
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -347,6 +413,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default 2^22; 2^16 for c5)")
     ap.add_argument("--cpu-frames", type=int, default=None, help="frames per step of the CPU sample (default 100000; 4096 for c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="also time the 2^23-frame global batch of SURVEY 8d at N = 1")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.frames is None:
@@ -393,9 +460,15 @@ def main():
 
     # started early: nvidia-smi takes a while to deliver its first row (CVF_BENCH_CLOCKS=0 switches the sampling off)
     sampler = ClockSampler(local).start() if rank == 0 and os.environ.get("CVF_BENCH_CLOCKS", "1") != "0" else None
-    step, X, w, task = build_workload(args.workload, args.frames, dev, seed=2026 + rank)
+    # strong scaling: the global batch of 2^23 frames split over the ranks, next to the weak-scaling headline
+    strong_frames = (1 << 23) // world if args.workload in ("c1", "c2", "c3", "c4") and (world > 1 or args.strong) else 0
+    step, X_all, w_all, task = build_workload(args.workload, max(args.frames, strong_frames), dev, seed=2026 + rank)
+    X, w = X_all[:args.frames], w_all[:args.frames]
     W = max(args.warmup, 3)
     K = args.steps
+    dp_parity = None
+    if world > 1 and task is not None:
+        dp_parity = dp_parity_check(task, X, w, rank, world)
 
     def barrier():
         if world > 1:
@@ -484,6 +557,29 @@ def main():
     e2e_value = args.frames * world * K / (float(ms_e2e) * 1e-3)
     del hosts, hw, devb, devw
 
+    # ---- strong scaling: global batch 2^23 fixed, K_s steps (>= 50: at N > 1 one host hiccup must not dominate)
+    strong = None
+    if strong_frames:
+        Xs, ws_ = X_all[:strong_frames], w_all[:strong_frames]
+        K_s = max(K, 50) if world > 1 else K
+        for _ in range(3):
+            step(Xs, ws_)
+        barrier()
+        gc.collect()
+        gc.disable()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(K_s):
+            step(Xs, ws_)
+        s1.record()
+        barrier()
+        gc.enable()
+        ms_s = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(ms_s, op=torch.distributed.ReduceOp.MAX)
+        strong = {"global_batch": strong_frames * world, "frames_per_gpu_per_step": strong_frames, "steps": K_s,
+                  "ms_per_step": float(ms_s) / K_s, "value": strong_frames * world * K_s / (float(ms_s) * 1e-3), "unit": "frames/s"}
+
     # ---- per-kernel device time: K more steps with a CUDA-event pair around every launch of the library
     L = _lib.lib()
     _lib.check(L.cvf_profile_enable(1), "cvf_profile_enable")
@@ -515,6 +611,7 @@ def main():
             torch.distributed.destroy_process_group()
         return
     hbm_peak, peak_src = measured_peaks()
+    traffic, traffic_src = measured_traffic(args.workload, dom_name, args.frames)
     achieved = bytes_per_frame * args.frames / (kern_ms * 1e-3) / 1e9
     step_tflops = value / world * flops_per_frame / 1e12
     dom_flops = KERNEL_FLOPS.get((args.workload, dom_name))
@@ -526,7 +623,7 @@ def main():
                 "ms_per_step": float(ms_e2e) / K},
         "gpu_launches": launches_timed * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": KERNEL_TRAFFIC.get((args.workload, dom_name, args.frames)), "kernel": dom_name, "kernel_ms": kern_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": dom_name, "kernel_ms": kern_ms,
                      "kernel_share_of_step": prof[dom_name][0] / K / step_kernel_ms, "peak_source": peak_src,
                      "note": ("HBM-bound kernel: algorithmic bytes = frame read + aligned frame written" if args.workload == "c2p" else
                               "this path is fp32-FMA bound, not HBM bound (SURVEY 8d): see roofline_fp32")},
@@ -538,7 +635,13 @@ def main():
                               "achieved": dom_flops * args.frames / (kern_ms * 1e-3) / 1e12,
                               "frac": dom_flops * args.frames / (kern_ms * 1e-3) / 1e12 / fma_peak}},
         "kernels": {k_: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K} for k_, v in sorted(prof.items())},
+        "native": {"so": "colvars-finder_b200/colvarsfinder/libcvf_sm100.so", "source_hash": entry.library_hash(),
+                   "matches_sources": entry.library_hash() == entry.source_hash()},
     }
+    if strong is not None:
+        out["scaling_strong"] = strong
+    if dp_parity is not None:
+        out["dp_parity"] = dp_parity
     if args.workload == "c5":
         # the layer products run on the tensor cores as three TF32 passes: the fp32-equivalent ceiling is the measured dense
         # bf16 rate / 2 (TF32 runs at half the bf16 rate) / 3 (passes)
@@ -556,9 +659,14 @@ def main():
                            "note": "achieved = algorithmic fp32 flops of the step (6P per frame) per second; tensor-pipe active "
                                    "cycles per product kernel are in profiles/"}
     if not args.no_cpu_baseline:
-        fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, 5, 1)
+        fps, ms, cores = cpu_reference_run(args.workload, args.cpu_frames, 5, 1, dataloader_steps=2)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": f"{args.cpu_frames} frames/step x 5 steps (+1 warm-up), oracle/ref_torch.py on the host"}
+        dl = getattr(cpu_reference_run, "dataloader_fps", None)
+        if dl is not None:
+            out["cpu_baseline"]["dataloader_value"] = dl
+            out["cpu_baseline"]["dataloader_sample"] = (f"2 batches of {args.cpu_frames} frames through the reference's DataLoader "
+                                                        "(TensorDataset, default collate, core.py:470-475) + the same step")
     emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()

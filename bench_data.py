@@ -11,8 +11,8 @@ import torch
 
 # 22 atoms of alanine dipeptide, nm (reference examples/dipeptide/top.gro:3-24); x10 -> Angstrom
 DIPEPTIDE_NM = np.array([
-    [0.208, 0.508, 0.089], [0.200, 0.440, 0.004], [0.097, 0.405, 0.004], [0.208, 0.508, -0.081],
-    [0.295, 0.315, -0.003], [0.252, 0.200, -0.000], [0.426, 0.349, -0.000], [0.445, 0.449, -0.000],
+    [0.200, 0.100, -0.000], [0.200, 0.209, 0.000], [0.149, 0.245, 0.089], [0.149, 0.245, -0.089],
+    [0.343, 0.264, -0.000], [0.439, 0.188, -0.000], [0.356, 0.397, -0.000], [0.273, 0.456, -0.000],
     [0.485, 0.461, -0.000], [0.541, 0.432, 0.089], [0.566, 0.422, -0.123], [0.512, 0.452, -0.213],
     [0.663, 0.472, -0.121], [0.581, 0.314, -0.124], [0.471, 0.613, 0.000], [0.360, 0.665, 0.000],
     [0.585, 0.683, 0.000], [0.674, 0.636, -0.000], [0.585, 0.828, 0.000], [0.482, 0.865, 0.000],

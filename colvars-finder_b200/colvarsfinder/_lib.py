@@ -34,6 +34,7 @@ class Mlp(C.Structure):
 _P, _I64, _I32, _D, _SZ = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t
 SYMBOLS = {
     "cvf_version": (C.c_int, []),
+    "cvf_source_hash": (C.c_char_p, []),
     "cvf_last_error_string": (C.c_char_p, []),
     "cvf_sizeof_preproc": (_SZ, []),
     "cvf_sizeof_mlp": (_SZ, []),
@@ -52,6 +53,7 @@ SYMBOLS = {
     "cvf_eigen_tlag_combine": (C.c_int, [_P, _P, _P, _I32, _D, C.POINTER(_D), _D, _I32, _P, _P, _P]),
     "cvf_ae_workspace_bytes": (_SZ, [C.POINTER(Mlp), _I64]),
     "cvf_ae_step": (C.c_int, [_P, _P, _I64, C.POINTER(Mlp), _P, _P, _P, _P, _SZ, _P]),
+    "cvf_ae_step_target": (C.c_int, [_P, _P, _P, _I64, C.POINTER(Mlp), _P, _P, _P, _P, _SZ, _P]),
     "cvf_ae_set_wide_path": (C.c_int, [_I32]),
     "cvf_ae_set_fast_path": (C.c_int, [_I32]),
     "cvf_fma_probe": (C.c_int, [_P, _I32, C.POINTER(_D), _P]),

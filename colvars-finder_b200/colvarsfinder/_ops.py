@@ -1,5 +1,17 @@
-"""Glue between the task classes and libcvf_sm100.so: descriptors, flat parameter storage, the autograd
-nodes that stand where the reference builds its autograd graph, and the one collective per pass.
+"""Glue between the task classes and libcvf_sm100.so: descriptors, flat parameter storage, the ``torch.library`` custom
+operators (namespace ``cvf``) that stand where the reference builds its autograd graph, and the one collective per pass.
+
+Operators (each with ``register_fake`` for shape inference and ``register_autograd``, so that the reference's
+``loss.backward()`` -- core.py:517,708,1115 -- fills ``param.grad`` from the CUDA passes):
+
+* ``cvf::eigen_stats(X, w, params, handle, slot) -> (y, stats)``   pass 1 + all-reduce; backward = ``cvf::eigen_grad`` (pass 2)
+* ``cvf::eigen_combine(stats, handle) -> comb``                    loss / eigenvalues / ordering of core.py:426-455
+* ``cvf::eigen_tlag_sx``, ``cvf::eigen_tlag_combine``              transfer-operator branch (core.py:412-416,428,440)
+* ``cvf::ae_sums(F, T, w, params, want_grad, handle) -> (sums, gsum)``  weighted reconstruction error and its gradient
+* ``cvf::align_fwd(x, ref, idx) -> y``                             Kabsch alignment (stand-alone pre-pass)
+
+``handle`` is an integer naming the host-side context (descriptors + scratch) of a task: operators take tensors and plain
+scalars only.
 
 Data-parallel layout: every rank holds a shard of the frames in its own HBM and the full (replicated)
 parameters.  The loss couples frames only through a handful of batch sums, so each pass ends with ONE
@@ -9,6 +21,9 @@ rank then runs the same tiny combine kernel / optimizer step.  With one process 
 from __future__ import annotations
 
 import ctypes as C
+import itertools
+import weakref
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
@@ -27,9 +42,29 @@ def rank() -> int:
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+def backend() -> str:
+    return dist.get_backend() if dist.is_available() and dist.is_initialized() else ''
+
+
+_COLLECTIVES_OFF = False
+
+
+class no_collectives:
+    """Context manager: the step runs as if this rank were alone (its all-reduces become no-ops).  Used by the data-parallel
+    parity checks, which compare the sharded step with the same step on the whole batch inside one process."""
+
+    def __enter__(self):
+        global _COLLECTIVES_OFF
+        self._saved, _COLLECTIVES_OFF = _COLLECTIVES_OFF, True
+
+    def __exit__(self, *exc):
+        global _COLLECTIVES_OFF
+        _COLLECTIVES_OFF = self._saved
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks on the current stream (no-op for a single process)."""
-    if world_size() > 1:
+    if world_size() > 1 and not _COLLECTIVES_OFF:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
 
@@ -207,24 +242,63 @@ def _check_batch(X, weight, what):
     return X, weight
 
 
+# ------------------------------------------------------------------------------------------ context registry
+# Operators registered with torch.library take tensors and scalars; everything else a call needs (descriptor structs, the
+# scratch buffer, loss constants) lives in a context object that the operator finds through an integer handle.
+_CONTEXTS = weakref.WeakValueDictionary()
+_HANDLES = itertools.count(1)
+
+
+def _register_context(obj) -> int:
+    h = next(_HANDLES)
+    _CONTEXTS[h] = obj
+    return h
+
+
+def _context(handle: int):
+    try:
+        return _CONTEXTS[handle]
+    except KeyError:
+        raise RuntimeError(f"cvf: context {handle} no longer exists (its task object was deleted)") from None
+
+
+class _PackFlat(torch.autograd.Function):
+    """The flat parameter buffer as a differentiable function of the parameters that alias it: forward is free (the
+    parameters ARE views of the buffer), backward hands every parameter its slice of the buffer's gradient."""
+
+    @staticmethod
+    def forward(ctx, flatp, *params):
+        ctx.flatp = flatp
+        return flatp.flat.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + ctx.flatp.split(g)
+
+
 # ------------------------------------------------------------------------------------------ eigenfunctions
 class EigenContext:
-    """Everything constant across steps for one EigenFunctionTask."""
+    """Everything constant across steps for one set of k equally-shaped networks on one pre-processing layer: descriptors,
+    loss constants, scratch.  ``model`` may be None when the caller packs the parameters itself (RegAutoEncoderTask)."""
 
-    def __init__(self, model, pp_layer, frame_shape, device, alpha, eig_w, beta, diag_coeff, sort):
+    def __init__(self, model, pp_layer, frame_shape, device, alpha, eig_w, beta, diag_coeff, sort, dims=None, acts=None, k=None):
         self.device = torch.device(device)
-        self.k = len(model.eigen_funcs)
+        if model is not None:
+            self.k = len(model.eigen_funcs)
+            self.flat = FlatParams(list(model.eigen_funcs), self.device)
+            if any(d != self.flat.dims[0] for d in self.flat.dims):
+                raise RuntimeError("all eigenfunction networks must share one architecture")
+            dims, acts = self.flat.dims[0], self.flat.acts[0]
+        else:
+            self.k, self.flat = int(k), None
         if self.k > _lib.MAX_K:
             raise RuntimeError(f"k = {self.k} eigenfunctions is outside the supported envelope (<= {_lib.MAX_K})")
-        self.flat = FlatParams(list(model.eigen_funcs), self.device)
-        if any(d != self.flat.dims[0] for d in self.flat.dims):
-            raise RuntimeError("all eigenfunction networks must share one architecture")
-        self.mlp = _lib.make_mlp(self.flat.dims[0], self.flat.acts[0])
+        self.mlp = _lib.make_mlp(dims, acts)
         self.spec = PreprocSpec(pp_layer, frame_shape, self.device, diag_coeff)
-        if self.spec.d_r != self.flat.dims[0][0]:
-            raise RuntimeError(f"pre-processing layer outputs {self.spec.d_r} features, the networks take {self.flat.dims[0][0]}")
+        if self.spec.d_r != dims[0]:
+            raise RuntimeError(f"pre-processing layer outputs {self.spec.d_r} features, the networks take {dims[0]}")
         self.alpha, self.beta, self.sort = float(alpha), float(beta), 1 if sort else 0
-        self.eig_w = (C.c_double * self.k)(*[float(v) for v in eig_w])
+        self.eig_w = (C.c_double * self.k)(*[float(v) for v in (list(eig_w) + [0.0] * self.k)[:self.k]])
         L = _lib.lib()
         self.n_stats = L.cvf_eigen_num_stats(self.k)
         self.n_comb = L.cvf_eigen_num_combine(self.k)
@@ -232,6 +306,12 @@ class EigenContext:
         self.fast_path = bool(L.cvf_eigen_path(self.spec.struct_ptr(), C.byref(self.mlp), self.k) == 1)
         # scratch slots: 0 for X, 1 for the time-lagged X of the transfer-operator loss (both must survive until backward)
         self._ws = {}
+        self.handle = _register_context(self)
+
+    def packed_params(self):
+        """[k * n_per_net] parameter vector of a model-backed context, differentiable w.r.t. the model's parameters."""
+        self.flat.check()
+        return _PackFlat.apply(self.flat, *self.flat.params)
 
     def _workspace_for(self, B, slot=0):
         """Scratch of the step kernels, grown to the largest batch seen (PyTorch's caching allocator owns it)."""
@@ -240,146 +320,299 @@ class EigenContext:
             need = int(_lib.lib().cvf_eigen_workspace_bytes(self.spec.struct_ptr(), C.byref(self.mlp), self.k, B))
             if need <= 0:
                 raise RuntimeError("cvf_eigen_workspace_bytes: unsupported configuration")
+            serial = ws["serial"] if ws else 0
             self._ws[slot] = None
-            ws = {"buf": torch.empty(need, dtype=torch.uint8, device=self.device), "bytes": need, "frames": B, "key": None}
+            ws = {"buf": torch.empty(need, dtype=torch.uint8, device=self.device), "bytes": need, "frames": B, "serial": serial,
+                  "valid": False, "pver": None}
             self._ws[slot] = ws
         return ws
 
-    def _key(self, X, weight):
-        return (X.data_ptr(), X.shape[0], X._version, weight.data_ptr(), weight._version, self.flat.flat._version)
+    def _param_version(self, params):
+        # the flat buffer's own counter does not see optimizer updates (they go through the parameters' views): add theirs
+        v = params._version
+        if self.flat is not None and params.data_ptr() == self.flat.flat.data_ptr():
+            v += sum(p._version for p in self.flat.params)
+        return (params.data_ptr(), v)
 
-    def stats(self, X, weight, slot=0):
-        """Pass 1 on this rank's frames -> (y [k,B] fp32, stats fp64)."""
+    def _own_params(self, params):
+        if params is not None:
+            return params
+        if self.flat is None:
+            raise RuntimeError("this context has no model of its own: pass the packed parameter vector")
+        self.flat.check()
+        return self.flat.flat
+
+    def stats(self, X, weight, params=None, slot=0):
+        """Pass 1 on this rank's frames -> (y [k,B] fp32, local stats fp64).  ``params`` defaults to the model's flat buffer."""
         L = _lib.lib()
         B = X.shape[0]
+        params = self._own_params(params)
+        if params.numel() != self.k * self.n_per_net or params.dtype != torch.float32 or not params.is_contiguous():
+            raise RuntimeError(f"cvf::eigen_stats: params must be a contiguous float32 vector of {self.k * self.n_per_net} entries")
         ws = self._workspace_for(B, slot)
         y = torch.empty(self.k, B, dtype=torch.float32, device=self.device)
         stats = torch.empty(self.n_stats, dtype=torch.float64, device=self.device)
-        _lib.check(L.cvf_eigen_stats(X.data_ptr(), weight.data_ptr(), B, self.spec.struct_ptr(), C.byref(self.mlp), self.k,
-                                     self.flat.flat.data_ptr(), y.data_ptr(), stats.data_ptr(), ws["buf"].data_ptr(), ws["bytes"],
-                                     _stream()), "cvf_eigen_stats")
-        ws["key"] = self._key(X, weight)
+        with torch.cuda.device(self.device):
+            _lib.check(L.cvf_eigen_stats(X.data_ptr(), weight.data_ptr(), B, self.spec.struct_ptr(), C.byref(self.mlp), self.k,
+                                         params.data_ptr(), y.data_ptr(), stats.data_ptr(), ws["buf"].data_ptr(), ws["bytes"],
+                                         _stream()), "cvf_eigen_stats")
+        ws["serial"] += 1
+        ws["valid"], ws["pver"] = True, self._param_version(params)
+        ws["xkey"] = (X.data_ptr(), X.shape[0], X._version, weight.data_ptr(), weight._version)
         return y, stats
+
+    def serial(self, slot=0):
+        ws = self._ws.get(slot)
+        return ws["serial"] if ws else -1
 
     def combine(self, stats):
         comb = torch.empty(self.n_comb, dtype=torch.float64, device=self.device)
-        _lib.check(_lib.lib().cvf_eigen_combine(stats.data_ptr(), self.k, self.alpha, self.eig_w, self.beta, self.sort,
-                                                comb.data_ptr(), _stream()), "cvf_eigen_combine")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cvf_eigen_combine(stats.data_ptr(), self.k, self.alpha, self.eig_w, self.beta, self.sort,
+                                                    comb.data_ptr(), _stream()), "cvf_eigen_combine")
         return comb
 
-    def grads(self, X, weight, y, comb, seed_extra=None, slot=0):
-        """Pass 2 on this rank's frames -> fp64 gradient sums [k * n_per_net]."""
+    def grads(self, X, weight, y, comb, seed_extra=None, slot=0, serial=None, params=None):
+        """Pass 2 on this rank's frames -> fp64 gradient sums [k * n_per_net].  ``serial`` names the stats() call whose scratch
+        may be reused (None: the latest one on the slot)."""
         g = torch.empty(self.k * self.n_per_net, dtype=torch.float64, device=self.device)
         ws = self._workspace_for(X.shape[0], slot)
-        # the scratch still holds pass 1's intermediates iff the last stats() call saw these very tensors and parameters
-        valid = 1 if ws["key"] is not None and ws["key"] == self._key(X, weight) else 0
-        _lib.check(_lib.lib().cvf_eigen_grad(X.data_ptr(), weight.data_ptr(), X.shape[0], self.spec.struct_ptr(),
-                                             C.byref(self.mlp), self.k, self.flat.flat.data_ptr(), y.data_ptr(),
-                                             comb.data_ptr(), None if seed_extra is None else seed_extra.data_ptr(),
-                                             g.data_ptr(), ws["buf"].data_ptr(), ws["bytes"], valid, _stream()),
-                   "cvf_eigen_grad")
+        params = self._own_params(params)
+        if serial is None:
+            serial = ws["serial"]
+        # the scratch still holds pass 1's intermediates iff the stats() call of THIS loss was the last one on the slot and
+        # neither the batch nor the parameters were written since
+        valid = 1 if (ws["valid"] and ws["serial"] == serial and ws["pver"] == self._param_version(params) and
+                      ws.get("xkey") == (X.data_ptr(), X.shape[0], X._version, weight.data_ptr(), weight._version)) else 0
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cvf_eigen_grad(X.data_ptr(), weight.data_ptr(), X.shape[0], self.spec.struct_ptr(),
+                                                 C.byref(self.mlp), self.k, params.data_ptr(), y.data_ptr(),
+                                                 comb.data_ptr(), None if seed_extra is None else seed_extra.data_ptr(),
+                                                 g.data_ptr(), ws["buf"].data_ptr(), ws["bytes"], valid, _stream()),
+                       "cvf_eigen_grad")
         # pass 2 consumes the scratch (it leaves v = J J^T u where pass 1 left u): a second backward recomputes it
-        ws["key"] = None
+        ws["valid"] = False
         return g
 
     def tlag_terms(self, y, y_lag, weight, coef=None):
         """sum_f w (y' - y)^2 per network (coef None), or the per-frame seed term coef_i w (y_i - y'_i) of the backward pass."""
         L, B = _lib.lib(), y.shape[1]
-        if coef is None:
-            sx = torch.empty(self.k, dtype=torch.float64, device=self.device)
-            ws = self._workspace_for(B, 0)
-            _lib.check(L.cvf_eigen_tlag_terms(y.data_ptr(), y_lag.data_ptr(), weight.data_ptr(), B, self.k, None, sx.data_ptr(),
-                                              None, ws["buf"].data_ptr(), ws["bytes"], _stream()), "cvf_eigen_tlag_terms")
-            return sx
-        extra = torch.empty(self.k, B, dtype=torch.float32, device=self.device)
-        _lib.check(L.cvf_eigen_tlag_terms(y.data_ptr(), y_lag.data_ptr(), weight.data_ptr(), B, self.k, coef.data_ptr(), None,
-                                          extra.data_ptr(), None, 0, _stream()), "cvf_eigen_tlag_terms")
+        with torch.cuda.device(self.device):
+            if coef is None:
+                sx = torch.empty(self.k, dtype=torch.float64, device=self.device)
+                ws = self._workspace_for(B, 0)
+                _lib.check(L.cvf_eigen_tlag_terms(y.data_ptr(), y_lag.data_ptr(), weight.data_ptr(), B, self.k, None, sx.data_ptr(),
+                                                  None, ws["buf"].data_ptr(), ws["bytes"], _stream()), "cvf_eigen_tlag_terms")
+                return sx
+            extra = torch.empty(self.k, B, dtype=torch.float32, device=self.device)
+            _lib.check(L.cvf_eigen_tlag_terms(y.data_ptr(), y_lag.data_ptr(), weight.data_ptr(), B, self.k, coef.data_ptr(), None,
+                                              extra.data_ptr(), None, 0, _stream()), "cvf_eigen_tlag_terms")
         return extra
 
     def tlag_combine(self, stats, stats_lag, sx, tau):
         comb = torch.empty(self.n_comb + self.k, dtype=torch.float64, device=self.device)
         comb_lag = torch.empty(self.n_comb, dtype=torch.float64, device=self.device)
-        _lib.check(_lib.lib().cvf_eigen_tlag_combine(stats.data_ptr(), stats_lag.data_ptr(), sx.data_ptr(), self.k, self.alpha,
-                                                     self.eig_w, float(tau), self.sort, comb.data_ptr(), comb_lag.data_ptr(),
-                                                     _stream()), "cvf_eigen_tlag_combine")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cvf_eigen_tlag_combine(stats.data_ptr(), stats_lag.data_ptr(), sx.data_ptr(), self.k, self.alpha,
+                                                         self.eig_w, float(tau), self.sort, comb.data_ptr(), comb_lag.data_ptr(),
+                                                         _stream()), "cvf_eigen_tlag_combine")
         return comb, comb_lag
 
 
-class _EigenLoss(torch.autograd.Function):
-    """loss = EigenFunctionTask.loss_func (reference core.py:387-457); backward = reference core.py:517."""
+def _coef_from_gstats(g_stats, k, n_comb):
+    """Gradient w.r.t. the batch sums (S0, S1[k], S2[k,k], SD[k]) -> the coefficient blocks of the combine vector
+    (mean = 0, cD = dL/dSD, C2 = dL/dS2 + its transpose, a0 = dL/dS1; include/cvf.h)."""
+    coef = torch.zeros(n_comb, dtype=torch.float64, device=g_stats.device)
+    g2 = g_stats[1 + k:1 + k + k * k].view(k, k)
+    coef[3 + 3 * k:3 + 4 * k] = g_stats[1 + k + k * k:1 + 2 * k + k * k]
+    coef[3 + 4 * k:3 + 4 * k + k * k] = (g2 + g2.t()).reshape(-1)
+    coef[3 + 4 * k + k * k:3 + 5 * k + k * k] = g_stats[1:1 + k]
+    return coef
 
-    @staticmethod
-    def forward(ctx, ectx, X, weight, *params):
-        with torch.cuda.device(ectx.device):
-            y, stats = ectx.stats(X, weight)
-            allreduce_sum_(stats)
-            comb = ectx.combine(stats)
-        ctx.ectx, ctx.X, ctx.weight, ctx.y, ctx.comb = ectx, X, weight, y, comb
-        k = ectx.k
-        out32 = comb[:3 + k].to(torch.float32)
-        loss, obj, pen, eig = out32[0], out32[1], out32[2], out32[3:3 + k]
-        cvec = comb[3 + k:3 + 2 * k].to(torch.int64)
-        ctx.mark_non_differentiable(obj, pen, eig, cvec)
-        return loss, eig, obj, pen, cvec
 
-    @staticmethod
-    def backward(ctx, g_loss, *unused):
-        ectx = ctx.ectx
-        with torch.cuda.device(ectx.device):
-            g = ectx.grads(ctx.X, ctx.weight, ctx.y, ctx.comb)
-            allreduce_sum_(g)
-            g32 = (g * g_loss.to(torch.float64)).to(torch.float32)
-        return (None, None, None) + ectx.flat.split(g32)
+def _gstats_from_comb(comb, k):
+    """The inverse map for a combine vector written by the library (a0 = 0, C2 symmetric): d loss / d (S0, S1, S2, SD)."""
+    mean = comb[3 + 2 * k:3 + 3 * k]
+    cD = comb[3 + 3 * k:3 + 4 * k]
+    C2 = comb[3 + 4 * k:3 + 4 * k + k * k].view(k, k)
+    a0 = comb[3 + 4 * k + k * k:3 + 5 * k + k * k]
+    return torch.cat([comb.new_zeros(1), a0 - C2 @ mean, (0.5 * C2).reshape(-1), cD])
+
+
+@torch.library.custom_op("cvf::eigen_stats", mutates_args=())
+def eigen_stats_op(X: torch.Tensor, w: torch.Tensor, params: torch.Tensor, handle: int, slot: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    ectx = _context(handle)
+    y, stats = ectx.stats(X, w, params, slot)
+    allreduce_sum_(stats)
+    return y, stats
+
+
+@eigen_stats_op.register_fake
+def _(X, w, params, handle, slot):
+    ectx = _context(handle)
+    return X.new_empty((ectx.k, X.shape[0]), dtype=torch.float32), X.new_empty((ectx.n_stats,), dtype=torch.float64)
+
+
+@torch.library.custom_op("cvf::eigen_grad", mutates_args=())
+def eigen_grad_op(X: torch.Tensor, w: torch.Tensor, y: torch.Tensor, params: torch.Tensor, coef: torch.Tensor,
+                  seed_extra: Optional[torch.Tensor], handle: int, slot: int, serial: int) -> torch.Tensor:
+    ectx = _context(handle)
+    if seed_extra is not None:
+        seed_extra = seed_extra.to(torch.float32).contiguous()
+    g = ectx.grads(X, w, y, coef.contiguous(), seed_extra, slot, serial, params)
+    allreduce_sum_(g)
+    return g.to(torch.float32)
+
+
+@eigen_grad_op.register_fake
+def _(X, w, y, params, coef, seed_extra, handle, slot, serial):
+    return params.new_empty(params.shape)
+
+
+def _eigen_stats_setup(ctx, inputs, output):
+    X, w, params, handle, slot = inputs
+    ctx.save_for_backward(X, w, params, output[0])
+    ctx.set_materialize_grads(False)      # an unused y must not turn into a [k, B] tensor of zeros
+    ctx.handle, ctx.slot = handle, slot
+    ctx.serial = _context(handle).serial(slot)
+
+
+def _eigen_stats_backward(ctx, g_y, g_stats):
+    X, w, params, y = ctx.saved_tensors
+    ectx = _context(ctx.handle)
+    if g_stats is None and g_y is None:
+        return None, None, None, None, None
+    if g_stats is None:
+        g_stats = torch.zeros(ectx.n_stats, dtype=torch.float64, device=X.device)
+    coef = _coef_from_gstats(g_stats.to(torch.float64), ectx.k, ectx.n_comb)
+    g = eigen_grad_op(X, w, y, params, coef, g_y, ctx.handle, ctx.slot, ctx.serial)
+    return None, None, g, None, None
+
+
+eigen_stats_op.register_autograd(_eigen_stats_backward, setup_context=_eigen_stats_setup)
+
+
+@torch.library.custom_op("cvf::eigen_combine", mutates_args=())
+def eigen_combine_op(stats: torch.Tensor, handle: int) -> torch.Tensor:
+    return _context(handle).combine(stats.contiguous())
+
+
+@eigen_combine_op.register_fake
+def _(stats, handle):
+    return stats.new_empty((_context(handle).n_comb,))
+
+
+def _eigen_combine_setup(ctx, inputs, output):
+    ctx.save_for_backward(output)
+    ctx.k = _context(inputs[1]).k
+
+
+def _eigen_combine_backward(ctx, g_comb):
+    comb, = ctx.saved_tensors
+    return g_comb[0] * _gstats_from_comb(comb, ctx.k), None      # only the loss entry is differentiable
+
+
+eigen_combine_op.register_autograd(_eigen_combine_backward, setup_context=_eigen_combine_setup)
+
+
+@torch.library.custom_op("cvf::eigen_tlag_sx", mutates_args=())
+def eigen_tlag_sx_op(y: torch.Tensor, y_lag: torch.Tensor, w: torch.Tensor, handle: int) -> torch.Tensor:
+    sx = _context(handle).tlag_terms(y.contiguous(), y_lag.contiguous(), w)
+    allreduce_sum_(sx)
+    return sx
+
+
+@eigen_tlag_sx_op.register_fake
+def _(y, y_lag, w, handle):
+    return y.new_empty((y.shape[0],), dtype=torch.float64)
+
+
+@torch.library.custom_op("cvf::eigen_tlag_seed", mutates_args=())
+def eigen_tlag_seed_op(y: torch.Tensor, y_lag: torch.Tensor, w: torch.Tensor, coef: torch.Tensor, handle: int) -> torch.Tensor:
+    return _context(handle).tlag_terms(y.contiguous(), y_lag.contiguous(), w, coef=coef.to(torch.float64).contiguous())
+
+
+@eigen_tlag_seed_op.register_fake
+def _(y, y_lag, w, coef, handle):
+    return torch.empty_like(y)
+
+
+def _tlag_sx_setup(ctx, inputs, output):
+    y, y_lag, w, handle = inputs
+    ctx.save_for_backward(y, y_lag, w)
+    ctx.set_materialize_grads(False)
+    ctx.handle = handle
+
+
+def _tlag_sx_backward(ctx, g_sx):
+    y, y_lag, w = ctx.saved_tensors
+    if g_sx is None:
+        return None, None, None, None
+    extra = eigen_tlag_seed_op(y, y_lag, w, 2.0 * g_sx, ctx.handle)      # d sx_i / d y_i = 2 w (y_i - y'_i)
+    return extra, -extra, None, None
+
+
+eigen_tlag_sx_op.register_autograd(_tlag_sx_backward, setup_context=_tlag_sx_setup)
+
+
+@torch.library.custom_op("cvf::eigen_tlag_combine", mutates_args=())
+def eigen_tlag_combine_op(stats: torch.Tensor, stats_lag: torch.Tensor, sx: torch.Tensor, tau: float,
+                          handle: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    return _context(handle).tlag_combine(stats.contiguous(), stats_lag.contiguous(), sx.contiguous(), tau)
+
+
+@eigen_tlag_combine_op.register_fake
+def _(stats, stats_lag, sx, tau, handle):
+    ectx = _context(handle)
+    return stats.new_empty((ectx.n_comb + ectx.k,)), stats.new_empty((ectx.n_comb,))
+
+
+def _tlag_combine_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[0], output[1])
+    ctx.set_materialize_grads(False)
+    ctx.k, ctx.n_comb = _context(inputs[4]).k, _context(inputs[4]).n_comb
+
+
+def _tlag_combine_backward(ctx, g_comb, g_comb_lag):
+    comb, comb_lag = ctx.saved_tensors
+    if g_comb is None:
+        return None, None, None, None, None
+    gl = g_comb[0]
+    k = ctx.k
+    return (gl * _gstats_from_comb(comb, k), gl * _gstats_from_comb(comb_lag, k), gl * 0.5 * comb[ctx.n_comb:ctx.n_comb + k],
+            None, None)
+
+
+eigen_tlag_combine_op.register_autograd(_tlag_combine_backward, setup_context=_tlag_combine_setup)
+
+
+def _loss_outputs(comb, k):
+    out32 = comb[:3 + k].to(torch.float32)
+    loss, obj, pen, eig = out32[0], out32[1].detach(), out32[2].detach(), out32[3:3 + k].detach()
+    cvec = comb[3 + k:3 + 2 * k].detach().to(torch.int64)
+    return loss, eig, obj, pen, cvec
 
 
 def eigen_loss(ectx: EigenContext, X, weight):
+    """EigenFunctionTask.loss_func, generator branch (reference core.py:387-457); ``loss.backward()`` = core.py:517."""
     X, weight = _check_batch(X, weight, "EigenFunctionTask.loss_func")
-    ectx.flat.check()
-    return _EigenLoss.apply(ectx, X, weight, *ectx.flat.params)
-
-
-class _EigenLagLoss(torch.autograd.Function):
-    """Transfer-operator branch of EigenFunctionTask.loss_func (reference core.py:412-416,428,440): forward passes on X and
-    on the time-lagged X, ONE all-reduce of {sums of y, sums of y', sum w (y'-y)^2}; backward = two first-order passes."""
-
-    @staticmethod
-    def forward(ctx, ectx, tau, X, weight, Xl, wl, *params):
-        k = ectx.k
-        with torch.cuda.device(ectx.device):
-            y, st = ectx.stats(X, weight, slot=0)
-            yl, stl = ectx.stats(Xl, wl, slot=1)
-            sx = ectx.tlag_terms(y, yl, weight)
-            packed = torch.cat([st, stl, sx])
-            allreduce_sum_(packed)
-            st, stl, sx = packed[:ectx.n_stats], packed[ectx.n_stats:2 * ectx.n_stats], packed[2 * ectx.n_stats:]
-            comb, comb_lag = ectx.tlag_combine(st.contiguous(), stl.contiguous(), sx.contiguous(), tau)
-        ctx.ectx, ctx.saved = ectx, (X, weight, Xl, wl, y, yl, comb, comb_lag)
-        out32 = comb[:3 + k].to(torch.float32)
-        loss, obj, pen, eig = out32[0], out32[1], out32[2], out32[3:3 + k]
-        cvec = comb[3 + k:3 + 2 * k].to(torch.int64)
-        ctx.mark_non_differentiable(obj, pen, eig, cvec)
-        return loss, eig, obj, pen, cvec
-
-    @staticmethod
-    def backward(ctx, g_loss, *unused):
-        ectx = ctx.ectx
-        X, weight, Xl, wl, y, yl, comb, comb_lag = ctx.saved
-        with torch.cuda.device(ectx.device):
-            extra = ectx.tlag_terms(y, yl, weight, coef=comb[ectx.n_comb:])
-            g = ectx.grads(X, weight, y, comb, seed_extra=extra, slot=0)
-            g += ectx.grads(Xl, wl, yl, comb_lag, seed_extra=extra.neg_(), slot=1)
-            allreduce_sum_(g)
-            g32 = (g * g_loss.to(torch.float64)).to(torch.float32)
-        return (None, None, None, None, None, None) + ectx.flat.split(g32)
+    y, stats = eigen_stats_op(X, weight, ectx.packed_params(), ectx.handle, 0)
+    return _loss_outputs(eigen_combine_op(stats, ectx.handle), ectx.k)
 
 
 def eigen_lag_loss(ectx: EigenContext, tau, X, weight, X_lagged, weight_lagged):
+    """Transfer-operator branch of EigenFunctionTask.loss_func (reference core.py:412-416,428,440): forward passes on X and on
+    the time-lagged X; backward = two first-order passes seeded through y and y'."""
     X, weight = _check_batch(X, weight, "EigenFunctionTask.loss_func")
     X_lagged, weight_lagged = _check_batch(X_lagged, weight_lagged, "EigenFunctionTask.loss_func (time-lagged data)")
     if X_lagged.shape != X.shape:
         raise RuntimeError(f"time-lagged batch has shape {tuple(X_lagged.shape)}, the batch {tuple(X.shape)}")
-    ectx.flat.check()
-    return _EigenLagLoss.apply(ectx, tau, X, weight, X_lagged, weight_lagged, *ectx.flat.params)
+    params = ectx.packed_params()
+    y, st = eigen_stats_op(X, weight, params, ectx.handle, 0)
+    yl, stl = eigen_stats_op(X_lagged, weight_lagged, params, ectx.handle, 1)
+    sx = eigen_tlag_sx_op(y, yl, weight, ectx.handle)
+    comb, _ = eigen_tlag_combine_op(st, stl, sx, float(tau), ectx.handle)
+    return _loss_outputs(comb, ectx.k)
 
 
 # ------------------------------------------------------------------------------------------ autoencoder
@@ -394,6 +627,11 @@ class AEContext:
         assert self.n_params == self.flat.n
         self.ws_bytes, self.ws_frames, self.workspace = 0, 0, None
         self.d_r = e_dims[0]
+        self.handle = _register_context(self)
+
+    def packed_params(self):
+        self.flat.check()
+        return _PackFlat.apply(self.flat, *self.flat.params)
 
     def _workspace_for(self, B):
         if self.workspace is None or B > self.ws_frames:
@@ -405,41 +643,82 @@ class AEContext:
             self.ws_bytes, self.ws_frames = need, B
         return self.workspace.data_ptr()
 
-    def step(self, F, weight, want_grad):
+    def step(self, F, target, weight, params, want_grad):
         """One pass over this rank's frames -> fp64 [2 + n_params]: sum w|e|^2, sum w, gradient of the first sum."""
-        buf = torch.empty(2 + (self.n_params if want_grad else 0), dtype=torch.float64, device=self.device)
+        buf = torch.zeros(2 + self.n_params, dtype=torch.float64, device=self.device) if not want_grad else \
+            torch.empty(2 + self.n_params, dtype=torch.float64, device=self.device)
         gptr = buf.data_ptr() + 16 if want_grad else None
         ws = self._workspace_for(F.shape[0])
-        _lib.check(_lib.lib().cvf_ae_step(F.data_ptr(), weight.data_ptr(), F.shape[0], C.byref(self.mlp),
-                                          self.flat.flat.data_ptr(), buf.data_ptr(), gptr, ws, self.ws_bytes, _stream()),
-                   "cvf_ae_step")
+        with torch.cuda.device(self.device):
+            if target is None:
+                _lib.check(_lib.lib().cvf_ae_step(F.data_ptr(), weight.data_ptr(), F.shape[0], C.byref(self.mlp),
+                                                  params.data_ptr(), buf.data_ptr(), gptr, ws, self.ws_bytes, _stream()),
+                           "cvf_ae_step")
+            else:
+                _lib.check(_lib.lib().cvf_ae_step_target(F.data_ptr(), target.data_ptr(), weight.data_ptr(), F.shape[0],
+                                                         C.byref(self.mlp), params.data_ptr(), buf.data_ptr(), gptr, ws,
+                                                         self.ws_bytes, _stream()), "cvf_ae_step_target")
         return buf
 
 
-class _AELoss(torch.autograd.Function):
-    """weighted MSE (reference core.py:652-666) with its parameter gradient computed in the same pass."""
-
-    @staticmethod
-    def forward(ctx, actx, F, weight, want_grad, *params):
-        with torch.cuda.device(actx.device):
-            buf = actx.step(F, weight, want_grad)
-            allreduce_sum_(buf)
-        ctx.actx, ctx.buf, ctx.want_grad = actx, buf, want_grad
-        return (buf[0] / buf[1]).to(torch.float32)
-
-    @staticmethod
-    def backward(ctx, g_loss):
-        if not ctx.want_grad:
-            raise RuntimeError("weighted_MSE_loss was evaluated without gradients (torch.no_grad or frozen parameters)")
-        buf = ctx.buf
-        g32 = (buf[2:] * (g_loss.to(torch.float64) / buf[1])).to(torch.float32)
-        return (None, None, None, None) + ctx.actx.flat.split(g32)
+@torch.library.custom_op("cvf::ae_sums", mutates_args=())
+def ae_sums_op(F: torch.Tensor, target: Optional[torch.Tensor], w: torch.Tensor, params: torch.Tensor, want_grad: bool,
+               handle: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    actx = _context(handle)
+    if params.numel() != actx.n_params or params.dtype != torch.float32 or not params.is_contiguous():
+        raise RuntimeError(f"cvf::ae_sums: params must be a contiguous float32 vector of {actx.n_params} entries")
+    buf = actx.step(F, target, w, params, want_grad)
+    allreduce_sum_(buf)
+    return buf[:2].clone(), buf[2:].clone()
 
 
-def ae_loss(actx: AEContext, F, weight):
-    F, weight = _check_batch(F, weight, "AutoEncoderTask.weighted_MSE_loss")
+@ae_sums_op.register_fake
+def _(F, target, w, params, want_grad, handle):
+    return F.new_empty((2,), dtype=torch.float64), F.new_empty((params.numel(),), dtype=torch.float64)
+
+
+def _ae_sums_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+    ctx.set_materialize_grads(False)
+    ctx.want_grad = inputs[4]
+
+
+def _ae_sums_backward(ctx, g_sums, g_gsum):
+    if g_sums is None:
+        return None, None, None, None, None, None
+    if not ctx.want_grad:
+        raise RuntimeError("weighted_MSE_loss was evaluated without gradients (torch.no_grad or frozen parameters)")
+    gsum, = ctx.saved_tensors
+    return None, None, None, (g_sums[0] * gsum).to(torch.float32), None, None
+
+
+ae_sums_op.register_autograd(_ae_sums_backward, setup_context=_ae_sums_setup)
+
+
+def ae_loss(actx: AEContext, F, weight, target=None):
+    """weighted MSE (reference core.py:652-666; with a target, core.py:876-887); its parameter gradient is formed in the same pass."""
+    F, weight = _check_batch(F, weight, "weighted_MSE_loss")
     if F.dim() != 2 or F.shape[1] != actx.d_r:
         raise RuntimeError(f"autoencoder input must be [B,{actx.d_r}], got {tuple(F.shape)}")
-    actx.flat.check()
+    if target is not None:
+        target, _ = _check_batch(target, weight, "weighted_MSE_loss (target)")
+        if target.shape != F.shape:
+            raise RuntimeError(f"reconstruction target has shape {tuple(target.shape)}, the input {tuple(F.shape)}")
     want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in actx.flat.params)
-    return _AELoss.apply(actx, F, weight, want_grad, *actx.flat.params)
+    sums, _ = ae_sums_op(F, target, weight, actx.packed_params(), want_grad, actx.handle)
+    return (sums[0] / sums[1]).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------------------ alignment
+@torch.library.custom_op("cvf::align_fwd", mutates_args=())
+def align_fwd_op(x: torch.Tensor, ref: torch.Tensor, align_idx: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().cvf_align_fwd(x.data_ptr(), x.shape[0], x.shape[1], align_idx.data_ptr(), align_idx.numel(),
+                                            ref.data_ptr(), y.data_ptr(), None, None, _stream()), "cvf_align_fwd")
+    return y
+
+
+@align_fwd_op.register_fake
+def _(x, ref, align_idx):
+    return torch.empty_like(x)

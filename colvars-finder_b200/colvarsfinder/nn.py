@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import re
 
+import numpy as np
 import torch
 
 
@@ -79,6 +80,70 @@ class AutoEncoder(torch.nn.Module):
 
     def forward(self, inp):
         return self.decoder(self.encoder(inp))
+
+
+class RegAutoEncoder(torch.nn.Module):
+    """Regularised autoencoder: encoder, decoder and K regulariser networks on the encoded variables
+    (reference nn.py:116-203).  ``state_dict`` keys ``encoder.{j}.*``, ``decoder.{j}.*``, ``reg.{i}.{j}.*``."""
+
+    def __init__(self, e_layer_dims, d_layer_dims, reg_layer_dims, K, activation=torch.nn.Tanh()):
+        super().__init__()
+        assert e_layer_dims[-1] == d_layer_dims[0], "ouput dimension of encoder and input dimension of decoder do not match!"
+        self.num_reg = K
+        assert self.num_reg == 0 or e_layer_dims[-1] == reg_layer_dims[0], \
+            "ouput dimension of encoder and input dimension of regulator part do not match!"
+        self.encoder = create_sequential_nn(e_layer_dims, activation)
+        self.decoder = create_sequential_nn(d_layer_dims, activation)
+        self.encoded_dim = e_layer_dims[-1]
+        self._num_encoder_layer = len(e_layer_dims) - 1
+        if self.num_reg > 0:
+            self.reg = torch.nn.ModuleList([create_sequential_nn(reg_layer_dims, activation) for _ in range(self.num_reg)])
+        else:
+            self.reg = None
+
+    def get_params_of_cv(self, cv_idx):
+        """[name, parameter] pairs of the encoder; the last layer is cut down to row cv_idx."""
+        assert 0 <= cv_idx < self.encoded_dim, f"index {cv_idx} exceeded the range [0, {self.encoded_dim-1}]!"
+        out = []
+        for name, param in self.encoder.named_parameters():
+            if int(re.search(r'\d+', name).group()) < self._num_encoder_layer:
+                out.append([name, param])
+            else:
+                out.append([name, param[cv_idx:cv_idx + 1, ...]])
+        return out
+
+    def forward_ae(self, inp):
+        return self.decoder(self.encoder(inp))
+
+    def forward_reg(self, inp):
+        assert self.num_reg > 0, 'number of regularizers is not positive.'
+        encoded = self.encoder(inp)
+        return torch.cat([f(encoded) for f in self.reg], dim=1)
+
+    def forward(self, inp):
+        encoded = self.encoder(inp)
+        return torch.cat((self.decoder(encoded), torch.cat([f(encoded) for f in self.reg], dim=1)), dim=1)
+
+
+class RegModel(torch.nn.Module):
+    """The regularisers of a :class:`RegAutoEncoder` as functions of the input, reordered by ``cvec``
+    (reference nn.py:205-239).  Shares the encoder / regulariser modules with ``reg_ae``."""
+
+    def __init__(self, reg_ae, cvec):
+        super().__init__()
+        assert reg_ae.num_reg > 0, 'number of regularizers is not positive.'
+        assert len(cvec) == reg_ae.num_reg, 'length of cvec doesn\'t equal to number of regularizers'
+        assert (np.sort(np.asarray([int(c) for c in cvec])) == np.arange(reg_ae.num_reg)).all(), \
+            f'cvec should be a permutation of 0,1,...,{len(cvec)-1}.'
+        self.encoder = reg_ae.encoder
+        self.reg = reg_ae.reg
+        self.cvec = cvec
+        self.encoded_dim = reg_ae.encoded_dim
+        self.num_reg = reg_ae.num_reg
+
+    def forward(self, inp):
+        encoded = self.encoder(inp)
+        return torch.cat([self.reg[int(idx)](encoded) for idx in self.cvec], dim=1)
 
 
 class EigenFunctions(torch.nn.Module):

@@ -135,7 +135,10 @@ class Align(torch.nn.Module):
             raise RuntimeError(f"Align expects [B,N,3], got {tuple(x.shape)}")
         if out is not None and (out.shape != x.shape or out.dtype != torch.float32 or out.device != x.device or not out.is_contiguous()):
             raise RuntimeError("Align: out must be a contiguous float32 tensor of the input's shape on the input's device")
-        y = torch.empty_like(x) if out is None else out
+        if out is None:
+            from . import _ops      # registers the cvf:: operators
+            return torch.ops.cvf.align_fwd(x, self.ref_pos, self.align_idx)
+        y = out
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().cvf_align_fwd(x.data_ptr(), x.shape[0], x.shape[1], self.align_idx.data_ptr(),
                                                 self.align_idx.numel(), self.ref_pos.data_ptr(), y.data_ptr(), None,

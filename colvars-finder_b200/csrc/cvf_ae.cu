@@ -52,7 +52,7 @@ static size_t ae_layout(AePlan* P, int F) {
 
 template <bool GRAD, int FPL>
 __global__ void __launch_bounds__(384, 1)
-ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restrict__ w, long long B,
+ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restrict__ target, const float* __restrict__ w, long long B,
           const float* __restrict__ params, double* __restrict__ partial) {
   extern __shared__ __align__(16) float smem[];
   const NetPlan& np = P.net;
@@ -140,8 +140,11 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
       const float* O = rows + P.a_row[L] * FS;
       float* S = rows + P.s_row[L] * FS;
       double e = 0.0;
+      // reconstruction target: the input itself, or (time-lagged autoencoder, RegAutoEncoderTask.weighted_MSE_loss,
+      // core.py:876-887) the features of another frame, read row-wise from global memory
+      const float* T = target != nullptr && f_base + f < B ? target + (size_t)(f_base + f) * dL : nullptr;
       for (int o = 0; o < dL; ++o) {
-        const float d = O[o * FS + f] - X[o * FS + f];
+        const float d = O[o * FS + f] - (T ? __ldg(T + o) : X[o * FS + f]);
         e += (double)d * (double)d;
         if (GRAD) S[o * FS + f] = 2.0f * wf * d;
       }
@@ -268,8 +271,8 @@ extern "C" size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B) {
   return general;
 }
 
-extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
-                           double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream_) {
+static int ae_step_impl(const float* feat, const float* target, const float* w, int64_t B, const cvf_mlp* net, const float* params,
+                        double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   AePlan P;
   const int path = ae_path(net, &P);
@@ -278,8 +281,18 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
     set_error("cvf_ae_step: null pointer or empty batch");
     return CVF_E_ARG;
   }
+  if (target == feat) target = nullptr;
+  if (target != nullptr && path == 0) {
+    set_error("cvf_ae_step_target: a separate reconstruction target needs a chain that fits shared memory");
+    return CVF_E_UNSUPPORTED;
+  }
+  if (target != nullptr && P.net.dims[P.net.L] != P.net.dims[0]) {
+    set_error("cvf_ae_step_target: output width %d differs from the feature width %d", P.net.dims[P.net.L], P.net.dims[0]);
+    return CVF_E_ARG;
+  }
   if (path == 0) return wide_ae_step(P.net, feat, w, B, params, sums_out, grad_out, workspace, workspace_bytes, stream);
-  if (fast_ae_supported(P.net)) return fast_ae_step(P.net, feat, w, B, params, sums_out, grad_out, workspace, workspace_bytes, stream);
+  if (target == nullptr && fast_ae_supported(P.net))
+    return fast_ae_step(P.net, feat, w, B, params, sums_out, grad_out, workspace, workspace_bytes, stream);
   const bool grad = grad_out != nullptr;
   const int n_part = 2 + (grad ? P.net.n_params : 0);
   const long long n_tiles = (B + P.F - 1) / P.F;
@@ -291,10 +304,10 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
   }
   if (grad) {
     CVF_CUDA(cudaFuncSetAttribute(ae_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    CVF_LAUNCH(K_AE_STEP, stream, ae_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace));
+    CVF_LAUNCH(K_AE_STEP, stream, ae_kernel<true, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, target, w, B, params, (double*)workspace));
   } else {
     CVF_CUDA(cudaFuncSetAttribute(ae_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes));
-    CVF_LAUNCH(K_AE_STEP, stream, ae_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, w, B, params, (double*)workspace));
+    CVF_LAUNCH(K_AE_STEP, stream, ae_kernel<false, 2><<<grid, P.nthreads, P.smem_bytes, stream>>>(P, feat, target, w, B, params, (double*)workspace));
   }
   CVF_CUDA(cudaGetLastError());
   // partial layout per CTA: [sum w|e|^2, sum w, grad...]; two reductions keep the output buffers separate
@@ -304,6 +317,17 @@ extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const c
                                                                              P.net.n_params, grad_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
+                           double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return ae_step_impl(feat, nullptr, w, B, net, params, sums_out, grad_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cvf_ae_step_target(const float* feat, const float* target, const float* w, int64_t B, const cvf_mlp* net,
+                                  const float* params, double* sums_out, double* grad_out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  return ae_step_impl(feat, target, w, B, net, params, sums_out, grad_out, workspace, workspace_bytes, stream);
 }
 
 extern "C" int cvf_ae_set_wide_path(int32_t mode) {

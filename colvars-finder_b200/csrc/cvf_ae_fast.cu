@@ -11,6 +11,7 @@
 //            with the accumulators in registers (4 x 12 per lane); the seven layers are packed into "types" of at most 32
 //            lanes, a pair of warps shares two cp.async staging buffers per type and run of tiles
 // Sums have one owner each (per-warp fp64 blocks, folded in a fixed order): the result is deterministic.
+#include <atomic>
 #include <string.h>
 
 #include "cvf_common.cuh"
@@ -632,7 +633,7 @@ static int dw_pairs(int rows_buf) {
 
 }  // namespace aefast
 
-static int g_ae_fast_mode = 0;   // 0: use the fast kernels when the shape allows, 1: never
+static std::atomic<int> g_ae_fast_mode{0};   // 0: use the fast kernels when the shape allows, 1: never
 
 int fast_ae_set_mode(int mode) {
   if (mode != 0 && mode != 1) return CVF_E_ARG;

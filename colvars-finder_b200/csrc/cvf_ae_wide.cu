@@ -16,6 +16,7 @@
 // Every matrix the products touch lives in the caller's workspace with a leading dimension padded to a multiple of 4 floats
 // and zero padding, so all global accesses are aligned 128-bit.  Activation buffers carry one extra column of ones, which
 // turns the bias gradient into the last column of the weight-gradient product.
+#include <atomic>
 #include <string.h>
 
 #include "cvf_common.cuh"
@@ -317,7 +318,7 @@ static void make_plan(const NetPlan& np, WidePlan* P) {
 }
 
 constexpr int kMaxSplits = 32;
-int g_wide_mode = 0;   // 0: tensor-core products (tcgen05, 3 x TF32; default), 1: fp32 SIMT products
+std::atomic<int> g_wide_mode{0};   // 0: tensor-core products (tcgen05, 3 x TF32; default), 1: fp32 SIMT products
 
 static int launch_gemm(const Gemm& g, int splits, cudaStream_t stream) {
   if (g_wide_mode == 0) return launch_gemm_tc(g, splits, stream);

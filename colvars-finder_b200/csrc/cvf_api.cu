@@ -1,6 +1,9 @@
 // cvf_api.cu -- version, error reporting and device queries of libcvf_sm100.so.
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "cvf_common.cuh"
 
 namespace cvf {
@@ -38,8 +41,9 @@ static int device_attr(int* cache, cudaDeviceAttr attr, int fallback) {
 static const char* const g_kernel_names[K_COUNT] = {
     "align_fwd", "features_fwd", "eigen_stats(general)", "eigen_grad(general)", "eigen_combine", "reduce_partials", "ae_step",
     "fast_pack", "fast_prep", "fast_pass1", "fast_stats", "fast_pass2a", "fast_pass2b(dW1)", "fma_probe", "fast_jjt", "ae_fast_prep", "ae_fast_main", "ae_fast_dw"};
-static long long g_launches[K_COUNT];
-static int g_prof_on = 0;
+static std::atomic<long long> g_launches[K_COUNT];
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mutex;   // guards g_recs / g_n_recs (timed launches are a profiling mode, not the hot path)
 struct ProfRec {
   int id;
   cudaEvent_t e0, e1;
@@ -48,15 +52,19 @@ static ProfRec g_recs[4096];
 static int g_n_recs = 0;
 
 void prof_begin(int id, cudaStream_t stream) {
-  ++g_launches[id];
-  if (!g_prof_on || g_n_recs >= 4096) return;
+  g_launches[id].fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (g_n_recs >= 4096) return;
   ProfRec& r = g_recs[g_n_recs];
   r.id = id;
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
   cudaEventRecord(r.e0, stream);
 }
 void prof_end(int id, cudaStream_t stream) {
-  if (!g_prof_on || g_n_recs >= 4096 || g_recs[g_n_recs].id != id) return;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (g_n_recs >= 4096 || g_recs[g_n_recs].id != id) return;
   cudaEventRecord(g_recs[g_n_recs].e1, stream);
   ++g_n_recs;
 }
@@ -68,8 +76,14 @@ int max_smem_optin() { return device_attr(g_smem, cudaDevAttrMaxSharedMemoryPerB
 
 extern "C" int cvf_version(void) { return CVF_VERSION; }
 
+#ifndef CVF_SOURCE_HASH
+#define CVF_SOURCE_HASH "unstamped"
+#endif
+static const char g_source_stamp[] = "CVF_SOURCE_HASH=" CVF_SOURCE_HASH;
+extern "C" const char* cvf_source_hash(void) { return g_source_stamp + 16; }
+
 extern "C" int cvf_profile_enable(int32_t on) {
-  cvf::g_prof_on = on ? 1 : 0;
+  cvf::g_prof_on.store(on ? 1 : 0);
   return 0;
 }
 extern "C" int32_t cvf_profile_num_kernels(void) { return cvf::K_COUNT; }
@@ -80,7 +94,8 @@ extern "C" int cvf_profile_read(double* ms_out, int64_t* timed_out, int64_t* lau
     set_error("cvf_profile_read: null pointer");
     return CVF_E_ARG;
   }
-  for (int i = 0; i < K_COUNT; ++i) ms_out[i] = 0.0, timed_out[i] = 0, launches_out[i] = g_launches[i];
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (int i = 0; i < K_COUNT; ++i) ms_out[i] = 0.0, timed_out[i] = 0, launches_out[i] = g_launches[i].load();
   for (int i = 0; i < g_n_recs; ++i) {
     float ms = 0.f;
     if (cudaEventSynchronize(g_recs[i].e1) == cudaSuccess && cudaEventElapsedTime(&ms, g_recs[i].e0, g_recs[i].e1) == cudaSuccess) {
@@ -92,7 +107,7 @@ extern "C" int cvf_profile_read(double* ms_out, int64_t* timed_out, int64_t* lau
   }
   g_n_recs = 0;
   if (reset)
-    for (int i = 0; i < K_COUNT; ++i) g_launches[i] = 0;
+    for (int i = 0; i < K_COUNT; ++i) g_launches[i].store(0);
   return 0;
 }
 extern "C" const char* cvf_last_error_string(void) { return cvf::g_err; }

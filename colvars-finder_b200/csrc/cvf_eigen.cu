@@ -11,6 +11,7 @@
 // One persistent CTA per SM walks over tiles of F frames.  See cvf_common.cuh for the row layout.  The k
 // networks are processed one after the other inside a tile so that one network's state
 // (activations A, adjoints G, tangents T, second adjoints S) fits in shared memory next to the frame.
+#include <atomic>
 #include <math.h>
 #include <string.h>
 
@@ -27,7 +28,7 @@ int fast_eigen_stats(const cvf_preproc* pp, const NetPlan& np, int k, const floa
 int fast_eigen_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float* x, const float* w, long long B,
                     const float* params, const double* combine, const float* seed_extra, double* grad_out, void* workspace,
                     size_t ws_bytes, int scratch_valid, cudaStream_t stream);
-static int g_eigen_path = 0;   // 0: fast path whenever it applies, 1: always the general row-engine kernels
+static std::atomic<int> g_eigen_path{0};   // 0: fast path whenever it applies, 1: always the general row-engine kernels
 
 // Optional per-phase cycle counters (profiling builds only: -DCVF_PHASE_TIMERS, see profiles/phase_timing.py).
 #ifdef CVF_PHASE_TIMERS
@@ -188,7 +189,7 @@ static size_t layout_plan(EigenPlan* P, int F, bool pos_alias) {
   // floats
   int off = 0;
   P->off_params = off, off += P->k * np.smem_floats;
-  P->off_comb = off, off += round4(2 * (3 + 4 * P->k + P->k * P->k));    // combine vector as doubles
+  P->off_comb = off, off += round4(2 * (3 + 5 * P->k + P->k * P->k));    // combine vector as doubles
   P->off_red = off, off += 2 * 4 * P->n_stats;   // warp-reduction scratch: n_stats x 4 warps, doubles
   off = (off + 3) & ~3;
   P->off_rows = off, off += P->n_rows * P->FS;
@@ -523,7 +524,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
   const int n_part = GRAD ? k * np.n_params : P.n_stats;
   double* part = partial + (size_t)blockIdx.x * n_part;
   if (GRAD) {
-    const int nc = 3 + 4 * k + k * k;
+    const int nc = 3 + 5 * k + k * k;
     for (int i = tid; i < nc; i += nt) comb[i] = combine[i];
     for (int i = tid; i < n_part; i += nt) part[i] = 0.0;
   }
@@ -531,10 +532,11 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
   PT_DECL;
   __syncthreads();
   PT_MARK(10);
-  // combine vector layout: loss, obj, pen, eig[k], cvec[k], mean[k], cD[k], C2[k*k]
+  // combine vector layout: loss, obj, pen, eig[k], cvec[k], mean[k], cD[k], C2[k*k], a0[k]
   const double* c_mean = comb + 3 + 2 * k;
   const double* c_cD = comb + 3 + 3 * k;
   const double* c_C2 = comb + 3 + 4 * k;
+  const double* c_a0 = comb + 3 + 4 * k + k * k;
   const int fl = P.kind == 0 ? P.dim : 3 * P.n_atoms;
 
   const long long n_tiles = (B + F - 1) / F;
@@ -634,7 +636,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
         if (GRAD) {
           const float wf = rows[P.row_w * FS + f];
           scale = (float)(2.0 * (double)wf * c_cD[n]);
-          double s = 0.0;
+          double s = c_a0[n];
           for (int j = 0; j < k; ++j) s += c_C2[n * k + j] * ((double)rows[(P.row_y + j) * FS + f] - c_mean[j]);
           float sd = (float)((double)wf * s);
           if (seed_extra != nullptr && f_base + f < B) sd += seed_extra[(size_t)n * B + f_base + f];   // transfer-operator term
@@ -825,6 +827,7 @@ __global__ void eigen_combine_kernel(const double* __restrict__ S, int k, double
     out[3 + k + r] = (double)cvec[r];
     out[3 + 2 * k + r] = mean[r];
     out[3 + 3 * k + r] = omega[r] / (beta * S0 * var[r]);
+    out[3 + 4 * k + k * k + r] = 0.0;   // a0
   }
 }
 
@@ -950,7 +953,8 @@ __global__ void tlag_combine_kernel(const double* __restrict__ S, const double* 
     out[3 + 2 * k + r] = mean[r], out[3 + 3 * k + r] = 0.0;
     out_lag[3 + r] = eig[cvec[r]], out_lag[3 + k + r] = (double)cvec[r];
     out_lag[3 + 2 * k + r] = meanl[r], out_lag[3 + 3 * k + r] = 0.0;
-    out[3 + 4 * k + k * k + r] = 2.0 * a[r];   // E
+    out[3 + 4 * k + k * k + r] = 0.0, out_lag[3 + 4 * k + k * k + r] = 0.0;   // a0
+    out[3 + 5 * k + k * k + r] = 2.0 * a[r];   // E
   }
   out_lag[0] = out[0], out_lag[1] = out[1], out_lag[2] = out[2];
 }
@@ -971,7 +975,7 @@ extern "C" int cvf_debug_phase_cycles(unsigned long long* out16, int reset) {
 #endif
 
 extern "C" int32_t cvf_eigen_num_stats(int32_t k) { return 1 + 2 * k + k * k; }
-extern "C" int32_t cvf_eigen_num_combine(int32_t k) { return 3 + 4 * k + k * k; }
+extern "C" int32_t cvf_eigen_num_combine(int32_t k) { return 3 + 5 * k + k * k; }
 
 extern "C" size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k, int64_t B) {
   NetPlan np;

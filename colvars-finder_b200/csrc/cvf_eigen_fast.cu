@@ -992,8 +992,8 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   const int drp = P.d_rp, d_r = P.d_r, k = P.k;
   float* wsm = sm;                                   // k * img2 (pass-2 prefix of every image)
   float* geo = wsm + k * P.img2_floats;
-  double* comb = reinterpret_cast<double*>(geo + P.geo_floats);   // mean[k], cD[k], C2[k*k]
-  const int n_comb = 2 * k + k * k;
+  double* comb = reinterpret_cast<double*>(geo + P.geo_floats);   // mean[k], cD[k], C2[k*k], a0[k]
+  const int n_comb = 3 * k + k * k;
   float* rows0 = reinterpret_cast<float*>(comb + n_comb + (n_comb & 1));
   float* Zr = rows0 + (size_t)warp * rows_per_warp * RP;   // [NH][2H] A_l | T_l
   float* Xr = Zr + 2 * NH * H * RP;                        // [2H]     s_l | G_l; flush buffer
@@ -1013,6 +1013,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   const double* c_mean = comb;
   const double* c_cD = comb + k;
   const double* c_C2 = comb + 2 * k;
+  const double* c_a0 = comb + 2 * k + k * k;
 
   const long long n_tiles = P.Bp / 32;
   for (long long t = (long long)blockIdx.x * nw + warp; t < n_tiles; t += (long long)gridDim.x * nw) {
@@ -1043,7 +1044,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       }
       float seed;
       {
-        double s = 0.0;
+        double s = c_a0[n];
 #pragma unroll
         for (int j = 0; j < kMaxK; ++j)
           if (j < k) s += c_C2[n * k + j] * ((double)ysv[j] - c_mean[j]);
@@ -1424,7 +1425,7 @@ static int pass2_rows_per_warp(int drp, int H, int NH) {
   return (need > stage ? need : stage) + (pass2_inline_dw1(drp) ? 2 * drp : 0);
 }
 static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH, int warps) {
-  const int n_comb = 2 * k + k * k;
+  const int n_comb = 3 * k + k * k;
   return ((size_t)k * img2_floats + geo_floats) * sizeof(float) + (size_t)(n_comb + (n_comb & 1)) * sizeof(double) +
          (size_t)warps * pass2_rows_per_warp(drp, H, NH) * kRowPad * sizeof(float);
 }

@@ -8,7 +8,9 @@
  *
  * Conventions
  *   - all data pointers are DEVICE pointers owned by the caller (PyTorch's caching allocator); the
- *     library allocates nothing on the device and keeps no state between calls;
+ *     library allocates nothing on the device.  The compute entry points keep no state between calls; the only process-wide
+ *     state is the three testing switches (cvf_eigen_set_path, cvf_ae_set_fast_path, cvf_ae_set_wide_path: atomic ints, read
+ *     once per call) and the launch accounting of cvf_profile_* (mutex-protected; meant for one profiling thread);
  *   - the descriptor structs (cvf_preproc, cvf_mlp) are HOST structs passed by pointer; the index /
  *     coefficient arrays they point to live on the device;
  *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no hidden sync;
@@ -79,6 +81,9 @@ typedef struct cvf_mlp {
 } cvf_mlp;
 
 int cvf_version(void);
+/* hash of the sources this binary was compiled from (csrc/, include/cvf.h, compile flags), stamped by __graft_entry__.build();
+ * "unstamped" for a build made by hand */
+const char* cvf_source_hash(void);
 const char* cvf_last_error_string(void);
 /* sizeof(cvf_preproc) / sizeof(cvf_mlp) as this library was compiled: lets a binding check its own struct layout */
 size_t cvf_sizeof_preproc(void);
@@ -100,7 +105,11 @@ int cvf_features_fwd(const float* x, int64_t B, const cvf_preproc* pp, float* r_
 
 /* doubles in the stats vector: S0, S1[k], S2[k*k], SD[k] */
 int32_t cvf_eigen_num_stats(int32_t k);
-/* doubles in the combine vector: loss, obj, pen, eig[k] (sorted), cvec[k], mean[k], cD[k], C2[k*k] */
+/* doubles in the combine vector: loss, obj, pen, eig[k] (sorted), cvec[k], mean[k], cD[k], C2[k*k], a0[k].
+ * The last four blocks are the coefficients of pass 2: for frame f and network i the seed d loss / d y_i is
+ * w_f (a0_i + sum_j C2_ij (y_j - mean_j)) and the Dirichlet term enters with weight 2 w_f cD_i.  cvf_eigen_combine writes
+ * a0 = 0 (its loss depends on S1, S2 only through central moments); a caller that differentiates another function of the
+ * batch sums fills the vector itself (colvarsfinder/_ops.py: cvf::eigen_stats backward). */
 int32_t cvf_eigen_num_combine(int32_t k);
 /* bytes of scratch needed by cvf_eigen_stats / cvf_eigen_grad on a batch of B frames: per-CTA partial sums and, on the
  * fast path, the frame-minor intermediates pass 1 leaves for pass 2 (aligned frames, grad_r y, Jacobian vectors). */
@@ -152,6 +161,13 @@ size_t cvf_ae_workspace_bytes(const cvf_mlp* net, int64_t B);
  * gradient of the FIRST sum (not yet divided by sum w).  grad_out may be NULL (evaluation only). */
 int cvf_ae_step(const float* feat, const float* w, int64_t B, const cvf_mlp* net, const float* params,
                 double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same with a separate reconstruction target: sum_f w_f |dec(enc(F_f)) - T_f|^2 with T [B, d] (the time-lagged
+ * autoencoder loss of RegAutoEncoderTask.weighted_MSE_loss, core.py:876-887, where T = pp(X_lagged)).  target == NULL or
+ * target == feat is cvf_ae_step; otherwise the chain must fit shared memory (general kernel). */
+int cvf_ae_step_target(const float* feat, const float* target, const float* w, int64_t B, const cvf_mlp* net,
+                       const float* params, double* sums_out, double* grad_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /* testing / profiling switch for chains that fit shared memory: 0 = the thread-private kernels (cvf_ae_fast.cu) when the chain
  * is encoder [d,20,20,20,e] + decoder [e,10,10,d], e = 1..3, d <= 72 (default); 1 = always the general row-engine kernel */

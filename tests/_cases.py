@@ -8,6 +8,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 EIGEN_GENERATOR_CASES = ["eigen_2d_k1", "eigen_2d_k3_diag", "eigen_2d_k2_nosort", "eigen_dipep_k3",
                          "eigen_dipep_subset_diag", "eigen_dipep_features", "eigen_dipep_invariant"]
 AE_CASES = ["ae_2d", "ae_dipep"]
+REGAE_CASES = ["regae_2d_generator", "regae_2d_lagged", "regae_2d_lagged_k2_frozen", "regae_dipep_generator"]
 
 
 def load(name):
@@ -41,6 +42,29 @@ def ae_case(name):
                 g32_enc=[d[f"g32_enc_{j}"] for j in range(2 * ne)], g64_enc=[d[f"g64_enc_{j}"] for j in range(2 * ne)],
                 g32_dec=[d[f"g32_dec_{j}"] for j in range(2 * nd)], g64_dec=[d[f"g64_dec_{j}"] for j in range(2 * nd)],
                 r32_loss=float(d["r32_loss"]), g64_loss=float(d["g64_loss"]))
+
+
+def regae_case(name):
+    """Golden vectors of RegAutoEncoderTask written by oracle/gen_golden_regae.py."""
+    d = load(name)
+    K = int(d["K"])
+    ne, nd, nr = len(d["e_dims"]) - 1, len(d["d_dims"]) - 1, len(d["r_dims"]) - 1
+    c = dict(X=d["X"], w=d["w"], K=K, e_dims=[int(v) for v in d["e_dims"]], d_dims=[int(v) for v in d["d_dims"]],
+             r_dims=[int(v) for v in d["r_dims"]], eig_w=[float(v) for v in d["eig_w"]], alpha=float(d["alpha"]),
+             gamma=[float(v) for v in d["gamma"]], eta=[float(v) for v in d["eta"]], lag_tau_ae=float(d["lag_tau_ae"]),
+             lag_tau_reg=float(d["lag_tau_reg"]), beta=float(d["beta"]), dt=float(d["dt"]), freeze=bool(d["freeze"]),
+             pp_kind=str(d["pp_kind"]), ref=d.get("ref"), align_idx=d.get("align_idx"))
+    c["enc"] = [d[f"enc_{j}"] for j in range(2 * ne)]
+    c["dec"] = [d[f"dec_{j}"] for j in range(2 * nd)]
+    c["reg"] = [[d[f"reg_{i}_{j}"] for j in range(2 * nr)] for i in range(K)]
+    for tag in ("g32", "g64"):
+        c[f"{tag}_enc"] = [d[f"{tag}_enc_{j}"] for j in range(2 * ne)]
+        c[f"{tag}_dec"] = [d[f"{tag}_dec_{j}"] for j in range(2 * nd)]
+        c[f"{tag}_reg"] = [[d[f"{tag}_reg_{i}_{j}"] for j in range(2 * nr)] for i in range(K)]
+    for tag in ("r32", "g64"):
+        for f in ("loss", "ae", "g0", "g1", "e0", "e1", "e2", "eig", "cvec"):
+            c[f"{tag}_{f}"] = d[f"{tag}_{f}"]
+    return c
 
 
 def rel_l2(a, b):

@@ -11,6 +11,13 @@ for p in (ROOT, os.path.join(ROOT, "colvars-finder_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the oracle's numpy products are small: OpenBLAS with one thread per visible core spends its time spinning (100x slower
+    # in a CPU-limited container)
+    try:
+        import threadpoolctl
+        config._cvf_blas_limit = threadpoolctl.threadpool_limits(limits=4, user_api="blas")
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -63,3 +63,31 @@ def test_two_rank_step_matches_single_rank(tmp_path):
     np.testing.assert_allclose(r0["eig"], c["g64_eig"], rtol=1e-9)
     gold = np.concatenate([g.ravel() for net in c["g64"] for g in net])
     assert C.rel_l2(r0["grad"], gold) < 1e-8
+
+
+def _plan_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from colvarsfinder import _ops, core
+        from sklearn.model_selection import train_test_split
+        # 100 000 frames with lag 1 on 2 ranks: shards of 50 000 and 49 999 frames -> 40 000 / 39 999 training frames
+        n = 100000 - 1
+        lo, hi = _ops.shard_range(n, rank, world)
+        tr, te = train_test_split(np.arange(hi - lo), test_size=0.2)
+        own = (min(1000, len(tr)), min(1000, len(te)), len(tr) // 1000, len(te) // 1000)
+        plan = core._iteration_plan(len(tr), len(te), 1000)
+        np.savez(os.path.join(out_dir, f"plan{rank}.npz"), own=np.asarray(own), plan=np.asarray(plan))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_iteration_plan_is_identical_on_all_ranks(tmp_path):
+    """Shards that differ by one frame give different per-rank iteration counts (40 vs 39 here); every iteration ends in
+    collectives, so the loop must run the collective minimum on every rank (multi-rank train() could hang)."""
+    port = _free_port()
+    mp.spawn(_plan_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = np.load(tmp_path / "plan0.npz"), np.load(tmp_path / "plan1.npz")
+    assert p0["own"][2] != p1["own"][2]                       # the situation the plan exists for
+    assert np.array_equal(p0["plan"], p1["plan"])
+    assert p0["plan"][2] == min(p0["own"][2], p1["own"][2]) and p0["plan"][3] == min(p0["own"][3], p1["own"][3])

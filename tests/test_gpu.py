@@ -789,6 +789,45 @@ def test_ae_wide_layers_match_oracle(B, mode, tmp_path):
         assert torch.equal(task.weighted_MSE_loss(task._feature_traj, task._weights), loss.detach())
 
 
+@pytest.mark.parametrize("mode", ["tensor_cores", "simt"])
+@pytest.mark.parametrize("B", [4096, 33000])
+def test_ae_c5_shape_matches_oracle(B, mode, tmp_path):
+    """BASELINE config 5 at its real shape, AutoEncoder([3000,512,512,2],[2,512,512,3000]): the 3000-term accumulations are where
+    the dropped lo*lo term of the 3 x TF32 split and the fp32 accumulation in tensor memory would show first.  Same bars as the
+    narrow cases (loss 1e-5, gradients 2e-5 rel-L2 against the fp64 closed form); the achieved errors are printed."""
+    from colvarsfinder import core, nn, _lib
+    _lib.check(_lib.lib().cvf_ae_set_wide_path(0 if mode == "tensor_cores" else 1), "cvf_ae_set_wide_path")
+    try:
+        e_dims, d_dims = [3000, 512, 512, 2], [2, 512, 512, 3000]
+        torch.manual_seed(B)
+        enc = [p.numpy() for p in ref_torch.init_mlp_params(e_dims)]
+        dec = [p.numpy() for p in ref_torch.init_mlp_params(d_dims)]
+        rng = np.random.default_rng(B)
+        # frames of a 1000-atom chain: a common structure plus thermal noise, Angstrom scale (SURVEY 8d, C5)
+        base = np.cumsum(rng.normal(scale=1.5 / np.sqrt(3), size=(1000, 3)), 0)
+        base -= base.mean(0)
+        F = (base.reshape(1, 3000) + rng.normal(scale=0.3, size=(B, 3000))).astype(np.float32)
+        w = ref_torch.boltzmann_weights(B, seed=B)
+        model = nn.AutoEncoder(e_dims, d_dims)
+        with torch.no_grad():
+            for p_, v in zip(model.encoder.parameters(), enc):
+                p_.copy_(torch.as_tensor(v))
+            for p_, v in zip(model.decoder.parameters(), dec):
+                p_.copy_(torch.as_tensor(v))
+        task = core.AutoEncoderTask(FakeTrajectory(F, w.astype(np.float64)), torch.nn.Identity(), model, str(tmp_path), device=DEV,
+                                    verbose=False, debug_mode=False)
+        loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+        loss.backward()
+        lo, genc, gdec = cf.ae_loss_and_grads(F, w, enc, dec)
+        got = [p_.grad.cpu().numpy() for p_ in model.encoder.parameters()] + [p_.grad.cpu().numpy() for p_ in model.decoder.parameters()]
+        errs = [C.rel_l2(g, go) for g, go in zip(got, genc + gdec)]
+        print(f"C5 shape, B={B}, {mode}: loss rel err {abs(float(loss) - lo) / abs(lo):.2e}, gradient rel-L2 max {max(errs):.2e}")
+        assert abs(float(loss) - lo) <= 1e-5 * abs(lo)
+        assert max(errs) < 2e-5, errs
+    finally:
+        _lib.check(_lib.lib().cvf_ae_set_wide_path(0), "cvf_ae_set_wide_path")
+
+
 def test_ae_prepass_and_train_match_reference_run(tmp_path):
     from colvarsfinder import core, nn, utils
     d = C.load("train_ae_2d")

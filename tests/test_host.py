@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name)
     assert lib.cvf_version() == 100
-    assert lib.cvf_eigen_num_stats(3) == 1 + 6 + 9 and lib.cvf_eigen_num_combine(3) == 3 + 12 + 9
+    assert lib.cvf_eigen_num_stats(3) == 1 + 6 + 9 and lib.cvf_eigen_num_combine(3) == 3 + 15 + 9
     m = _lib.make_mlp([66, 20, 20, 20, 1], [1, 1, 1, 0])
     assert lib.cvf_mlp_param_count(C.byref(m)) == 2201
     ae = _lib.make_mlp([66, 20, 2, 20, 66], [1, 0, 1, 0])
@@ -124,6 +124,54 @@ def test_nn_layout_matches_reference_state_dict():
     ref = ref_torch.init_mlp_params([5, 7, 7, 1])
     for a, b in zip(ref, list(m.eigen_funcs[0].parameters())):
         assert torch.equal(a, b.detach())
+
+
+def test_regautoencoder_layout_matches_reference():
+    """nn.RegAutoEncoder / nn.RegModel (reference nn.py:116-239): state_dict keys, attributes, forward shapes, assertions."""
+    from colvarsfinder import nn
+    torch.manual_seed(5)
+    m = nn.RegAutoEncoder([4, 6, 2], [2, 6, 4], [2, 5, 1], 3)
+    keys = list(m.state_dict().keys())
+    assert keys[0] == "encoder.1.weight" and "decoder.2.bias" in keys and "reg.2.2.weight" in keys
+    assert m.num_reg == 3 and m.encoded_dim == 2 and len(m.reg) == 3
+    x = torch.randn(7, 4)
+    assert m.forward_ae(x).shape == (7, 4) and m.forward_reg(x).shape == (7, 3) and m(x).shape == (7, 7)
+    assert [n for n, _ in m.get_params_of_cv(1)] == ["1.weight", "1.bias", "2.weight", "2.bias"]
+    rm = nn.RegModel(m, [2, 0, 1])
+    assert torch.equal(rm(x), m.forward_reg(x)[:, [2, 0, 1]])
+    assert nn.RegAutoEncoder([4, 2], [2, 4], [2, 1], 0).reg is None
+    with pytest.raises(AssertionError):
+        nn.RegAutoEncoder([4, 2], [2, 4], [3, 1], 1)
+    with pytest.raises(AssertionError):
+        nn.RegModel(m, [0, 0, 1])
+    from oracle import ref_import
+    if ref_import.available():      # same construction order -> same state_dict and init stream as the reference class
+        _, rnn, _ = ref_import.load()
+        torch.manual_seed(5)
+        r = rnn.RegAutoEncoder([4, 6, 2], [2, 6, 4], [2, 5, 1], 3)
+        assert list(r.state_dict().keys()) == keys
+        for a, b in zip(r.parameters(), m.parameters()):
+            assert torch.equal(a, b)
+
+
+def test_custom_operators_are_registered():
+    """The step is exposed as torch.library operators (namespace cvf) with fake kernels and autograd formulas."""
+    from colvarsfinder import _ops  # noqa: F401
+    for name in ("eigen_stats", "eigen_grad", "eigen_combine", "eigen_tlag_sx", "eigen_tlag_seed", "eigen_tlag_combine", "ae_sums",
+                 "align_fwd"):
+        assert hasattr(torch.ops.cvf, name), name
+    schema = str(torch.ops.cvf.eigen_stats.default._schema)
+    assert schema.startswith("cvf::eigen_stats(Tensor X, Tensor w, Tensor params, SymInt handle, SymInt slot) -> (Tensor, Tensor)")
+    with pytest.raises(RuntimeError, match="no longer exists"):
+        _ops._context(10 ** 9)
+
+
+def test_device_default_is_the_references_and_raises_clearly(tmp_path):
+    """Signature default device=cpu as in the reference (core.py:311,621,797); without a CUDA device the constructor says so."""
+    import inspect
+    from colvarsfinder import core
+    for cls in (core.EigenFunctionTask, core.AutoEncoderTask, core.RegAutoEncoderTask):
+        assert inspect.signature(cls.__init__).parameters["device"].default == torch.device("cpu")
 
 
 def test_flat_params_alias_module_parameters():
