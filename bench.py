@@ -63,9 +63,10 @@ WORKLOADS = {
 METRIC = "train-step frames/sec"
 # fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
 KERNEL_FLOPS = {
-    ("c3", "fast_pass2a"): 45240, ("c3", "fast_pass1"): 25680, ("c3", "fast_pass2b(dW1)"): 15840,
-    ("c1", "fast_pass2a"): 5240, ("c1", "fast_pass1"): 1760,
-    ("c4", "fast_pass2a"): 48720, ("c4", "fast_pass1"): 29160, ("c4", "fast_pass2b(dW1)"): 19440,
+    # fast_pass2 = primal + tangent forward, reverse sweep of (G, s), every weight-gradient outer product incl. dW_1
+    ("c3", "fast_pass2"): 45240 + 15840, ("c3", "fast_pass1"): 25680,
+    ("c1", "fast_pass2"): 5240, ("c1", "fast_pass1"): 1760,
+    ("c4", "fast_pass2"): 48720 + 19440, ("c4", "fast_pass1"): 29160,
     ("c2", "ae_fast_main"): 9120, ("c2", "ae_fast_dw"): 6176,   # forward P + delta sweep (P - first layer); weight + bias products
 }
 def measured_traffic(workload, kernel, frames):

@@ -73,6 +73,7 @@ __device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long
 }
 
 constexpr int kP1Frames = 512, kP1Threads = 256;
+constexpr int kDw1Chunk = 24;   // columns of dW_1 formed per pass over the warp's 32 frames (pass 2)
 constexpr int kP2MaxWarps = 8, kP2MinWarps = 4;
 
 // Shared-memory image of one network (floats; every block 16-byte aligned because H % 4 == 0 and d_rp % 12 == 0):
@@ -116,9 +117,7 @@ struct FastPlan {
   float* JQ;                     // [k][12][Bp]   gm, q, dc, om
   float* Dq;                     // [k][Bp]
   float* Ys;                     // [k][Bp]
-  float* SG;                     // [k][2H][Bp]   s_1 | scale G_1 (pass 2a -> pass 2b)
   double* part;                  // per-CTA / per-warp partial sums
-  double* part2;                 // pass 2b: per-warp partial [H][d_r] blocks
 };
 
 // geo block (floats): kind 1: refA [d_rp] (reference position of the atom a coordinate belongs to, 0 if not aligned),
@@ -919,6 +918,98 @@ __global__ void __launch_bounds__(256) stats_kernel(const FastPlan P, const floa
   }
 }
 
+
+// ---- tensor memory as per-warp accumulator storage -----------------------------------------------------------------------
+// Pass 2 adds ~2 200 weight-gradient partial sums per (32-frame tile, network) to running totals.  As fp64 atomics to a
+// per-warp vector in global memory those additions were the kernel's largest consumer of load/store-pipe cycles (measured:
+// ~1.3 cycles per lane).  Tensor memory (256 KB per SM, untouched by this SIMT kernel) holds them instead: a warp owns the 32
+// lanes of its quadrant x 256 columns, every lane keeps the totals of the (output, input) pairs it computes anyway in columns
+// of its own lane, and one tcgen05.ld / add / tcgen05.st round trip per group of 16 replaces the atomics (single owner, fixed
+// order: deterministic).  The totals are fp32 over the ~10^2 tiles a warp processes and go to the fp64 vector once, at the end.
+template <int N>
+struct TmIo;
+template <>
+struct TmIo<1> {
+  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[1]) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(a) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(r);
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[1]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(__float_as_uint(v[0])) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+};
+template <>
+struct TmIo<16> {
+  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(a),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+};
+template <>
+struct TmIo<32> {
+  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[32]) {
+    float lo[16], hi[16];
+    TmIo<16>::ld(a, lo);
+    TmIo<16>::ld(a + 16, hi);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = lo[i], v[16 + i] = hi[i];
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[32]) {
+    float lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) lo[i] = v[i], hi[i] = v[16 + i];
+    TmIo<16>::st(a, lo);
+    TmIo<16>::st(a + 16, hi);
+  }
+};
+// totals[a .. a+N) += v
+template <int N>
+__device__ __forceinline__ void tm_add(uint32_t a, const float (&v)[N]) {
+  float t[N];
+  TmIo<N>::ld(a, t);
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] += v[i];
+  TmIo<N>::st(a, t);
+}
+// Lane (half, og, ig) of a warp holds, after the cross-half shuffle, the full sum of every entry r[j][i] of its TO x TI tile; entry
+// e = j * TI + i is kept by the half-warp e & 1, in slot e >> 1 of the group.
+template <int TO, int TI, int GS>
+__device__ __forceinline__ void tm_add_tile(uint32_t a, const float (&r)[TO][TI], int half) {
+  static_assert((TO * TI + 1) / 2 <= GS, "group too small");
+  float v[GS];
+#pragma unroll
+  for (int p = 0; p < GS; ++p) {
+    const int e0 = 2 * p, e1 = 2 * p + 1;
+    const float v0 = e0 < TO * TI ? r[e0 / TI][e0 % TI] : 0.0f;
+    const float v1 = e1 < TO * TI ? r[e1 / TI][e1 % TI] : 0.0f;
+    v[p] = half ? v1 : v0;
+  }
+  tm_add<GS>(a, v);
+}
+__host__ __device__ constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : n <= 16 ? 16 : 32; }
+constexpr int kTmColsPerWarp = 256;
+
 // ------------------------------------------------------------------------------------------------ pass 2
 // lane L ends with sum over lanes of v[L] (v[i >= N] treated as 0); 31 shuffles for up to 32 values.
 template <int N>
@@ -977,10 +1068,11 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
   }
 }
 
-// Pass 2a.  One CTA per SM, up to 8 independent warps; a warp owns tiles of 32 frames (lane = frame) and a private set of
+// Pass 2.  One CTA per SM, up to 8 independent warps; a warp owns tiles of 32 frames (lane = frame) and a private set of
 // operand rows: Z rows (A_l | T_l of every hidden layer; during layer 1 they stage r and u) and X rows (s_l | G_l of the
-// layer being reduced, then the flush buffer).  The first layer's weight gradient needs r and v of every frame as operand
-// rows, which would halve the number of resident warps: (s_1, scale G_1) go to global memory and pass 2b does that product.
+// layer being reduced, then the flush buffer).  The first layer's weight gradient needs r and vhat of every frame as operand
+// rows once (s_1, G_1) exist, when the Z rows are free again: they are re-staged from global memory (L2: the warp read r and
+// wrote vhat a few microseconds earlier) in double-buffered column chunks, so no intermediate of pass 2 goes through HBM.
 template <int H, int NH>
 __global__ void __launch_bounds__(256, 1)
 pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp,
@@ -995,10 +1087,11 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   double* comb = reinterpret_cast<double*>(geo + P.geo_floats);   // mean[k], cD[k], C2[k*k], a0[k]
   const int n_comb = 3 * k + k * k;
   float* rows0 = reinterpret_cast<float*>(comb + n_comb + (n_comb & 1));
-  float* Zr = rows0 + (size_t)warp * rows_per_warp * RP;   // [NH][2H] A_l | T_l
-  float* Xr = Zr + 2 * NH * H * RP;                        // [2H]     s_l | G_l; flush buffer
   const bool inline_dw1 = drp == 12;                       // pass2_inline_dw1(): r and vhat keep rows of their own
-  float* Sr = inline_dw1 ? Xr + 2 * H * RP : Zr;           // [drp]    r staged for layer 1
+  const int base_rows = rows_per_warp - (inline_dw1 ? 2 * drp : 0);
+  float* Zr = rows0 + (size_t)warp * rows_per_warp * RP;   // [NH][2H] A_l | T_l; at the end, two chunk buffers of r | vhat rows
+  float* Xr = Zr + (size_t)(base_rows - 2 * H) * RP;       // [2H]     s_l | G_l; flush buffer (the last rows of the block)
+  float* Sr = inline_dw1 ? Zr + (size_t)base_rows * RP : Zr;   // [drp]    r staged for layer 1
   float* Su = Sr + drp * RP;                               // [drp]    u staged for layer 1
   float* Sj = Zr + 2 * drp * RP;                           // [12]     alignment-Jacobian vectors staged for layer 1
   for (int n = 0; n < k; ++n)
@@ -1009,7 +1102,30 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   const int n_part = k * P.n_params;
   double* part = P.part + ((size_t)blockIdx.x * nw + warp) * n_part;
   for (int i = lane; i < n_part; i += 32) part[i] = 0.0;
+  // tensor-memory accumulators (see above): per network n_chunks groups for dW_1, NH - 1 groups for the hidden layers' dW,
+  // four single slots (dWout | dbout by lane, db_NH .. db_1 by lane)
+  constexpr int CI1 = kDw1Chunk / 4;
+  constexpr int GS1 = pow2_at_least((TQ * CI1 + 1) / 2), GSH = pow2_at_least((TQ * TQ + 1) / 2);
+  const int n_chunks1 = inline_dw1 ? 1 : (d_r + kDw1Chunk - 1) / kDw1Chunk;
+  const int tm_hid = n_chunks1 * GS1, tm_sing = tm_hid + (NH - 1) * GSH, tm_per_net = tm_sing + 4;
+  const int tm_nets = kTmColsPerWarp / tm_per_net < k ? kTmColsPerWarp / tm_per_net : k;   // further networks: fp64 atomics
+  __shared__ uint32_t tmem_slot;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmw = tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTmColsPerWarp * (warp >> 2));
+  {
+    float z16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z16[i] = 0.0f;
+    for (int c = 0; c < kTmColsPerWarp; c += 16) TmIo<16>::st(tmw + c, z16);
+  }
   const double* c_mean = comb;
   const double* c_cD = comb + k;
   const double* c_C2 = comb + 2 * k;
@@ -1026,6 +1142,8 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
     for (int n = 0; n < k; ++n) {
       const float* W = wsm + n * P.img2_floats;
       double* pn = part + (size_t)n * P.n_params;
+      const bool tm = n < tm_nets;                          // this network's totals live in tensor memory
+      const uint32_t tmn = tmw + (uint32_t)(n * tm_per_net);
       float* Ut = P.U + ((size_t)n * drp) * P.Bp + t * 32;
       __syncwarp();   // the previous network's flush has finished reading the X rows
       stage_rows(Sr, P.Y + t * 32, d_r, P.Bp, lane);
@@ -1158,7 +1276,10 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         for (int o = 0; o < H; ++o) red[o] = fmaf(seed, a[o], tg[o]);
         red[H] = seed;
         const float tot = warp_reduce_scatter<H + 1>(red, lane);
-        if (lane < H) atomicAdd(pn + P.gw_off[NH] + lane, (double)tot);
+        if (tm) {
+          const float t1[1] = {tot};
+          tm_add<1>(tmn + tm_sing, t1);
+        } else if (lane < H) atomicAdd(pn + P.gw_off[NH] + lane, (double)tot);
         else if (lane == H) atomicAdd(pn + P.gb_off[NH], (double)tot);
 #pragma unroll
         for (int qq = 0; qq < TQ; ++qq) {
@@ -1182,7 +1303,10 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll
           for (int o = 0; o < H; ++o) red[o] = sl[o];
           const float tot = warp_reduce_scatter<H>(red, lane);
-          if (lane < H) atomicAdd(pn + P.gb_off[l - 1] + lane, (double)tot);
+          if (tm) {
+            const float t1[1] = {tot};
+            tm_add<1>(tmn + tm_sing + 1 + (NH - l), t1);
+          } else if (lane < H) atomicAdd(pn + P.gb_off[l - 1] + lane, (double)tot);
         }
         if (l >= 2) {
           __syncwarp();
@@ -1208,14 +1332,18 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
               r2[j][i] += __shfl_xor_sync(0xffffffffu, r2[j][i], 16);
             }
           __syncwarp();
-          if (half == 0) {
+          if (tm) {
+            tm_add_tile<TQ, TQ, GSH>(tmn + tm_hid + (l - 2) * GSH, r2, half);
+          } else {
+            if (half == 0) {
 #pragma unroll
-            for (int j = 0; j < TQ; ++j)
+              for (int j = 0; j < TQ; ++j)
 #pragma unroll
-              for (int i = 0; i < TQ; ++i) Xr[(4 * j + og) * H + 4 * i + ig] = r2[j][i];
+                for (int i = 0; i < TQ; ++i) Xr[(4 * j + og) * H + 4 * i + ig] = r2[j][i];
+            }
+            __syncwarp();
+            for (int e = lane; e < H * H; e += 32) atomicAdd(pn + P.gw_off[l - 1] + e, (double)Xr[e]);
           }
-          __syncwarp();
-          for (int e = lane; e < H * H; e += 32) atomicAdd(pn + P.gw_off[l - 1] + e, (double)Xr[e]);
           // next (G, s): h = W_l^T (G_l, s_l);  G_{l-1} = om h_G,  s_{l-1} = -2 A h_G T + om h_s
           float2 hg[HP], hs[HP];
 #pragma unroll
@@ -1246,13 +1374,66 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
             }
           }
         } else {
-          // (s_1, scale G_1) of this frame for pass 2b:  dW_1 = sum_f s_1 (x) r + (scale G_1) (x) (v / scale)
+          // dW_1 = sum_f s_1 (x) r + (scale G_1) (x) vhat:  (s_1 | scale G_1) become X rows; r and vhat (the latter was written to
+          // global memory in place of u during layer 1) come back in column chunks of kDw1Chunk rows each, double-buffered in the
+          // Z rows that the reverse sweep no longer needs
           __syncwarp();
 #pragma unroll
           for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = scale * gl[o];
           __syncwarp();
           if (!inline_dw1) {
-            store_rows(P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, Xr, 2 * H, P.Bp, lane);
+            constexpr int CW = kDw1Chunk, CI = CW / 4;      // columns per chunk, columns per lane (4 column groups)
+            const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
+            const int n_chunks = (d_r + CW - 1) / CW;
+            const float* Yt = P.Y + t * 32;
+            auto stage_chunk = [&](int c) {
+              float* R = Zr + (size_t)(c & 1) * 2 * CW * RP;
+              const int c0 = c * CW, nr = d_r - c0 < CW ? d_r - c0 : CW;
+              stage_rows(R, Yt + (size_t)c0 * P.Bp, nr, P.Bp, lane);
+              stage_rows(R + CW * RP, Ut + (size_t)c0 * P.Bp, nr, P.Bp, lane);
+              cp_async_commit();
+            };
+            stage_chunk(0);
+            for (int c = 0; c < n_chunks; ++c) {
+              if (c + 1 < n_chunks) {
+                stage_chunk(c + 1);
+                cp_async_wait_group<1>();
+              } else {
+                cp_async_wait_all();
+              }
+              __syncwarp();
+              const float* R = Zr + (size_t)(c & 1) * 2 * CW * RP;
+              const int c0 = c * CW;
+              float2 acc[TQ][CI];
+#pragma unroll
+              for (int j = 0; j < TQ; ++j)
+#pragma unroll
+                for (int i = 0; i < CI; ++i) acc[j][i] = make_float2(0.f, 0.f);
+              // rows beyond d_r in the last chunk hold stale (finite) values of earlier tiles: their columns are not flushed
+              outer_tile<TQ, CI>(acc, Xr + og * RP, R + (CI * ig) * RP, Xr + (H + og) * RP, R + (CW + CI * ig) * RP, 4 * RP, RP,
+                                 16 * half, 16 * half + 16);
+              // both half-warps end with the sums over all 32 frames; each keeps / flushes half of the entries
+              float r1[TQ][CI];
+#pragma unroll
+              for (int j = 0; j < TQ; ++j)
+#pragma unroll
+                for (int i = 0; i < CI; ++i) {
+                  r1[j][i] = acc[j][i].x + acc[j][i].y;
+                  r1[j][i] += __shfl_xor_sync(0xffffffffu, r1[j][i], 16);
+                }
+              if (tm) {
+                tm_add_tile<TQ, CI, GS1>(tmn + c * GS1, r1, half);
+              } else {
+#pragma unroll
+                for (int j = 0; j < TQ; ++j)
+#pragma unroll
+                  for (int i = 0; i < CI; ++i) {
+                    const int col = c0 + CI * ig + i;
+                    if (((j * CI + i) & 1) == half && col < d_r) atomicAdd(pn + P.gw_off[0] + (4 * j + og) * d_r + col, (double)r1[j][i]);
+                  }
+              }
+              __syncwarp();   // the chunk's buffer is restaged two iterations later; all lanes are done reading it
+            }
           } else {
             // dW_1 [H][d_r <= 12] here: the same half-warp product as the hidden layers, 12 columns
             const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
@@ -1272,141 +1453,79 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
                 r1[j][i] += __shfl_xor_sync(0xffffffffu, r1[j][i], 16);
               }
             __syncwarp();   // every lane has finished reading the X rows
-            if (half == 0) {
+            if (tm) {
+              tm_add_tile<TQ, 3, GS1>(tmn, r1, half);
+            } else {
+              if (half == 0) {
 #pragma unroll
-              for (int j = 0; j < TQ; ++j)
+                for (int j = 0; j < TQ; ++j)
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                  const int col = 4 * i + ig;
-                  if (col < d_r) Xr[(4 * j + og) * d_r + col] = r1[j][i];
-                }
+                  for (int i = 0; i < 3; ++i) {
+                    const int col = 4 * i + ig;
+                    if (col < d_r) Xr[(4 * j + og) * d_r + col] = r1[j][i];
+                  }
+              }
+              __syncwarp();
+              for (int e = lane; e < H * d_r; e += 32) atomicAdd(pn + P.gw_off[0] + e, (double)Xr[e]);
             }
-            __syncwarp();
-            for (int e = lane; e < H * d_r; e += 32) atomicAdd(pn + P.gw_off[0] + e, (double)Xr[e]);
           }
         }
       }
     }
   }
+  // tensor-memory totals -> this warp's fp64 vector (every entry has exactly one owning lane)
+  {
+    const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
+    for (int n = 0; n < tm_nets; ++n) {
+      double* pn = part + (size_t)n * P.n_params;
+      const uint32_t tmn = tmw + (uint32_t)(n * tm_per_net);
+      for (int c = 0; c < n_chunks1; ++c) {
+        float v[GS1];
+        TmIo<GS1>::ld(tmn + c * GS1, v);
+        const int ti = inline_dw1 ? 3 : CI1;
+#pragma unroll
+        for (int p = 0; p < GS1; ++p) {
+          const int e = 2 * p + half;
+          if (e >= TQ * ti) continue;
+          const int j = e / ti, i = e - j * ti;
+          const int col = inline_dw1 ? 4 * i + ig : c * kDw1Chunk + CI1 * ig + i;
+          if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] = (double)v[p];
+        }
+      }
+      for (int l = 2; l <= NH; ++l) {
+        float v[GSH];
+        TmIo<GSH>::ld(tmn + tm_hid + (l - 2) * GSH, v);
+#pragma unroll
+        for (int p = 0; p < GSH; ++p) {
+          const int e = 2 * p + half;
+          if (e >= TQ * TQ) continue;
+          const int j = e / TQ, i = e - j * TQ;
+          pn[P.gw_off[l - 1] + (4 * j + og) * H + 4 * i + ig] = (double)v[p];
+        }
+      }
+      {
+        float v[1];
+        TmIo<1>::ld(tmn + tm_sing, v);
+        if (lane < H) pn[P.gw_off[NH] + lane] = (double)v[0];
+        else if (lane == H) pn[P.gb_off[NH]] = (double)v[0];
+        for (int l = NH; l >= 1; --l) {
+          TmIo<1>::ld(tmn + tm_sing + 1 + (NH - l), v);
+          if (lane < H) pn[P.gb_off[l - 1] + lane] = (double)v[0];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   // fold the warps' fp64 partial vectors into the first one (fixed order: deterministic), so that the final reduction
   // reads one vector per CTA
   __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
   double* cta_part = P.part + (size_t)blockIdx.x * nw * n_part;
   for (int i = tid; i < n_part; i += nt) {
     double sacc = 0.0;
     for (int q = 0; q < nw; ++q) sacc += __ldcg(cta_part + (size_t)q * n_part + i);
     cta_part[i] = sacc;
   }
-}
-
-// Pass 2b:  dW_1[n] = sum_f s_1 (x) r + (scale G_1) (x) vhat  -- a product over the frames with the accumulators of one
-// network's [H][d_r] block held in a warp's registers for a run of kRun tiles (32 frames each).  Work items
-// (network, run) are dealt round-robin to all warps of the grid, so the load is even for any k; a warp stages the operand
-// rows (r, vhat left by pass 2a in place of u, s_1 | scale G_1) in warp-private shared memory, and after a run adds its
-// fp32 sums to its own fp64 block of that network (one owner per address: deterministic).
-constexpr int kRun = 16;
-
-// half of stage_rows: of the row quads 0, 1, 2, ... warp `h` of a pair takes the even (h = 0) or odd (h = 1) ones
-__device__ __forceinline__ void stage_rows_half(float* dst, const float* src, int nrows, long long Bp, int lane, int h) {
-  const int c4 = 4 * (lane & 7);
-#pragma unroll 4
-  for (int r = (lane >> 3) + 4 * h; r < nrows; r += 8) cp_async16(dst + r * kRowPad + c4, src + (size_t)r * Bp + c4);
-}
-
-// Two warps share one pair of staging buffers: each issues half of the copies of a tile and multiplies half of its frames, so
-// the shared memory that held four independent warps holds eight and the dependency stalls of one are covered by the others.
-template <int H, int TI>
-__global__ void __launch_bounds__(256, 1) dw1_kernel(const FastPlan P, double* __restrict__ part2) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int RP = kRowPad, TQ = H / 4, LPO = 32 / TQ;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nw = nt >> 5;
-  const int pair = warp >> 1, h = warp & 1, npairs = nw >> 1;
-  const int drp = P.d_rp, d_r = P.d_r, nig = drp / TI, k = P.k, blk = H * d_r;
-  const int rows_per_buf = 2 * drp + 2 * H;
-  float* buf0 = sm + (size_t)pair * 2 * rows_per_buf * RP;   // two staging buffers per pair: r | vhat | s_1, scale G_1
-  for (int i = tid; i < npairs * 2 * rows_per_buf * RP; i += nt) sm[i] = 0.0f;
-  double* part = part2 + ((size_t)blockIdx.x * nw + warp) * (size_t)(k * blk);   // [k][H * d_r]
-  for (int i = lane; i < k * blk; i += 32) part[i] = 0.0;
-  __syncthreads();
-  const int og = lane / LPO, ig = lane - og * LPO;
-  const bool active = og < TQ && ig < nig;
-  const long long n_tiles = P.Bp / 32;
-  const long long n_runs = (n_tiles + kRun - 1) / kRun, n_items = n_runs * k;
-  const long long stride = (long long)gridDim.x * npairs;
-  // the pair's tiles form one sequence (item q, tile t inside its run); tile i + 1 is staged while tile i is multiplied
-  auto stage = [&](int b, int n, long long t) {
-    float* R = buf0 + (size_t)b * rows_per_buf * RP;
-    stage_rows_half(R, P.Y + t * 32, d_r, P.Bp, lane, h);
-    stage_rows_half(R + drp * RP, P.U + ((size_t)n * drp) * P.Bp + t * 32, d_r, P.Bp, lane, h);
-    stage_rows_half(R + 2 * drp * RP, P.SG + ((size_t)n * 2 * H) * P.Bp + t * 32, 2 * H, P.Bp, lane, h);
-    cp_async_commit();
-  };
-  long long q = (long long)blockIdx.x * npairs + pair;
-  int cur = 0;
-  if (q < n_items) stage(0, (int)(q % k), (q / k) * kRun);
-  for (; q < n_items; q += stride) {
-    const int n = (int)(q % k);
-    const long long t0 = (q / k) * kRun, t1 = t0 + kRun < n_tiles ? t0 + kRun : n_tiles;
-    float2 acc[4][TI];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int i = 0; i < TI; ++i) acc[j][i] = make_float2(0.f, 0.f);
-    for (long long t = t0; t < t1; ++t) {
-      // successor of (q, t) in this pair's sequence
-      long long tn = t + 1, qn = q;
-      if (tn >= t1) qn = q + stride, tn = (qn / k) * kRun;
-      named_barrier(1 + pair, 64);   // both warps have finished reading the buffer that is staged next
-      if (qn < n_items) {
-        stage(cur ^ 1, (int)(qn % k), tn);
-        cp_async_wait_group<1>();
-      } else {
-        cp_async_wait_all();
-      }
-      named_barrier(1 + pair, 64);   // both halves of the current tile have landed
-      const float* R = buf0 + (size_t)cur * rows_per_buf * RP;
-      if (active)
-        outer_tile<4, TI>(acc, R + (2 * drp + og) * RP, R + ig * RP, R + (2 * drp + H + og) * RP, R + (drp + ig) * RP, TQ * RP,
-                          nig * RP, 16 * h, 16 * h + 16);
-      cur ^= 1;
-    }
-    // fp32 sums of the run -> this warp's fp64 block of network n, transposed through its half of the buffer just used so that
-    // the additions are coalesced (the buffer is restaged, after the pair's next barrier, before its next use)
-    named_barrier(1 + pair, 64);
-    float* T = buf0 + (size_t)(cur ^ 1) * rows_per_buf * RP + (size_t)h * (rows_per_buf * RP / 2);
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < TI; ++i) {
-          const int o = j * TQ + og, col = i * nig + ig;
-          if (col < d_r) T[o * d_r + col] = acc[j][i].x + acc[j][i].y;
-        }
-    }
-    __syncwarp();
-    for (int e = lane; e < blk; e += 32) atomicAdd(part + (size_t)n * blk + e, (double)T[e]);   // result unused: RED
-  }
-  // fold the CTA's warps into the first warp's blocks (fixed order)
-  __syncthreads();
-  {
-    double* cta = part2 + (size_t)blockIdx.x * nw * (size_t)(k * blk);
-    for (int e = tid; e < k * blk; e += nt) {
-      double sacc = 0.0;
-      for (int qq = 0; qq < nw; ++qq) sacc += __ldcg(cta + (size_t)qq * (k * blk) + e);
-      cta[e] = sacc;
-    }
-  }
-}
-
-// grad_out[n][W1 block] += sum over the CTAs' folded blocks of network n
-__global__ void dw1_reduce_kernel(const double* __restrict__ part2, int n_ctas, size_t cta_stride, int block, int n_params,
-                                  int w1_off, double* __restrict__ grad_out) {
-  const int n = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= block) return;
-  double s = 0.0;
-  for (int c = 0; c < n_ctas; ++c) s += part2[(size_t)c * cta_stride + (size_t)n * block + e];
-  grad_out[(size_t)n * n_params + w1_off + e] += s;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1421,7 +1540,10 @@ static size_t pass1_smem_bytes(int k, int img_floats, int geo_floats, int tile_r
 // vhat then stay in 24 rows of their own behind the X rows, and pass 2b (one 12-column group for 5 of 32 lanes) is not launched.
 static bool pass2_inline_dw1(int drp) { return drp == 12; }
 static int pass2_rows_per_warp(int drp, int H, int NH) {
-  const int need = 2 * NH * H + 2 * H, stage = 2 * drp + 12;
+  // Z rows (A_l | T_l of every layer; later two double-buffered chunks of r | vhat rows for dW_1) followed by the X rows;
+  // the staging of layer 1 (r, u, Jacobian vectors) may overlap the X rows, which are not in use yet
+  const int z = 2 * NH * H > 4 * kDw1Chunk ? 2 * NH * H : 4 * kDw1Chunk;
+  const int need = z + 2 * H, stage = 2 * drp + 12;
   return (need > stage ? need : stage) + (pass2_inline_dw1(drp) ? 2 * drp : 0);
 }
 static size_t pass2_smem_bytes(int k, int img2_floats, int geo_floats, int drp, int H, int NH, int warps) {
@@ -1435,27 +1557,10 @@ static int pass2_warps(int k, int img2_floats, int geo_floats, int drp, int H, i
     if (pass2_smem_bytes(k, img2_floats, geo_floats, drp, H, NH, wv) <= (size_t)max_smem_optin()) return wv;
   return 0;
 }
-static size_t dw1_smem_bytes(int warps, int drp, int H) { return (size_t)(warps / 2) * 2 * (2 * drp + 2 * H) * kRowPad * sizeof(float); }
-// warps of a pass-2b CTA (pairs of warps share two staging buffers): as many as fit (<= 8); 0 if no pair fits, or if a
-// warp's half of a buffer cannot hold the [H][d_r] block it transposes through it
-static int dw1_warps(int k, int drp, int H) {
-  (void)k;
-  if ((size_t)H * drp > (size_t)(2 * drp + 2 * H) * kRowPad / 2) return 0;
-  for (int wv = kP2MaxWarps; wv >= 2; wv -= 2)
-    if (dw1_smem_bytes(wv, drp, H) <= (size_t)max_smem_optin()) return wv;
-  return 0;
-}
 // image sizes without the template (same arithmetic as Img<H, NH>)
 static int img2_floats_of(int H, int NH, int drp) { return drp * H + H + (NH - 1) * (H * H + H) + H + 4 + (NH - 1) * H * H; }
 static int img_floats_of(int H, int NH, int drp) { return img2_floats_of(H, NH, drp) + H * drp; }
 
-// pass 2b register tile: 4 outputs x TI columns of dW_1 per lane, lanes = (H/4 output groups) x (d_rp / TI column groups)
-static int dw1_cols_per_lane(int drp, int H) {
-  const int lpo = 32 / (H / 4);
-  for (int ti = 12; ti <= 16; ti += 2)
-    if (drp % ti == 0 && drp / ti <= lpo) return ti;
-  return 0;
-}
 // kind 2
 static int n_adj_of(const int* c) { return 3 * c[0] + 2 * c[1] + 3 * c[2] + 4 * c[3]; }
 static int n_st_of(const int* c, int n_self) {
@@ -1530,10 +1635,8 @@ bool fast_eigen_supported(const cvf_preproc* pp, const NetPlan& np, int k) {
   }
   if (d_r < 1) return false;
   const int drp = (d_r + 11) / 12 * 12, geo = fast::geo_floats_of(drp);
-  if (fast::dw1_cols_per_lane(drp, s.H) == 0) return false;   // pass 2b: the [H][d_rp] block of dW_1 must fit one warp's registers
   return fast::pass1_smem_bytes(k, fast::img_floats_of(s.H, s.NH, drp), geo, tile_rows) <= cap &&
-         fast::pass2_warps(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) > 0 &&
-         fast::dw1_warps(k, drp, s.H) > 0;
+         fast::pass2_warps(k, fast::img2_floats_of(s.H, s.NH, drp), geo, drp, s.H, s.NH) > 0;
 }
 
 namespace fast {
@@ -1578,7 +1681,6 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   };
   const int n_part = k * np.n_params > 1 + 2 * k + k * k ? k * np.n_params : 1 + 2 * k + k * k;
   P->part = (double*)take((size_t)sm_count() * kP2MaxWarps * n_part * sizeof(double));
-  P->part2 = (double*)take((size_t)sm_count() * kP2MaxWarps * k * H * P->d_r * sizeof(double));
   P->img = (float*)take(((size_t)k * P->img_floats + P->geo_floats) * sizeof(float));
   P->Y = (float*)take((size_t)P->d_rp * P->Bp * sizeof(float));
   P->Kinv = (float*)take((size_t)6 * P->Bp * sizeof(float));
@@ -1586,7 +1688,6 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   P->JQ = (float*)take((size_t)k * 12 * P->Bp * sizeof(float));
   P->Dq = (float*)take((size_t)k * P->Bp * sizeof(float));
   P->Ys = (float*)take((size_t)k * P->Bp * sizeof(float));
-  P->SG = (float*)take((size_t)k * 2 * H * P->Bp * sizeof(float));
   P->tab = nullptr, P->ST = nullptr;
   if (P->kind == 2) {
     P->tab = (int*)take((size_t)tab_ints(P->n_feat, P->n_used, P->n_adj) * sizeof(int));
@@ -1697,34 +1798,6 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
   CVF_CUDA(cudaGetLastError());
   const int n_part = k * np.n_params;
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, nw * n_part, 0, n_part, grad_out));
-  CVF_CUDA(cudaGetLastError());
-  if (pass2_inline_dw1(P.d_rp)) return 0;   // pass 2a has formed the first layer's weight gradient itself
-  // pass 2b: the first layer's weight gradient
-  const int warps_b = dw1_warps(k, P.d_rp, H);
-  const size_t smem3 = dw1_smem_bytes(warps_b, P.d_rp, H);
-  const long long n_items = (n_tiles + kRun - 1) / kRun * k;
-  const int pairs_b = warps_b / 2;
-  long long grid_b = sm_count();
-  if ((n_items + pairs_b - 1) / pairs_b < grid_b) grid_b = (n_items + pairs_b - 1) / pairs_b;
-  const int ti = dw1_cols_per_lane(P.d_rp, H);
-#define CVF_DW1(TI_)                                                                                                       \
-  do {                                                                                                                     \
-    CVF_CUDA(cudaFuncSetAttribute(dw1_kernel<H, TI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));           \
-    CVF_LAUNCH(K_FAST_PASS2B, stream, dw1_kernel<H, TI_><<<(int)grid_b, 32 * warps_b, smem3, stream>>>(P, P.part2));        \
-  } while (0)
-  if (ti == 12) CVF_DW1(12);
-  else if (ti == 14) CVF_DW1(14);
-  else if (ti == 16) CVF_DW1(16);
-  else {
-    set_error("fast eigen path: pass 2b has no register tile for d_rp = %d", P.d_rp);
-    return CVF_E_UNSUPPORTED;
-  }
-#undef CVF_DW1
-  CVF_CUDA(cudaGetLastError());
-  const int block = H * P.d_r;
-  CVF_LAUNCH(K_REDUCE, stream,
-             dw1_reduce_kernel<<<dim3((block + 127) / 128, k), 128, 0, stream>>>(P.part2, (int)grid_b, (size_t)warps_b * k * block, block,
-                                                                                 np.n_params, np.gw_off[0], grad_out));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }

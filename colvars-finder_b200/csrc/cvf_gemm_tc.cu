@@ -12,8 +12,14 @@
 //     stages fill (mbarrier per stage, 256 arrivals) and commit them (tcgen05.commit on a second mbarrier per stage, which
 //     returns the stage); three stages, and the staging threads' global loads run two blocks ahead of their stores, so load
 //     latency, staging and the tensor core overlap;
-//   * the 128 x 128 fp32 accumulator lives in 128 columns of tensor memory and is read back with tcgen05.ld (32 lanes x 32
-//     columns per warp instruction) for the fused epilogue (bias / tanh / multiplication by 1 - act^2).
+//   * the 128 x 128 fp32 accumulator lives in tensor memory and is read back with tcgen05.ld (32 lanes x 32 columns per warp
+//     instruction).  The tensor core adds into it with truncation, not round-to-nearest: the error is a bias that grows with
+//     the number of accumulated MMAs (measured: 3e-5 relative after the 1128 MMAs of a K = 3000 product, which broke the 2e-5
+//     gradient bar at the real C5 shape).  So a chain is at most kGroup k-blocks (96 MMAs) long: two chain buffers (2 x 128
+//     columns) alternate, and while the tensor core fills one the staging warps add the other, 16 columns at a time and with
+//     ordinary round-to-nearest additions in registers, onto a third 128-column "master" tile that also lives in tensor
+//     memory (register pressure stays what it was); the fused epilogue (bias / tanh / multiplication by 1 - act^2) reads the
+//     master tile.
 #include <stdint.h>
 
 #include "cvf_common.cuh"
@@ -26,7 +32,9 @@ constexpr int TM = 128, TN = 128, TK = 32;            // CTA tile; TK fp32 = one
 constexpr int kTileBytes = TM * TK * 4;               // 16 KB per operand tile
 constexpr int kStageBytes = 4 * kTileBytes;           // Ahi, Alo, Bhi, Blo
 constexpr int kStages = 3;
-constexpr uint32_t kTmemCols = 128;
+constexpr int kGroup = 8;                             // k-blocks accumulated in tensor memory before a drain (8 x 12 MMAs, K = 256)
+constexpr uint32_t kTmemCols = 512;                   // two chain buffers and the master tile, 128 columns each (power of two: 512)
+constexpr uint32_t kMasterCol = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -172,6 +180,8 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_done[kStages];   // tensor core has finished reading the stage
   __shared__ __align__(8) uint64_t full[kStages];       // the 256 staging threads have filled the stage
+  __shared__ __align__(8) uint64_t acc_full[2];         // the MMAs of a group have all landed in accumulator buffer b
+  __shared__ __align__(8) uint64_t acc_free[2];         // the 256 draining threads have read accumulator buffer b
   __shared__ uint32_t tmem_base_slot;
   // 1024-byte aligned operand area (the swizzle pattern is a function of the absolute address bits)
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&mma_done[s], 1), mbar_init(&full[s], 256);
+    for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_free[b], 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -203,6 +214,44 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
   // image of this CTA's row tile of each operand (k-block 0), or null
   const float* a_img = g.a_img ? g.a_img + (size_t)blockIdx.y * g.a_img_kblocks * (2 * kTileBytes / 4) : nullptr;
   const float* b_img = g.b_img ? g.b_img + (size_t)blockIdx.x * g.b_img_kblocks * (2 * kTileBytes / 4) : nullptr;
+  const int n_groups = (n_blocks + kGroup - 1) / kGroup;
+  // group g sits in chain buffer g & 1; its i-th use (i = g >> 1) completes phase i & 1 of the buffer's barriers.  A thread
+  // owns lanes 32 (warp % 4) .. +31 (rows) x columns 64 (warp / 4) .. +63 of the tile.
+  auto ld16 = [&](uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+  };
+  auto drain = [&](int grp) {
+    const int b = grp & 1;
+    mbar_wait(&acc_full[b], (uint32_t)((grp >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t lane_base = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
+#pragma unroll 1
+    for (int piece = 0; piece < 4; ++piece) {
+      uint32_t c[16], m[16];
+      ld16(lane_base + (uint32_t)(128 * b + 16 * piece), c);
+      if (grp > 0) ld16(lane_base + kMasterCol + (uint32_t)(16 * piece), m);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (grp > 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = __float_as_uint(__uint_as_float(c[i]) + __uint_as_float(m[i]));
+      }
+      asm volatile(
+          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+              lane_base + kMasterCol + (uint32_t)(16 * piece)),
+          "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(c[8]), "r"(c[9]), "r"(c[10]),
+          "r"(c[11]), "r"(c[12]), "r"(c[13]), "r"(c[14]), "r"(c[15])
+          : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(&acc_free[b]);
+  };
+  int next_drain = 0;
   if (warp < 8) {
     Stage4 ra0, rb0, ra1, rb1;
     if (n_blocks > 0) {
@@ -235,40 +284,43 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&full[s]);
+      // one group behind the staging: the group before the one just completed has long been multiplied
+      if (blk % kGroup == kGroup - 1 && blk / kGroup >= 1) drain(next_drain++);
     };
     for (int blk = 0; blk < n_blocks; blk += 2) {
       body(blk, ra0, rb0);
       if (blk + 1 < n_blocks) body(blk + 1, ra1, rb1);
     }
+    while (next_drain < n_groups) drain(next_drain++);
   } else {
     uint32_t fphase[kStages] = {0, 0, 0};
     for (int blk = 0; blk < n_blocks; ++blk) {
       const int s = blk % kStages;
+      const int grp = blk / kGroup, kb = blk - grp * kGroup, ab = grp & 1;
+      // a buffer is reused by group g + 2: its previous contents (group g) must have been drained
+      if (kb == 0 && grp >= 2) mbar_wait(&acc_free[ab], (uint32_t)(((grp >> 1) - 1) & 1));
       mbar_wait(&full[s], fphase[s]);
       fphase[s] ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
+        const uint32_t tmem_acc = tmem_d + (uint32_t)(128 * ab);
         const uint32_t a_hi = smem_u32(tiles + (size_t)s * kStageBytes);
         const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + kTileBytes), db_hi = umma_desc(a_hi + 2 * kTileBytes),
                        db_lo = umma_desc(a_hi + 3 * kTileBytes);
 #pragma unroll
         for (int kk = 0; kk < TK / 8; ++kk) {
           const uint64_t ko = (uint64_t)(kk * 32 >> 4);   // 8 TF32 = 32 bytes along K inside the swizzle row (address field: >> 4)
-          umma_tf32(tmem_d, da_hi + ko, db_hi + ko, (blk | kk) != 0);
-          umma_tf32(tmem_d, da_lo + ko, db_hi + ko, 1);
-          umma_tf32(tmem_d, da_hi + ko, db_lo + ko, 1);
+          umma_tf32(tmem_acc, da_hi + ko, db_hi + ko, (kb | kk) != 0);
+          umma_tf32(tmem_acc, da_lo + ko, db_hi + ko, 1);
+          umma_tf32(tmem_acc, da_hi + ko, db_lo + ko, 1);
         }
         umma_commit(&mma_done[s]);
+        if (kb == kGroup - 1 || blk == n_blocks - 1) umma_commit(&acc_full[ab]);
       }
       __syncwarp();
     }
   }
-  // the last commit covers every MMA issued before it
-  if (warp < 8 && n_blocks > 0) {
-    const int last = (n_blocks - 1) % kStages;
-    mbar_wait(&mma_done[last], phase[last]);
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // every group has been added onto the master tile (each drain waited for the commit that covers the group's MMAs)
 
   // epilogue: warp w reads lanes 32 (w % 4) .. +31 (rows) and columns 64 (w / 4) .. +63
   float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
@@ -276,31 +328,25 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
 #pragma unroll 1
   for (int cb = 0; cb < (warp < 8 ? 2 : 0); ++cb) {
     const int col0 = 64 * (warp >> 2) + 32 * cb;
-    uint32_t v[32];
+    float v[32];
     if (n_blocks > 0) {
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr)
-          : "memory");
+      uint32_t lo[16], hi[16];
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + kMasterCol + (uint32_t)col0;
+      ld16(taddr, lo);
+      ld16(taddr + 16, hi);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(lo[c]), v[16 + c] = __uint_as_float(hi[c]);
     } else {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = 0u;
+      for (int c = 0; c < 32; ++c) v[c] = 0.0f;
     }
     if (row < g.M) {
 #pragma unroll
       for (int c4 = 0; c4 < 8; ++c4) {
         const int n = n0 + col0 + 4 * c4;
         if (n >= g.N) continue;
-        float o[4] = {__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]), __uint_as_float(v[4 * c4 + 2]),
-                      __uint_as_float(v[4 * c4 + 3])};
+        float o[4] = {v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]};
         if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)

@@ -299,6 +299,25 @@ def eigen_loss_and_grads(X, w, nets, pp, alpha, eig_w, diag_coeff=None, beta=1.0
     return comb, eigen_grads(w, nets, state, comb), S
 
 
+def eigen_loss_and_grads_chunked(X, w, nets, pp, alpha, eig_w, diag_coeff=None, beta=1.0, sort=True, chunk=32768):
+    """eigen_loss_and_grads for batches whose per-frame state does not fit the host: pass 1 over chunks (batch sums add),
+    combine, pass 2 over chunks with pass 1 recomputed (gradient sums add).  Returns (comb, grads)."""
+    nets = [[np.asarray(p, dtype=np.float64) for p in n] for n in nets]
+    a = np.ones(np.asarray(X[0]).size) if diag_coeff is None else np.asarray(diag_coeff, dtype=np.float64)
+    S = None
+    for s in range(0, len(X), chunk):
+        Sc, _ = eigen_stats(np.asarray(X[s:s + chunk], dtype=np.float64), np.asarray(w[s:s + chunk], dtype=np.float64), nets, pp, a)
+        S = Sc if S is None else {key: S[key] + Sc[key] for key in S}
+    comb = eigen_combine(S, alpha, eig_w, beta, sort)
+    grads = None
+    for s in range(0, len(X), chunk):
+        wc = np.asarray(w[s:s + chunk], dtype=np.float64)
+        _, st = eigen_stats(np.asarray(X[s:s + chunk], dtype=np.float64), wc, nets, pp, a)
+        gc = eigen_grads(wc, nets, st, comb)
+        grads = gc if grads is None else [[p + q for p, q in zip(gi, gj)] for gi, gj in zip(grads, gc)]
+    return comb, grads
+
+
 # ----------------------------------------------------------------------------- autoencoder loss
 def ae_loss_and_grads(F, w, enc, dec):
     """weighted MSE (core.py:666) and its parameter gradients; encoder's last layer is linear."""

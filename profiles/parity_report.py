@@ -37,23 +37,8 @@ except Exception:
     pass
 
 
-def chunked_closed_form(X, w, nets, pp, alpha, eig_w, chunk=32768):
-    """cf.eigen_loss_and_grads without holding the per-frame state of the whole batch."""
-    nets64 = [[np.asarray(p, dtype=np.float64) for p in n] for n in nets]
-    k = len(nets)
-    a = np.ones(X[0].size)
-    S = None
-    for s in range(0, len(X), chunk):
-        Sc, _ = cf.eigen_stats(np.asarray(X[s:s + chunk], dtype=np.float64), np.asarray(w[s:s + chunk], dtype=np.float64), nets64, pp, a)
-        S = Sc if S is None else {key: S[key] + Sc[key] for key in S}
-    comb = cf.eigen_combine(S, alpha, eig_w)
-    grads = None
-    for s in range(0, len(X), chunk):
-        wc = np.asarray(w[s:s + chunk], dtype=np.float64)
-        _, st = cf.eigen_stats(np.asarray(X[s:s + chunk], dtype=np.float64), wc, nets64, pp, a)
-        gc = cf.eigen_grads(wc, nets64, st, comb)
-        grads = gc if grads is None else [[p + q for p, q in zip(gi, gj)] for gi, gj in zip(grads, gc)]
-    return comb, grads
+def chunked_closed_form(X, w, nets, pp, alpha, eig_w):
+    return cf.eigen_loss_and_grads_chunked(X, w, nets, pp, alpha, eig_w)
 
 
 def eigen_errors(task, model, X, w, nets, ppo, alpha, eig_w):

@@ -73,6 +73,6 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / n) if n > 0 else float(np.linalg.norm(a - b))
 
 
-def tol(gold, ref32, rel=1e-5, slack=2.0):
+def tol(gold, ref32, rel=1e-5, slack=1.0):
     """pass when |ours-gold| <= max(rel*|gold|, slack*|ref32-gold|)."""
     return max(rel * abs(float(gold)), slack * abs(float(ref32) - float(gold)))

@@ -100,6 +100,56 @@ def test_features_fwd_matches_oracle():
     assert np.abs(r - ppo.prepare(X.astype(np.float64))["r"]).max() < 2e-5
 
 
+
+# --------------------------------------------------------------------------------------------- envelopes
+# pass when |ours - gold64| <= max(1e-5 |gold64|, 1 x |ref32 - gold64|): gold64 = fp64 closed form, ref32 = the reference's own
+# fp32 arithmetic (oracle/ref_torch.py: autograd through torch.linalg.svd, double backward) on the same fp32 inputs.  The
+# achieved errors at BASELINE sizes are in profiles/r02_parity_errors.json (loss ~1e-8, eigenvalues ~6e-8, gradients ~1e-5).
+def _ref32(X, w, nets, ppo, alpha, eig_w, diag=None, beta=1.0, sort=True):
+    """(loss, eig, grads) of the reference's fp32 path; None when the batch is too large to be worth a CPU autograd run."""
+    if len(X) > 25000:
+        return None
+    if ppo.identity:
+        ppt = ref_torch.Preprocess()
+    else:
+        al = None if ppo.align_idx is None else ref_torch.Align(ppo.ref, ppo.align_idx)
+        ppt = ref_torch.Preprocess(al, None if ppo.feats is None else ref_torch.FeatureMap(ppo.feats))
+    tn = [[torch.as_tensor(p).float().requires_grad_() for p in n] for n in nets]
+    Xt = torch.as_tensor(X).float().requires_grad_()
+    a = None if diag is None else torch.as_tensor(diag).float()
+    out = ref_torch.eigen_loss(Xt, torch.as_tensor(w).float(), tn, ppt, alpha, eig_w, a, beta, sort)
+    out[0].backward()
+    return float(out[0]), out[1].numpy().astype(np.float64), [[np.zeros(tuple(p.shape)) if p.grad is None else p.grad.numpy() for p in n] for n in tn]
+
+
+def _assert_within_envelope(out, grads, comb, g64, ref32, tag=""):
+    loss, eig, obj, pen, cvec = out
+    bad = []
+    if list(cvec.cpu().numpy()) != list(comb["cvec"]):
+        # an ordering flip is legitimate only between eigenvalues closer than the fp32 floor
+        bad.append(("cvec", list(cvec.cpu().numpy()), list(comb["cvec"])))
+    l32 = ref32[0] if ref32 else comb["loss"]
+    if not abs(float(loss) - comb["loss"]) <= max(1e-5 * abs(comb["loss"]), abs(l32 - comb["loss"])):
+        bad.append(("loss", float(loss), comb["loss"], l32))
+    e = eig.cpu().numpy().astype(np.float64)
+    for i in range(len(e)):
+        e32 = ref32[1][i] if ref32 else comb["eig"][i]
+        if not abs(e[i] - comb["eig"][i]) <= max(1e-5 * abs(comb["eig"][i]), abs(e32 - comb["eig"][i])):
+            bad.append(("eig", i, e[i], comb["eig"][i], e32))
+    scale = max(np.abs(t).max() for n in g64 for t in n)
+    for i in range(len(g64)):
+        for j in range(len(g64[i])):
+            if np.abs(g64[i][j]).max() < 1e-9 * scale:     # last-layer bias: zero up to rounding
+                if not np.abs(grads[i][j]).max() < 1e-5 * scale:
+                    bad.append(("zero-grad", i, j, float(np.abs(grads[i][j]).max())))
+                continue
+            floor = C.rel_l2(ref32[2][i][j], g64[i][j]) if ref32 else 0.0
+            err = C.rel_l2(grads[i][j], g64[i][j])
+            if not err <= max(2e-5, floor):
+                bad.append(("grad", i, j, err, floor))
+    assert not bad, (tag, bad)
+
+
 # --------------------------------------------------------------------------------------------- eigenfunction loss
 def _check_eigen(c, out, grads, gold, tag=""):
     loss, eig, obj, pen, cvec = out
@@ -117,7 +167,7 @@ def _check_eigen(c, out, grads, gold, tag=""):
                 assert np.abs(grads[i][j]).max() < 1e-4 * max(1.0, abs(gold["loss"]))
                 continue
             ref_err = C.rel_l2(gold["grads32"][i][j], g64) if "grads32" in gold else 0.0
-            assert C.rel_l2(grads[i][j], g64) <= max(2e-5, 2.0 * ref_err), (tag, i, j, C.rel_l2(grads[i][j], g64), ref_err)
+            assert C.rel_l2(grads[i][j], g64) <= max(2e-5, ref_err), (tag, i, j, C.rel_l2(grads[i][j], g64), ref_err)
 
 
 @pytest.mark.parametrize("name", C.EIGEN_GENERATOR_CASES)
@@ -156,17 +206,8 @@ def test_eigen_loss_matches_oracle_ragged_sizes(name, B, tmp_path):
     grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
     _, ppo = _pp_pair(c)
     comb, g64, _ = cf.eigen_loss_and_grads(X, w, c["params"], ppo, c["alpha"], c["eig_w"], c["diag_coeff"], c["beta"], c["sort"])
-    # fp32 floor of the reference formula var = E[y^2] - E[y]^2 is not available here: use a fixed 1e-4 envelope
-    loss, eig, obj, pen, cvec = out
-    assert list(cvec.cpu().numpy()) == list(comb["cvec"])
-    assert abs(float(loss) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
-    np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
-    for i in range(c["k"]):
-        for j in range(len(g64[i])):
-            if np.abs(g64[i][j]).max() < 1e-9 * abs(comb["loss"]):     # last-layer bias: zero up to rounding
-                assert np.abs(grads[i][j]).max() < 1e-4 * abs(comb["loss"])
-                continue
-            assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (i, j, C.rel_l2(grads[i][j], g64[i][j]))
+    ref32 = _ref32(X, w, c["params"], ppo, c["alpha"], c["eig_w"], c["diag_coeff"], c["beta"], c["sort"])
+    _assert_within_envelope(out, grads, comb, g64, ref32, f"{name}/B={B}")
 
 
 def _random_nets(dims, k, seed):
@@ -222,16 +263,7 @@ def test_eigen_fast_path_matches_oracle(name, B, tmp_path):
     out[0].backward()
     grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
     comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, eig_w, diag)
-    loss, eig, obj, pen, cvec = out
-    assert list(cvec.cpu().numpy()) == list(comb["cvec"])
-    assert abs(float(loss) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
-    np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
-    for i in range(k):
-        for j in range(len(g64[i])):
-            if np.abs(g64[i][j]).max() < 1e-9 * abs(comb["loss"]):
-                assert np.abs(grads[i][j]).max() < 1e-4 * abs(comb["loss"])
-                continue
-            assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (i, j, C.rel_l2(grads[i][j], g64[i][j]))
+    _assert_within_envelope(out, grads, comb, g64, _ref32(X, w, nets, ppo, 20.0, eig_w, diag), f"{name}/B={B}")
 
 
 @pytest.mark.parametrize("name", ["eigen_2d_k1", "eigen_dipep_k3"])
@@ -283,14 +315,8 @@ def test_eigen_invariant_features_with_alignment_matches_oracle(tmp_path):
     out = task.loss_func(task._traj, task._weights, None, None)
     out[0].backward()
     comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, [1.0, 0.5])
-    assert list(out[4].cpu().numpy()) == list(comb["cvec"])
-    assert abs(float(out[0]) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
-    np.testing.assert_allclose(out[1].cpu().numpy(), comb["eig"], rtol=2e-4)
-    for i in range(k):
-        for p, g in zip(model.eigen_funcs[i].parameters(), g64[i]):
-            if np.abs(g).max() < 1e-9 * abs(comb["loss"]):
-                continue
-            assert C.rel_l2(p.grad.cpu().numpy(), g) < 2e-3
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    _assert_within_envelope(out, grads, comb, g64, _ref32(X, w, nets, ppo, 20.0, [1.0, 0.5]), "invariant features after alignment")
 
 
 FEATURE_FAST_CASES = {
@@ -356,19 +382,9 @@ def test_eigen_fast_feature_path_matches_oracle(name, B, tmp_path):
         finally:
             _lib.lib().cvf_eigen_set_path(0)
     comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, eig_w, diag)
+    ref32 = _ref32(X, w, nets, ppo, 20.0, eig_w, diag)
     for mode in (0, 1):
-        (loss, eig, obj, pen, cvec), grads = res[mode]
-        assert list(cvec.cpu().numpy()) == list(comb["cvec"]), mode
-        # two frames: var = E[y^2] - E[y]^2 is a difference of nearly equal fp32-rounded outputs, so the loss keeps fewer digits
-        assert abs(float(loss) - comb["loss"]) <= (1e-4 if B > 2 else 5e-4) * abs(comb["loss"]), mode
-        np.testing.assert_allclose(eig.cpu().numpy(), comb["eig"], rtol=2e-4)
-        for i in range(k):
-            for j in range(len(g64[i])):
-                if np.abs(g64[i][j]).max() < 1e-9 * abs(comb["loss"]):
-                    assert np.abs(grads[i][j]).max() < 1e-4 * abs(comb["loss"])
-                    continue
-                assert C.rel_l2(grads[i][j], g64[i][j]) < 2e-3, (mode, i, j, C.rel_l2(grads[i][j], g64[i][j]))
-    assert abs(float(res[0][0][0]) - float(res[1][0][0])) <= (5e-5 if B > 2 else 5e-4) * abs(float(res[1][0][0]))
+        _assert_within_envelope(res[mode][0], res[mode][1], comb, g64, ref32, f"{name}/B={B}/mode{mode}")
 
 
 def _feature_task(tmp_path, base, feats, align_idx, dims, k, X, w, diag=None, lag_tau=0, dt=1.0, eig_w=None):
@@ -401,15 +417,10 @@ def test_eigen_fast_feature_path_network_shapes(dims_k, tmp_path):
     assert task._ctx.fast_path
     out = task.loss_func(task._traj, task._weights, None, None)
     out[0].backward()
-    comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, cf.Preproc(feats=feats), 20.0, eig_w)
-    assert list(out[4].cpu().numpy()) == list(comb["cvec"])
-    assert abs(float(out[0]) - comb["loss"]) <= 1e-4 * abs(comb["loss"])
-    np.testing.assert_allclose(out[1].cpu().numpy(), comb["eig"], rtol=2e-4)
-    for i in range(k):
-        for p, g in zip(model.eigen_funcs[i].parameters(), g64[i]):
-            if np.abs(g).max() < 1e-9 * abs(comb["loss"]):
-                continue
-            assert C.rel_l2(p.grad.cpu().numpy(), g) < 2e-3
+    ppo = cf.Preproc(feats=feats)
+    comb, g64, _ = cf.eigen_loss_and_grads(X, w, nets, ppo, 20.0, eig_w)
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    _assert_within_envelope(out, grads, comb, g64, _ref32(X, w, nets, ppo, 20.0, eig_w), f"{dims}/k={k}")
 
 
 def test_eigen_feature_path_determinism_and_additivity(tmp_path):
@@ -441,6 +452,25 @@ def test_eigen_feature_path_determinism_and_additivity(tmp_path):
     np.testing.assert_allclose(s_small.cpu().numpy()[-3:], S["SD"], rtol=1e-4)
 
 
+def _lag_ref(X, w, nets, ppt, alpha, eig_w, lag, lag_time, sort, dtype):
+    tn = [[torch.tensor(p, dtype=dtype, requires_grad=True) for p in net] for net in nets]
+    Xt, wt = torch.tensor(X, dtype=dtype), torch.tensor(w, dtype=dtype)
+    pp = ppt.double() if dtype == torch.float64 else ppt.float()
+    ref = ref_torch.eigen_loss(Xt[:-lag], wt[:-lag], tn, pp, alpha, eig_w, sort=sort, X_lagged=Xt[lag:], weight_lagged=wt[lag:],
+                               lag_time=lag_time)
+    ref[0].backward()
+    grads = [[np.zeros(tuple(t.shape)) if t.grad is None else t.grad.numpy().astype(np.float64) for t in n] for n in tn]
+    return dict(loss=float(ref[0]), eig=np.asarray(ref[1], dtype=np.float64), cvec=[int(v) for v in ref[4]]), grads
+
+
+def _assert_lag_within_envelope(out, model, X, w, nets, ppt, alpha, eig_w, lag, lag_time, sort=True, tag=""):
+    """Transfer-operator loss against the reference formula in fp64, with the reference's fp32 run as the floor."""
+    gold, g64 = _lag_ref(X, w, nets, ppt, alpha, eig_w, lag, lag_time, sort, torch.float64)
+    r32, g32 = _lag_ref(X, w, nets, ppt, alpha, eig_w, lag, lag_time, sort, torch.float32)
+    grads = [[p.grad.cpu().numpy() for p in f.parameters()] for f in model.eigen_funcs]
+    _assert_within_envelope(out, grads, gold, g64, (r32["loss"], r32["eig"], g32), tag)
+
+
 def test_eigen_lag_loss_on_feature_path(tmp_path):
     """Transfer-operator branch with a feature map as pre-processing: both forward passes and both backward passes run on the
     feature kernels (the lagged batch uses the second scratch slot)."""
@@ -453,19 +483,8 @@ def test_eigen_lag_loss_on_feature_path(tmp_path):
     Xd, wd = task._traj, task._weights
     out = task.loss_func(Xd[:-lag].contiguous(), wd[:-lag].contiguous(), Xd[lag:].contiguous(), wd[lag:].contiguous())
     out[0].backward()
-    tn = [[torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in net] for net in nets]
-    Xt, wt = torch.tensor(X, dtype=torch.float64), torch.tensor(w, dtype=torch.float64)
-    ppo = ref_torch.Preprocess(None, ref_torch.FeatureMap(feats)).double()
-    ref = ref_torch.eigen_loss(Xt[:-lag], wt[:-lag], tn, ppo, 20.0, eig_w, X_lagged=Xt[lag:], weight_lagged=wt[lag:], lag_time=1.0)
-    ref[0].backward()
-    assert abs(float(out[0]) - float(ref[0])) <= 2e-5 * abs(float(ref[0]))
-    assert list(out[4].cpu().numpy()) == [int(v) for v in ref[4]]
-    for i in range(k):
-        for p, t in zip(model.eigen_funcs[i].parameters(), tn[i]):
-            g64 = t.grad.numpy()
-            if np.abs(g64).max() < 1e-9 * abs(float(ref[0])):
-                continue
-            assert C.rel_l2(p.grad.cpu().numpy(), g64) < 2e-4
+    _assert_lag_within_envelope(out, model, X, w, nets, ref_torch.Preprocess(None, ref_torch.FeatureMap(feats)), 20.0, eig_w, lag, 1.0,
+                                tag="lag loss on the feature path")
 
 
 def test_eigen_feature_descriptor_too_small_poisons_instead_of_overrunning(tmp_path):
@@ -513,6 +532,36 @@ def test_eigen_batch_sums_are_additive_at_full_size(tmp_path):
     _, s_small = ctx.stats(Xd[:3000].contiguous(), wd[:3000].contiguous())
     np.testing.assert_allclose(s_small.cpu().numpy()[0], S["S0"], rtol=1e-6)
     np.testing.assert_allclose(s_small.cpu().numpy()[-3:], S["SD"], rtol=1e-4)
+
+
+def test_eigen_full_comparison_at_large_batch(tmp_path):
+    """Loss, eigenvalues, ordering and EVERY gradient of C3 at 2^18 frames against the fp64 closed form (evaluated in chunks);
+    the same comparison at 2^20 frames for C1-C4 is profiles/parity_report.py -> profiles/r02_parity_errors.json."""
+    from colvarsfinder import core, nn, utils
+    n = 1 << 18
+    X = ref_torch.synth_frames(BASE, n, seed=2026)
+    w = ref_torch.boltzmann_weights(n, seed=2026)
+    dims, k, eig_w = [66, 20, 20, 20, 1], 3, [1.0, 0.6, 0.3]
+    nets = _random_nets(dims, k, seed=2026)
+    model = nn.EigenFunctions(dims, k)
+    with torch.no_grad():
+        for i in range(k):
+            for p, v in zip(model.eigen_funcs[i].parameters(), nets[i]):
+                p.copy_(torch.as_tensor(v))
+    task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64)), utils.Align(BASE, list(range(22))), model, str(tmp_path),
+                                  20.0, eig_w, k=k, device=DEV, verbose=False, debug_mode=False)
+    out = task.loss_func(task._traj, task._weights, None, None)
+    out[0].backward()
+    comb, g64 = cf.eigen_loss_and_grads_chunked(X, w, nets, cf.Preproc(align_idx=list(range(22)), ref=BASE), 20.0, eig_w)
+    assert list(out[4].cpu().numpy()) == list(comb["cvec"])
+    assert abs(float(out[0]) - comb["loss"]) <= 1e-6 * abs(comb["loss"])          # achieved: ~1e-8
+    np.testing.assert_allclose(out[1].cpu().numpy(), comb["eig"], rtol=2e-6)      # achieved: ~6e-8
+    scale = max(np.abs(t).max() for net in g64 for t in net)
+    for i in range(k):
+        for p, t in zip(model.eigen_funcs[i].parameters(), g64[i]):
+            if np.abs(t).max() < 1e-9 * scale:
+                continue
+            assert C.rel_l2(p.grad.cpu().numpy(), t) < 5e-5                       # achieved: max 1.2e-5, median 3e-6
 
 
 def test_eigen_determinism(tmp_path):
@@ -614,21 +663,7 @@ def test_eigen_lag_loss_matches_autograd_oracle(case, tmp_path):
     Xd, wd = task._traj, task._weights
     out = task.loss_func(Xd[:-lag].contiguous(), wd[:-lag].contiguous(), Xd[lag:].contiguous(), wd[lag:].contiguous())
     out[0].backward()
-    # oracle in float64
-    tn = [[torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in net] for net in nets]
-    Xt, wt = torch.tensor(X, dtype=torch.float64), torch.tensor(w, dtype=torch.float64)
-    ref = ref_torch.eigen_loss(Xt[:-lag], wt[:-lag], tn, ppo.double(), 15.0, eig_w, sort=sort, X_lagged=Xt[lag:],
-                               weight_lagged=wt[lag:], lag_time=1.5)
-    ref[0].backward()
-    assert abs(float(out[0]) - float(ref[0])) <= 2e-5 * abs(float(ref[0]))
-    np.testing.assert_allclose(out[1].cpu().numpy(), np.asarray(ref[1], dtype=np.float64), rtol=2e-4)
-    assert list(out[4].cpu().numpy()) == [int(v) for v in ref[4]]
-    for i in range(k):
-        for p, t in zip(model.eigen_funcs[i].parameters(), tn[i]):
-            g64 = t.grad.numpy()
-            if np.abs(g64).max() < 1e-9 * abs(float(ref[0])):
-                continue
-            assert C.rel_l2(p.grad.cpu().numpy(), g64) < 2e-4, (i, C.rel_l2(p.grad.cpu().numpy(), g64))
+    _assert_lag_within_envelope(out, model, X, w, nets, ppo, 15.0, eig_w, lag, 1.5, sort=sort, tag=case)
 
 
 def test_eigen_lag_train_follows_oracle_loop(tmp_path):
@@ -790,11 +825,14 @@ def test_ae_wide_layers_match_oracle(B, mode, tmp_path):
 
 
 @pytest.mark.parametrize("mode", ["tensor_cores", "simt"])
-@pytest.mark.parametrize("B", [4096, 33000])
-def test_ae_c5_shape_matches_oracle(B, mode, tmp_path):
+@pytest.mark.parametrize("B,data", [(4096, "unit"), (33000, "unit"), (4096, "angstrom")])
+def test_ae_c5_shape_matches_oracle(B, data, mode, tmp_path):
     """BASELINE config 5 at its real shape, AutoEncoder([3000,512,512,2],[2,512,512,3000]): the 3000-term accumulations are where
-    the dropped lo*lo term of the 3 x TF32 split and the fp32 accumulation in tensor memory would show first.  Same bars as the
-    narrow cases (loss 1e-5, gradients 2e-5 rel-L2 against the fp64 closed form); the achieved errors are printed."""
+    the dropped lo*lo term of the 3 x TF32 split and the fp32 accumulation in tensor memory would show first.
+    "unit": standardised features (what bench.py feeds): loss 1e-5, gradients 2e-5 rel-L2 against the fp64 closed form, as for
+    the narrow cases.  "angstrom": raw coordinates of a 1000-atom chain (|x| up to tens of Angstrom) with torch's default
+    initialisation saturate the first tanh layer, 1 - a^2 cancels in fp32 and the reference's own fp32 run loses digits: there
+    the reference's fp32 error is the floor.  The achieved errors are printed."""
     from colvarsfinder import core, nn, _lib
     _lib.check(_lib.lib().cvf_ae_set_wide_path(0 if mode == "tensor_cores" else 1), "cvf_ae_set_wide_path")
     try:
@@ -803,10 +841,12 @@ def test_ae_c5_shape_matches_oracle(B, mode, tmp_path):
         enc = [p.numpy() for p in ref_torch.init_mlp_params(e_dims)]
         dec = [p.numpy() for p in ref_torch.init_mlp_params(d_dims)]
         rng = np.random.default_rng(B)
-        # frames of a 1000-atom chain: a common structure plus thermal noise, Angstrom scale
-        base = np.cumsum(rng.normal(scale=1.5 / np.sqrt(3), size=(1000, 3)), 0)
-        base -= base.mean(0)
-        F = (base.reshape(1, 3000) + rng.normal(scale=0.3, size=(B, 3000))).astype(np.float32)
+        if data == "unit":
+            F = rng.normal(size=(B, 3000)).astype(np.float32)
+        else:
+            base = np.cumsum(rng.normal(scale=1.5 / np.sqrt(3), size=(1000, 3)), 0)
+            base -= base.mean(0)
+            F = (base.reshape(1, 3000) + rng.normal(scale=0.3, size=(B, 3000))).astype(np.float32)
         w = ref_torch.boltzmann_weights(B, seed=B)
         model = nn.AutoEncoder(e_dims, d_dims)
         with torch.no_grad():
@@ -821,9 +861,20 @@ def test_ae_c5_shape_matches_oracle(B, mode, tmp_path):
         lo, genc, gdec = cf.ae_loss_and_grads(F, w, enc, dec)
         got = [p_.grad.cpu().numpy() for p_ in model.encoder.parameters()] + [p_.grad.cpu().numpy() for p_ in model.decoder.parameters()]
         errs = [C.rel_l2(g, go) for g, go in zip(got, genc + gdec)]
-        print(f"C5 shape, B={B}, {mode}: loss rel err {abs(float(loss) - lo) / abs(lo):.2e}, gradient rel-L2 max {max(errs):.2e}")
-        assert abs(float(loss) - lo) <= 1e-5 * abs(lo)
-        assert max(errs) < 2e-5, errs
+        floor_loss, floors = 0.0, [0.0] * len(errs)
+        if data == "angstrom":
+            te = [torch.as_tensor(p_).requires_grad_() for p_ in enc]
+            td = [torch.as_tensor(p_).requires_grad_() for p_ in dec]
+            l32 = ref_torch.ae_loss(torch.as_tensor(F), torch.as_tensor(w), te, td)
+            l32.backward()
+            floor_loss = abs(float(l32) - lo)
+            floors = [C.rel_l2(t.grad.numpy(), go) for t, go in zip(te + td, genc + gdec)]
+        print(f"C5 shape, B={B}, {data}, {mode}: loss rel err {abs(float(loss) - lo) / abs(lo):.2e} (ref32 {floor_loss / abs(lo):.2e}), "
+              f"gradient rel-L2 max {max(errs):.2e} (ref32 max {max(floors):.2e}); per tensor (W1 b1 W2 b2 ...): " +
+              " ".join(f"{e:.1e}" for e in errs))
+        assert abs(float(loss) - lo) <= max(1e-5 * abs(lo), floor_loss)
+        for e, f in zip(errs, floors):
+            assert e <= max(2e-5, f), (errs, floors)
     finally:
         _lib.check(_lib.lib().cvf_ae_set_wide_path(0), "cvf_ae_set_wide_path")
 

@@ -117,7 +117,13 @@ def test_regae_train_reproduces_reference_history(tmp_path):
     np.testing.assert_allclose(tr, d["train_hist"], rtol=2e-3, atol=1e-5)
     np.testing.assert_allclose(te, d["test_hist"], rtol=2e-3, atol=1e-5)
     np.testing.assert_allclose(task.train_loss_df.to_numpy(), d["train_df"], rtol=2e-3, atol=1e-5)
+    # The last-layer bias of a regulariser has an exactly zero gradient in the eigenfunction loss (it cancels from the variance,
+    # the covariance and y' - y); the reference's autograd leaves rounding noise there, which Adam's normalisation turns into
+    # full-size steps of arbitrary sign.  The parameter does not enter the loss: it is left out of the comparison.
+    skip = {id(list(f.parameters())[-1]) for f in model.reg}
     for j, p in enumerate(model.parameters()):
+        if id(p) in skip:
+            continue
         np.testing.assert_allclose(p.detach().cpu().numpy(), d[f"final_{j}"], rtol=5e-3, atol=2e-4)
 
 
