@@ -103,7 +103,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -168,6 +168,31 @@ def dist_env():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     return rank, world, local
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and, by first touch, the pinned host buffers it allocates next) to the NUMA node of GPU `index`: with one
+    process per GPU, eight ranks streaming their batches out of one node's memory share that node's bandwidth (r01: 23 GB/s per
+    GPU at N = 8).  Returns a short description for the JSON line; silently does nothing where sysfs does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: none of its cores is available to this process"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to numa node {node} ({len(cpus)} cores)"
+    except Exception as exc:
+        return f"not bound ({type(exc).__name__})"
 
 
 def measured_peaks():
@@ -506,6 +531,7 @@ def main():
     launches_timed = sum(v[2] for v in _lib.profile_read(reset=True).values())
 
     # ---- end to end: batch in pinned host memory, H2D + step + D2H(loss) per step, copy of step i+1 overlapped
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single process: not bound"
     hosts = [torch.empty(X.shape, dtype=X.dtype).pin_memory() for _ in range(2)]
     hw = [torch.empty(w.shape, dtype=w.dtype).pin_memory() for _ in range(2)]
     for hb, hwb in zip(hosts, hw):
@@ -592,6 +618,12 @@ def main():
     dom_name = max(prof, key=lambda k_: prof[k_][0])
     kern_ms = prof[dom_name][0] / prof[dom_name][1]
     step_kernel_ms = sum(v[0] for v in prof.values()) / K
+    rank_kernel_ms = None
+    if world > 1:      # every rank's own kernel time per step: tells a slow GPU (all ranks wait for it at the all-reduces) from waiting
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = step_kernel_ms
+        torch.distributed.all_reduce(t)
+        rank_kernel_ms = [round(float(v), 4) for v in t]
     # ---- fp32 FMA peak probe
     sink = torch.zeros(4, device=dev)
     flops = C.c_double(0.0)
@@ -621,7 +653,7 @@ def main():
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config, "clocks": clocks, "final_loss": final_loss,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
-                "ms_per_step": float(ms_e2e) / K},
+                "ms_per_step": float(ms_e2e) / K, "host_memory": numa},
         "gpu_launches": launches_timed * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": dom_name, "kernel_ms": kern_ms,
@@ -639,6 +671,8 @@ def main():
         "native": {"so": "colvars-finder_b200/colvarsfinder/libcvf_sm100.so", "source_hash": entry.library_hash(),
                    "matches_sources": entry.library_hash() == entry.source_hash()},
     }
+    if rank_kernel_ms is not None:
+        out["kernel_ms_per_step_by_rank"] = rank_kernel_ms
     if strong is not None:
         out["scaling_strong"] = strong
     if dp_parity is not None:

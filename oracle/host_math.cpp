@@ -7,6 +7,14 @@ extern "C" void host_rotation(const double* H, int n, float* R, float* Kinv) {
   for (int i = 0; i < n; ++i) cvf_rotation(H + 9 * i, R + 9 * i, Kinv + 6 * i);
 }
 
+// the same with the fp64 rotation the kernels transform with (before its rounding to float)
+extern "C" void host_rotation_d(const double* H, int n, double* Rd, float* Kinv) {
+  for (int i = 0; i < n; ++i) {
+    float R[9];
+    cvf_rotation(H + 9 * i, R, Kinv + 6 * i, Rd + 9 * i);
+  }
+}
+
 extern "C" void host_dihedral(const float* p, int n, float* cs_sn, float* g) {
   for (int i = 0; i < n; ++i) {
     const float* q = p + 12 * i;
