@@ -6,6 +6,7 @@ Operators (each with ``register_fake`` for shape inference and ``register_autogr
 
 * ``cvf::eigen_stats(X, w, params, handle, slot) -> (y, stats)``   pass 1 + all-reduce; backward = ``cvf::eigen_grad`` (pass 2)
 * ``cvf::eigen_combine(stats, handle) -> comb``                    loss / eigenvalues / ordering of core.py:426-455
+* ``cvf::eigen_loss(X, w, params, handle) -> (y, comb)``           the two above fused (EigenFunctionTask's generator loss)
 * ``cvf::eigen_tlag_sx``, ``cvf::eigen_tlag_combine``              transfer-operator branch (core.py:412-416,428,440)
 * ``cvf::ae_sums(F, T, w, params, want_grad, handle) -> (sums, gsum)``  weighted reconstruction error and its gradient
 * ``cvf::align_fwd(x, ref, idx) -> y``                             Kabsch alignment (stand-alone pre-pass)
@@ -586,6 +587,43 @@ def _tlag_combine_backward(ctx, g_comb, g_comb_lag):
 eigen_tlag_combine_op.register_autograd(_tlag_combine_backward, setup_context=_tlag_combine_setup)
 
 
+@torch.library.custom_op("cvf::eigen_loss", mutates_args=())
+def eigen_loss_op(X: torch.Tensor, w: torch.Tensor, params: torch.Tensor, handle: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cvf::eigen_stats + cvf::eigen_combine in one operator (the generator branch of EigenFunctionTask.loss_func): the backward
+    pass reads the coefficient blocks straight out of the combine vector instead of going through d loss / d stats."""
+    ectx = _context(handle)
+    y, stats = ectx.stats(X, w, params, 0)
+    allreduce_sum_(stats)
+    return y, ectx.combine(stats)
+
+
+@eigen_loss_op.register_fake
+def _(X, w, params, handle):
+    ectx = _context(handle)
+    return X.new_empty((ectx.k, X.shape[0]), dtype=torch.float32), X.new_empty((ectx.n_comb,), dtype=torch.float64)
+
+
+def _eigen_loss_setup(ctx, inputs, output):
+    X, w, params, handle = inputs
+    ctx.save_for_backward(X, w, params, output[0], output[1])
+    ctx.set_materialize_grads(False)
+    ctx.handle = handle
+    ctx.serial = _context(handle).serial(0)
+
+
+def _eigen_loss_backward(ctx, g_y, g_comb):
+    X, w, params, y, comb = ctx.saved_tensors
+    if g_comb is None and g_y is None:
+        return None, None, None, None
+    g = eigen_grad_op(X, w, y, params, comb, g_y, ctx.handle, 0, ctx.serial)
+    if g_comb is not None:
+        g = g * g_comb[0].to(torch.float32)      # only the loss entry of the combine vector is differentiable
+    return None, None, g, None
+
+
+eigen_loss_op.register_autograd(_eigen_loss_backward, setup_context=_eigen_loss_setup)
+
+
 def _loss_outputs(comb, k):
     out32 = comb[:3 + k].to(torch.float32)
     loss, obj, pen, eig = out32[0], out32[1].detach(), out32[2].detach(), out32[3:3 + k].detach()
@@ -596,8 +634,8 @@ def _loss_outputs(comb, k):
 def eigen_loss(ectx: EigenContext, X, weight):
     """EigenFunctionTask.loss_func, generator branch (reference core.py:387-457); ``loss.backward()`` = core.py:517."""
     X, weight = _check_batch(X, weight, "EigenFunctionTask.loss_func")
-    y, stats = eigen_stats_op(X, weight, ectx.packed_params(), ectx.handle, 0)
-    return _loss_outputs(eigen_combine_op(stats, ectx.handle), ectx.k)
+    _, comb = eigen_loss_op(X, weight, ectx.packed_params(), ectx.handle)
+    return _loss_outputs(comb, ectx.k)
 
 
 def eigen_lag_loss(ectx: EigenContext, tau, X, weight, X_lagged, weight_lagged):

@@ -682,6 +682,15 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
         const int r = i / (F / 4), c4 = i - r * (F / 4);
         st4(tile + r * F + 4 * c4, __ldg(reinterpret_cast<const float4*>(P.Y + (size_t)r * P.Bp + f0) + c4));
       }
+      // the CTA's next tile into L2 while this one is processed: its loads then find every line on the chip
+      const long long tn = t + gridDim.x;
+      if (tn < n_tiles) {
+        const int lines = P.tile_rows * (F * 4 / 128);
+        for (int i = tid; i < lines; i += kP1Threads) {
+          const int r = i / (F * 4 / 128), c = i - r * (F * 4 / 128);
+          prefetch_l2_line(P.Y + (size_t)r * P.Bp + tn * F + 32 * c);
+        }
+      }
     }
     __syncthreads();
     for (int n = 0; n < k; ++n) {
@@ -887,37 +896,45 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
 }
 
 // ------------------------------------------------------------------------------------------------ stats
-// fp64 batch sums S0, S1[i], S2[i][j], SD[i] (core.py:406-410,426) from w, y, D; deterministic two-stage reduction.
+// fp64 batch sums S0, S1[i], S2[i][j], SD[i] (core.py:406-410,426) from w, y, D in ONE pass over the frames: a thread keeps all
+// 1 + 2k + k^2 sums of its frames in registers (K networks: template), then a fixed-order block reduction; deterministic.
+template <int K>
 __global__ void __launch_bounds__(256) stats_kernel(const FastPlan P, const float* __restrict__ w, double* __restrict__ part) {
-  __shared__ double red[8];
-  const int k = P.k, ns = 1 + 2 * k + k * k;
+  constexpr int NS = 1 + 2 * K + K * K;
+  __shared__ double red[8][NS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int s = 0; s < ns; ++s) {
-    double acc = 0.0;
-    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < P.B; f += (long long)gridDim.x * blockDim.x) {
-      const double wf = w[f];
-      double v;
-      if (s == 0) v = wf;
-      else if (s < 1 + k) v = wf * P.Ys[(size_t)(s - 1) * P.Bp + f];
-      else if (s < 1 + k + k * k) {
-        const int i = (s - 1 - k) / k, j = (s - 1 - k) % k;
-        v = wf * (double)P.Ys[(size_t)i * P.Bp + f] * (double)P.Ys[(size_t)j * P.Bp + f];
-      } else v = wf * P.Dq[(size_t)(s - 1 - k - k * k) * P.Bp + f];
-      acc += v;
-    }
+  double acc[NS];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) red[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int q = 0; q < 8; ++q) t += red[q];
-      part[(size_t)blockIdx.x * ns + s] = t;
+  for (int s = 0; s < NS; ++s) acc[s] = 0.0;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < P.B; f += (long long)gridDim.x * blockDim.x) {
+    const double wf = w[f];
+    double y[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) y[i] = (double)P.Ys[(size_t)i * P.Bp + f];
+    acc[0] += wf;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const double wy = wf * y[i];
+      acc[1 + i] += wy;
+#pragma unroll
+      for (int j = 0; j < K; ++j) acc[1 + K + i * K + j] += wy * y[j];
+      acc[1 + K + K * K + i] += wf * (double)P.Dq[(size_t)i * P.Bp + f];
     }
-    __syncthreads();
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    double v = acc[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][s] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+    part[(size_t)blockIdx.x * NS + threadIdx.x] = t;
   }
 }
-
 
 // ---- tensor memory as per-warp accumulator storage -----------------------------------------------------------------------
 // Pass 2 adds ~2 200 weight-gradient partial sums per (32-frame tile, network) to running totals.  As fp64 atomics to a
@@ -1763,7 +1780,24 @@ static int run_stats(const cvf_preproc* pp, const NetPlan& np, int k, const floa
   const int ns = 1 + 2 * k + k * k;
   long long grid = (long long)sm_count() * 2;
   if ((B + 255) / 256 < grid) grid = (B + 255) / 256;
-  CVF_LAUNCH(K_FAST_STATS, stream, stats_kernel<<<(int)grid, 256, 0, stream>>>(P, w, P.part));
+  switch (k) {
+#define CVF_STATS_CASE(K_) \
+  case K_:                 \
+    CVF_LAUNCH(K_FAST_STATS, stream, stats_kernel<K_><<<(int)grid, 256, 0, stream>>>(P, w, P.part)); \
+    break;
+    CVF_STATS_CASE(1)
+    CVF_STATS_CASE(2)
+    CVF_STATS_CASE(3)
+    CVF_STATS_CASE(4)
+    CVF_STATS_CASE(5)
+    CVF_STATS_CASE(6)
+    CVF_STATS_CASE(7)
+    CVF_STATS_CASE(8)
+#undef CVF_STATS_CASE
+    default:
+      set_error("fast eigen path: k = %d", k);
+      return CVF_E_UNSUPPORTED;
+  }
   CVF_CUDA(cudaGetLastError());
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(ns + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, ns, 0, ns, stats_out));
   CVF_CUDA(cudaGetLastError());

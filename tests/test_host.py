@@ -157,7 +157,7 @@ def test_regautoencoder_layout_matches_reference():
 def test_custom_operators_are_registered():
     """The step is exposed as torch.library operators (namespace cvf) with fake kernels and autograd formulas."""
     from colvarsfinder import _ops  # noqa: F401
-    for name in ("eigen_stats", "eigen_grad", "eigen_combine", "eigen_tlag_sx", "eigen_tlag_seed", "eigen_tlag_combine", "ae_sums",
+    for name in ("eigen_stats", "eigen_grad", "eigen_combine", "eigen_loss", "eigen_tlag_sx", "eigen_tlag_seed", "eigen_tlag_combine", "ae_sums",
                  "align_fwd"):
         assert hasattr(torch.ops.cvf, name), name
     schema = str(torch.ops.cvf.eigen_stats.default._schema)

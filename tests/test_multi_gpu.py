@@ -56,6 +56,23 @@ def _worker(rank, world, port, out_dir):
         task.train()                                                     # unequal shards: must not hang (collective plan)
         res["iters"] = int(task.loss_list[0][0].shape[0])
         res["final"] = float(task.loss_list[-1][0][-1, 0])
+        # the same run with the iteration captured as a CUDA graph (NCCL all-reduces inside) replays the eager steps
+        hist = {}
+        for mode in ("0", "1"):
+            os.environ["CVF_CUDA_GRAPH"] = mode
+            os.environ["CVF_CUDA_GRAPH_MIN_STEPS"] = "1"
+            torch.manual_seed(1)
+            m2 = nn.EigenFunctions([66, 20, 20, 20, 1], 3)
+            t2 = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64)), utils.Align(base, list(range(22))), m2,
+                                        os.path.join(out_dir, f"g{mode}r{rank}"), 20.0, [1.0, 0.6, 0.3], k=3, batch_size=1500,
+                                        num_epochs=3, learning_rate=1e-3, save_model_every_step=0, device=dev, verbose=False,
+                                        debug_mode=False)
+            np.random.seed(4)
+            t2.train()
+            hist[mode] = torch.stack([l[0] for l in t2.loss_list])
+            if mode == "1":
+                res["replays"] = int(t2._graphed_step.replays)
+        res["graph_max_abs_diff"] = float((hist["0"] - hist["1"]).abs().max())
         np.savez(os.path.join(out_dir, f"dp{rank}.npz"), **res)
     finally:
         dist.destroy_process_group()
@@ -69,3 +86,5 @@ def test_two_gpu_step_matches_single_gpu(tmp_path):
     for r in (r0, r1):
         assert r["loss"] < 1e-6 and r["eig"] < 1e-6 and r["grad"] < 1e-5, dict(r)
     assert int(r0["iters"]) == int(r1["iters"]) and float(r0["final"]) == float(r1["final"])
+    assert int(r0["replays"]) > 0 and int(r1["replays"]) == int(r0["replays"])
+    assert float(r0["graph_max_abs_diff"]) == 0.0 and float(r1["graph_max_abs_diff"]) == 0.0

@@ -164,6 +164,16 @@ def test_custom_operators_pass_opcheck(tmp_path):
     torch.library.opcheck(torch.ops.cvf.eigen_stats.default, (X, w, params, ectx.handle, 0), test_utils=tests)
     y, stats = torch.ops.cvf.eigen_stats(X, w, params.detach(), ectx.handle, 0)
     torch.library.opcheck(torch.ops.cvf.eigen_combine.default, (stats.clone().requires_grad_(), ectx.handle), test_utils=tests)
+    torch.library.opcheck(torch.ops.cvf.eigen_loss.default, (X, w, params, ectx.handle), test_utils=tests)
+    # the fused operator and the two-operator composition give the same loss and gradients
+    la = _ops.eigen_loss(ectx, X, w)[0]
+    ga = torch.autograd.grad(la, list(model.parameters()))
+    y2, st2 = torch.ops.cvf.eigen_stats(X, w, ectx.packed_params(), ectx.handle, 0)
+    lb = torch.ops.cvf.eigen_combine(st2, ectx.handle)[0].to(torch.float32)
+    gb = torch.autograd.grad(lb, list(model.parameters()))
+    assert torch.equal(la, lb)
+    for a_, b_ in zip(ga, gb):
+        assert torch.allclose(a_, b_, rtol=1e-5, atol=1e-7 * float(a_.abs().max()))
     coef = torch.zeros(ectx.n_comb, dtype=torch.float64, device=DEV)
     torch.library.opcheck(torch.ops.cvf.eigen_grad.default, (X, w, y, params.detach(), coef, None, ectx.handle, 0, -1), test_utils=tests)
     yl = y + 0.1
