@@ -56,6 +56,8 @@ SYMBOLS = {
     "cvf_ae_step_target": (C.c_int, [_P, _P, _P, _I64, C.POINTER(Mlp), _P, _P, _P, _P, _SZ, _P]),
     "cvf_ae_set_wide_path": (C.c_int, [_I32]),
     "cvf_ae_set_fast_path": (C.c_int, [_I32]),
+    "cvf_weights_filter_workspace_bytes": (_SZ, [_I64]),
+    "cvf_weights_filter": (C.c_int, [_P, _I64, _D, _D, _P, _P, _P, _P, _SZ, _P]),
     "cvf_fma_probe": (C.c_int, [_P, _I32, C.POINTER(_D), _P]),
     "cvf_profile_enable": (C.c_int, [_I32]),
     "cvf_profile_num_kernels": (_I32, []),

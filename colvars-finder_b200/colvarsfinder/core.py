@@ -78,6 +78,14 @@ def _iteration_plan(n_train, n_test, batch_size):
     return bs_train, bs_test, n_train // max(bs_train, 1), n_test // max(bs_test, 1)
 
 
+def _shard_to_device(data, lo, hi, device):
+    """Rows [lo, hi) of a trajectory / weight array -- numpy (reference WeightedTrajectory) or torch (WeightedTrajectory(device=...))
+    -- as a contiguous float32 tensor on `device`."""
+    part = data[lo:hi]
+    t = part if torch.is_tensor(part) else torch.as_tensor(np.asarray(part))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
 def _split(n, test_ratio, draws):
     """Index split drawn like the reference: sklearn on numpy's global RNG, `draws` calls, last one kept."""
     from sklearn.model_selection import train_test_split
@@ -322,9 +330,8 @@ class EigenFunctionTask(TrainingTask):
         if self.verbose:
             print('\nEigenfunctions:\n', self.model, flush=True)
         self.init_model_and_optimizer()
-        traj = np.asarray(traj_obj.trajectory)
-        weights = np.asarray(traj_obj.weights)
-        self.tot_dim = traj[0, ...].size
+        traj, weights = traj_obj.trajectory, traj_obj.weights
+        self.tot_dim = int(np.prod(traj.shape[1:]))
         self._beta = beta
         if diag_coeff is not None:
             assert diag_coeff.dim() == 1 and diag_coeff.size(dim=0) == self.tot_dim, \
@@ -336,8 +343,8 @@ class EigenFunctionTask(TrainingTask):
         # that follow it so that index + lag_idx (reference core.py:511) stays local
         lo, hi = self._shard(traj.shape[0] - self.lag_idx)
         hi += self.lag_idx
-        self._traj = torch.as_tensor(traj[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
-        self._weights = torch.as_tensor(weights[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
+        self._traj = _shard_to_device(traj, lo, hi, self.device)
+        self._weights = _shard_to_device(weights, lo, hi, self.device)
         self._ctx = _ops.EigenContext(self.model, self.preprocessing_layer, traj.shape[1:], self.device, alpha, eig_weights,
                                       beta, diag_coeff, sort_eigvals_in_training)
 
@@ -450,10 +457,10 @@ class AutoEncoderTask(TrainingTask):
                          plot_frequency, verbose, debug_mode)
         assert isinstance(model, AutoEncoder), 'model must be an object of the class AutoEncoder'
         self.init_model_and_optimizer()
-        traj = np.asarray(traj_obj.trajectory)
+        traj = traj_obj.trajectory
         lo, hi = self._shard(traj.shape[0])
-        self._weights = torch.as_tensor(np.asarray(traj_obj.weights)[lo:hi]).to(device=self.device, dtype=torch.float32)
-        x = torch.as_tensor(traj[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
+        self._weights = _shard_to_device(traj_obj.weights, lo, hi, self.device)
+        x = _shard_to_device(traj, lo, hi, self.device)
         # whole-trajectory pre-pass (reference core.py:635) on the device
         self._feature_traj = self.preprocessing_layer(x)
         if self._feature_traj.dim() != 2:
@@ -568,13 +575,12 @@ class RegAutoEncoderTask(TrainingTask):
         self.init_model_and_optimizer()
         assert isinstance(model, RegAutoEncoder), 'model must be an object of the class RegAutoEncoder'
         assert model.num_reg == len(eig_weights), 'number of weights does not match the number of eigenfunctions!'
-        traj = np.asarray(traj_obj.trajectory)
-        weights = np.asarray(traj_obj.weights)
+        traj, weights = traj_obj.trajectory, traj_obj.weights
         self.alpha = alpha
         self.gamma = gamma
         self.eta = eta
         self.num_reg = model.num_reg
-        self.tot_dim = traj[0, ...].size
+        self.tot_dim = int(np.prod(traj.shape[1:]))
         self._eps = 1e-5
         self._eig_w = eig_weights
         self._cvec = None
@@ -601,8 +607,8 @@ class RegAutoEncoderTask(TrainingTask):
         lo, hi = self._shard(traj.shape[0] - halo)
         hi += halo
         self._halo = halo
-        self._traj = torch.as_tensor(traj[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
-        self._weights = torch.as_tensor(weights[lo:hi]).to(device=self.device, dtype=torch.float32).contiguous()
+        self._traj = _shard_to_device(traj, lo, hi, self.device)
+        self._weights = _shard_to_device(weights, lo, hi, self.device)
         if self.verbose:
             print('\nShape of trajectory data array:\n {}'.format(self._traj.shape), flush=True)
         # contexts of the CUDA passes

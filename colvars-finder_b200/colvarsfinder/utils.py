@@ -28,7 +28,10 @@ class WeightedTrajectory:
     """Trajectory data + statistical weights (reference utils.py:62-169)."""
 
     def __init__(self, universe=None, input_ag=None, traj_filename=None, weight_filename=None, min_w=0.0,
-                 max_w=float("inf"), verbose=True):
+                 max_w=float("inf"), verbose=True, device=None):
+        """``device`` (an addition to the reference's signature): a CUDA device on which the weights are normalised, the states
+        selected and the trajectory gathered (``cvf_weights_filter``); ``trajectory`` / ``weights`` are then device tensors, which
+        the task classes take as they are.  None keeps the reference's host-side numpy arrays."""
         if universe is not None:
             ix = universe.atoms.ix if input_ag is None else input_ag.ix
             self.trajectory = universe.trajectory.timeseries(order='fac')[:, ix, :]
@@ -48,20 +51,46 @@ class WeightedTrajectory:
         if weight_filename:
             import pandas as pd
             w = pd.read_csv(weight_filename, usecols=[0], header=None)[0].to_numpy(dtype=np.float64)
-            w = w / w.mean()
             if verbose:
                 print('\nloading weights from file: ', weight_filename)
             if self.n_frames != len(w):
                 raise ValueError('length in weight file does match the trajectory data!\n')
-            keep = (w > min_w) & (w < max_w)
-            self.trajectory = self.trajectory[keep, ...]
-            w = w[keep]
-            self.weights = w / w.mean()
+            if device is not None:
+                idx, self.weights = filter_weights(torch.as_tensor(w, device=device), min_w, max_w)
+                self.trajectory = torch.as_tensor(self.trajectory, device=device).index_select(0, idx)
+            else:
+                w = w / w.mean()
+                keep = (w > min_w) & (w < max_w)
+                self.trajectory = self.trajectory[keep, ...]
+                w = w[keep]
+                self.weights = w / w.mean()
             if verbose:
                 print('\nAfter selecting states whose weights are in [{:.3e}, {:.3e}] and renormalization:\n'
                       '\nShape of trajectory: {}'.format(min_w, max_w, self.trajectory.shape))
         else:
             self.weights = np.ones(self.n_frames)
+            if device is not None:
+                self.trajectory = torch.as_tensor(self.trajectory, device=device)
+                self.weights = torch.ones(self.n_frames, dtype=torch.float64, device=device)
+
+
+def filter_weights(w, min_w=0.0, max_w=float("inf")):
+    """The weight handling of reference utils.py:140-169 on the device: normalise ``w`` (CUDA tensor) to mean 1, keep the states
+    with min_w < w < max_w, renormalise the kept weights to mean 1.  Returns (indices of the kept states, their weights)."""
+    if not (isinstance(w, torch.Tensor) and w.is_cuda):
+        raise RuntimeError("filter_weights: the weights must be a CUDA tensor (this build has no CPU path)")
+    w = w.detach().to(torch.float64).contiguous()
+    n = w.numel()
+    L = _lib.lib()
+    ws = torch.empty(int(L.cvf_weights_filter_workspace_bytes(n)), dtype=torch.uint8, device=w.device)
+    idx = torch.empty(n, dtype=torch.int64, device=w.device)
+    out = torch.empty(n, dtype=torch.float64, device=w.device)
+    n_keep = torch.zeros(1, dtype=torch.int64, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(L.cvf_weights_filter(w.data_ptr(), n, float(min_w), float(min(max_w, 1.7e308)), idx.data_ptr(), out.data_ptr(),
+                                        n_keep.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()), "cvf_weights_filter")
+    m = int(n_keep.item())
+    return idx[:m], out[:m]
 
 
 def calc_weights(csv_filename, sampling_beta, sys_beta, traj_weight_filename='weights.txt', energy_col_idx=1):

@@ -177,6 +177,14 @@ int cvf_ae_set_fast_path(int32_t mode);
  * products per block (hi*hi + lo*hi + hi*lo) accumulated in fp32 in tensor memory; 1 = fp32 SIMT (FFMA2). */
 int cvf_ae_set_wide_path(int32_t mode);
 
+/* ---- WeightedTrajectory's weight handling on the device (utils.py:140-169) ----
+ * w [n] fp64 raw weights.  w is normalised to mean 1; states with min_w < w < max_w are kept; the kept weights are renormalised
+ * to mean 1.  idx_out [n] receives the ascending indices of the kept states, w_out [n] their weights, *n_keep_out (device) their
+ * number.  workspace: cvf_weights_filter_workspace_bytes(n). */
+size_t cvf_weights_filter_workspace_bytes(int64_t n);
+int cvf_weights_filter(const double* w, int64_t n, double min_w, double max_w, int64_t* idx_out, double* w_out,
+                       int64_t* n_keep_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Launch accounting for bench.py (no reference counterpart).  The library counts every kernel it launches; with
  * cvf_profile_enable(1) each launch is also bracketed by CUDA events on the stream it was enqueued on.
  * cvf_profile_read fills, per kernel id < cvf_profile_num_kernels(): summed milliseconds of the timed launches, how many were

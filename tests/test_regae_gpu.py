@@ -189,3 +189,37 @@ def test_custom_operators_pass_opcheck(tmp_path):
     loss = _ops.eigen_loss(ectx, X, w)[0]
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("n", [1, 5, 2048, 2049, 100003])
+def test_weight_filter_on_device_matches_reference_semantics(n, tmp_path):
+    """cvf_weights_filter against the reference's host-side arithmetic (utils.py:140-169): normalise, select (min_w, max_w),
+    renormalise; kept indices ascending; and WeightedTrajectory(device=...) feeding a task directly."""
+    from colvarsfinder import core, nn, utils
+    rng = np.random.default_rng(n)
+    w = np.exp(rng.normal(size=n))
+    lo, hi = (0.2, 3.0) if n > 1 else (0.0, float("inf"))
+    idx, wk = utils.filter_weights(torch.as_tensor(w, device=DEV), lo, hi)
+    wn = w / w.mean()
+    keep = (wn > lo) & (wn < hi)
+    assert np.array_equal(idx.cpu().numpy(), np.nonzero(keep)[0])
+    np.testing.assert_allclose(wk.cpu().numpy(), wn[keep] / wn[keep].mean(), rtol=1e-13)
+    if n == 2049:
+        t = 0.5 * np.arange(n)
+        X = rng.normal(size=(n, 2))
+        np.savetxt(tmp_path / "traj.txt", np.column_stack([t, X]))
+        np.savetxt(tmp_path / "w.txt", w)
+        host = utils.WeightedTrajectory(traj_filename=str(tmp_path / "traj.txt"), weight_filename=str(tmp_path / "w.txt"), min_w=lo,
+                                        max_w=hi, verbose=False)
+        devt = utils.WeightedTrajectory(traj_filename=str(tmp_path / "traj.txt"), weight_filename=str(tmp_path / "w.txt"), min_w=lo,
+                                        max_w=hi, verbose=False, device=DEV)
+        assert devt.trajectory.is_cuda and devt.weights.is_cuda
+        np.testing.assert_array_equal(devt.trajectory.cpu().numpy(), host.trajectory)
+        np.testing.assert_allclose(devt.weights.cpu().numpy(), host.weights, rtol=1e-13)
+        torch.manual_seed(2)
+        model = nn.EigenFunctions([2, 20, 20, 20, 1], 1)
+        task = core.EigenFunctionTask(devt, torch.nn.Identity(), model, str(tmp_path), 20.0, [1.0], k=1, device=DEV, verbose=False,
+                                      debug_mode=False)
+        assert task._traj.shape == (int(keep.sum()), 2)
+        loss = task.loss_func(task._traj, task._weights)[0]
+        assert torch.isfinite(loss)
