@@ -85,6 +85,71 @@ CVF_HD void cvf_jacobi_rot(float (&a)[4][4], float (&v)[4][4]) {
   }
 }
 
+
+// Largest eigenvalue / eigenvector of Horn's symmetric traceless 4x4 matrix `a` (entries O(1)) without iterating on the matrix:
+// Newton on its characteristic polynomial  P(l) = l^4 + c2 l^2 + c1 l + c0  from an upper bound of the largest root (all roots are
+// real, so the iteration descends monotonically onto it; Theobald 2005, "QCP"), then the eigenvector as the best-conditioned row
+// of adj(a - l I) = const * q q^T.  ~250 instructions instead of the ~2 500 of four cyclic Jacobi sweeps; the result only has to
+// be good to ~1e-4, the fp64 Newton polish of the rotation does the rest.  Returns false when the top eigenvalue is (nearly)
+// degenerate -- adj(a - l I) vanishes -- and the caller falls back to the Jacobi sweeps.
+CVF_HD bool cvf_top_quaternion_qcp(const float (&a)[4][4], float& q0, float& qx, float& qy, float& qz) {
+  const double a00 = a[0][0], a01 = a[0][1], a02 = a[0][2], a03 = a[0][3], a11 = a[1][1], a12 = a[1][2], a13 = a[1][3], a22 = a[2][2],
+               a23 = a[2][3], a33 = a[3][3];
+  // coefficients from the invariants of a symmetric matrix with zero trace: c2 = -tr(a^2)/2, c1 = -tr(a^3)/3, c0 = det(a)
+  const double s01 = a01 * a01, s02 = a02 * a02, s03 = a03 * a03, s12 = a12 * a12, s13 = a13 * a13, s23 = a23 * a23;
+  const double c2 = -0.5 * (a00 * a00 + a11 * a11 + a22 * a22 + a33 * a33) - (s01 + s02 + s03 + s12 + s13 + s23);
+  // 2x2 minors of rows 2,3 (columns i<j), shared by det(a) and by the cofactors below
+  const double m01 = a02 * a13 - a03 * a12, m02 = a02 * a23 - a03 * a22, m03 = a02 * a33 - a03 * a23;
+  const double m12 = a12 * a23 - a13 * a22, m13 = a12 * a33 - a13 * a23, m23 = a22 * a33 - a23 * a23;
+  const double c0 = a00 * (a11 * m23 - a12 * m13 + a13 * m12) - a01 * (a01 * m23 - a12 * m03 + a13 * m02) +
+                    a02 * (a01 * m13 - a11 * m03 + a13 * m01) - a03 * (a01 * m12 - a11 * m02 + a12 * m01);
+  // tr(a^3) = sum_ijk a_ij a_jk a_ki
+  const double t3 = a00 * a00 * a00 + a11 * a11 * a11 + a22 * a22 * a22 + a33 * a33 * a33 +
+                    3.0 * (a00 * (s01 + s02 + s03) + a11 * (s01 + s12 + s13) + a22 * (s02 + s12 + s23) + a33 * (s03 + s13 + s23)) +
+                    6.0 * (a01 * a02 * a12 + a01 * a03 * a13 + a02 * a03 * a23 + a12 * a13 * a23);
+  const double c1 = -t3 / 3.0;
+  // sum of squared roots = -2 c2, zero sum  =>  largest root <= sqrt(3/4 * (-2 c2))
+  double l = sqrt(-1.5 * c2);
+  if (!(l > 0.0)) return false;
+  for (int it = 0; it < 24; ++it) {
+    const double l2 = l * l;
+    const double P = (l2 + c2) * l2 + c1 * l + c0;
+    const double dP = (4.0 * l2 + 2.0 * c2) * l + c1;
+    if (!(dP > 0.0)) return false;
+    const double step = P * (double)(1.0f / (float)dP);   // approximate reciprocal: still a contraction, 3 instructions
+    l -= step;
+    if (fabs(step) < 1e-11 * l) break;
+  }
+  // k = a - l I; cofactors of the symmetric 4x4 (adjugate entries), fp32 is enough
+  const float k00 = (float)(a00 - l), k11 = (float)(a11 - l), k22 = (float)(a22 - l), k33 = (float)(a33 - l);
+  const float k01 = a[0][1], k02 = a[0][2], k03 = a[0][3], k12 = a[1][2], k13 = a[1][3], k23 = a[2][3];
+  // 2x2 minors of rows (2,3) and rows (0,1)
+  const float p01 = k02 * k13 - k03 * k12, p02 = k02 * k23 - k03 * k22, p03 = k02 * k33 - k03 * k23;
+  const float p12 = k12 * k23 - k13 * k22, p13 = k12 * k33 - k13 * k23, p23 = k22 * k33 - k23 * k23;
+  const float r01 = k00 * k11 - k01 * k01, r02 = k00 * k12 - k01 * k02, r03 = k00 * k13 - k01 * k03;
+  const float r12 = k01 * k12 - k11 * k02, r13 = k01 * k13 - k11 * k03, r23 = k02 * k13 - k12 * k03;
+  // adj_ij (symmetric); rows (2,3) minors p serve rows 0,1 of the adjugate, rows (0,1) minors r serve rows 2,3
+  const float A00 = k11 * p23 - k12 * p13 + k13 * p12;
+  const float A01 = -(k01 * p23 - k12 * p03 + k13 * p02);
+  const float A02 = k01 * p13 - k11 * p03 + k13 * p01;
+  const float A03 = -(k01 * p12 - k11 * p02 + k12 * p01);
+  const float A11 = k00 * p23 - k02 * p03 + k03 * p02;
+  const float A12 = -(k00 * p13 - k01 * p03 + k03 * p01);
+  const float A13 = k00 * p12 - k01 * p02 + k02 * p01;
+  const float A22 = k33 * r01 - k13 * r03 + k03 * r13;
+  const float A23 = -(k23 * r01 - k13 * r02 + k03 * r12);
+  const float A33 = k22 * r01 - k12 * r02 + k02 * r12;
+  // the row with the largest diagonal entry |const| q_i^2 is the best-conditioned multiple of q
+  float best = fabsf(A00);
+  q0 = A00, qx = A01, qy = A02, qz = A03;
+  if (fabsf(A11) > best) best = fabsf(A11), q0 = A01, qx = A11, qy = A12, qz = A13;
+  if (fabsf(A22) > best) best = fabsf(A22), q0 = A02, qx = A12, qy = A22, qz = A23;
+  if (fabsf(A33) > best) best = fabsf(A33), q0 = A03, qx = A13, qy = A23, qz = A33;
+  (void)r23;
+  // |adj| ~ product of the gaps to the other three eigenvalues (entries of a are O(1)): tiny means a degenerate top eigenvalue
+  return best > 1e-6f;
+}
+
 // H[9] row-major covariance (x_A-c)^T ref in double.  Outputs R[9] (row-major, y = (x-c) R) and,
 // if Kinv != nullptr, the inverse of K = tr(M) I - M, M = sym(R^T H), as (xx,xy,xz,yy,yz,zz).
 CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out = nullptr) {
@@ -108,28 +173,33 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
     a[2][3] = a[3][2] = sc * (Syz + Szy);
     a[3][3] = sc * (-Sxx - Syy + Szz);
   }
+  float q0, qx, qy, qz;
+  if (!cvf_top_quaternion_qcp(a, q0, qx, qy, qz)) {
+    // (nearly) degenerate top eigenvalue: cyclic Jacobi on the 4x4 (rare; the two paths may diverge inside a warp)
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0f : 0.0f;
-  for (int sweep = 0; sweep < CVF_JACOBI_SWEEPS; ++sweep) {
-    cvf_jacobi_rot<0, 1>(a, v);
-    cvf_jacobi_rot<0, 2>(a, v);
-    cvf_jacobi_rot<0, 3>(a, v);
-    cvf_jacobi_rot<1, 2>(a, v);
-    cvf_jacobi_rot<1, 3>(a, v);
-    cvf_jacobi_rot<2, 3>(a, v);
-  }
-  // column of the largest eigenvalue (branch-free select keeps v in registers)
-  float best = a[0][0], q0 = v[0][0], qx = v[1][0], qy = v[2][0], qz = v[3][0];
+      for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0f : 0.0f;
+    for (int sweep = 0; sweep < CVF_JACOBI_SWEEPS; ++sweep) {
+      cvf_jacobi_rot<0, 1>(a, v);
+      cvf_jacobi_rot<0, 2>(a, v);
+      cvf_jacobi_rot<0, 3>(a, v);
+      cvf_jacobi_rot<1, 2>(a, v);
+      cvf_jacobi_rot<1, 3>(a, v);
+      cvf_jacobi_rot<2, 3>(a, v);
+    }
+    // column of the largest eigenvalue (branch-free select keeps v in registers)
+    float best = a[0][0];
+    q0 = v[0][0], qx = v[1][0], qy = v[2][0], qz = v[3][0];
 #pragma unroll
-  for (int c = 1; c < 4; ++c) {
-    const bool take = a[c][c] > best;
-    best = take ? a[c][c] : best;
-    q0 = take ? v[0][c] : q0;
-    qx = take ? v[1][c] : qx;
-    qy = take ? v[2][c] : qy;
-    qz = take ? v[3][c] : qz;
+    for (int c = 1; c < 4; ++c) {
+      const bool take = a[c][c] > best;
+      best = take ? a[c][c] : best;
+      q0 = take ? v[0][c] : q0;
+      qx = take ? v[1][c] : qx;
+      qy = take ? v[2][c] : qy;
+      qz = take ? v[3][c] : qz;
+    }
   }
   double Rd[9];
   {
@@ -147,8 +217,9 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
     Rd[8] = w * w - x * x - y * y + z * z;
   }
   double Ki[6] = {0, 0, 0, 0, 0, 0};
+  double last_th2 = 0.0;   // squared size of the previous Newton step (0 before the first)
   // Newton on the rotation: R <- R exp([d]x),  K d = axial(M - M^T),  M = R^T H.  Error e -> O(e^2).
-  for (int it = 0; it < CVF_NEWTON_EVALS; ++it) {
+  for (int it = 0; it < CVF_NEWTON_EVALS + 2; ++it) {
     double M[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -162,13 +233,15 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
     const double det = kxx * c00 + kxy * c01 + kxz * c02;
     const double idet = det != 0.0 ? 1.0 / det : 0.0;
     Ki[0] = c00 * idet, Ki[1] = c01 * idet, Ki[2] = c02 * idet, Ki[3] = c11 * idet, Ki[4] = c12 * idet, Ki[5] = c22 * idet;
-    if (it == CVF_NEWTON_EVALS - 1) break;   // K^-1 of the polished rotation is what the Jacobian uses
+    // K^-1 of the polished rotation is what the Jacobian uses: stop after the planned evaluations once the last step was tiny
+    if (it >= CVF_NEWTON_EVALS - 1 && (it == CVF_NEWTON_EVALS + 1 || last_th2 < 1e-16)) break;
     const double t0 = M[7] - M[5], t1 = M[2] - M[6], t2 = M[3] - M[1];
     double d0 = Ki[0] * t0 + Ki[1] * t1 + Ki[2] * t2;
     double d1 = Ki[1] * t0 + Ki[3] * t1 + Ki[4] * t2;
     double d2 = Ki[2] * t0 + Ki[4] * t1 + Ki[5] * t2;
     const double th2 = d0 * d0 + d1 * d1 + d2 * d2;
-    if (!(th2 < 0.01)) break;   // degenerate frame (K singular): keep the Jacobi rotation
+    if (!(th2 < 0.01)) break;   // degenerate frame (K singular): keep the starting rotation
+    last_th2 = th2;
     const double A = 1.0 - th2 / 6.0 + th2 * th2 / 120.0;        // sin(th)/th
     const double Bc = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;      // (1-cos th)/th^2
     // E = I + A [d]x + B [d]x^2
