@@ -73,7 +73,9 @@ __device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long
 }
 
 constexpr int kP1Frames = 512, kP1Threads = 256;
-constexpr int kDw1Chunk = 24;   // columns of dW_1 formed per pass over the warp's 32 frames (pass 2)
+// columns of dW_1 formed per pass over the warp's 32 frames (pass 2): 24, or 28 when that divides the padded input width
+// (C4: 84 = 3 x 28, so that three networks' totals fit the 256 tensor-memory columns of a warp)
+__host__ __device__ constexpr int dw1_chunk_of(int drp) { return drp % 28 == 0 ? 28 : 24; }
 constexpr int kP2MaxWarps = 8, kP2MinWarps = 4;
 
 // Shared-memory image of one network (floats; every block 16-byte aligned because H % 4 == 0 and d_rp % 12 == 0):
@@ -682,15 +684,6 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
         const int r = i / (F / 4), c4 = i - r * (F / 4);
         st4(tile + r * F + 4 * c4, __ldg(reinterpret_cast<const float4*>(P.Y + (size_t)r * P.Bp + f0) + c4));
       }
-      // the CTA's next tile into L2 while this one is processed: its loads then find every line on the chip
-      const long long tn = t + gridDim.x;
-      if (tn < n_tiles) {
-        const int lines = P.tile_rows * (F * 4 / 128);
-        for (int i = tid; i < lines; i += kP1Threads) {
-          const int r = i / (F * 4 / 128), c = i - r * (F * 4 / 128);
-          prefetch_l2_line(P.Y + (size_t)r * P.Bp + tn * F + 32 * c);
-        }
-      }
     }
     __syncthreads();
     for (int n = 0; n < k; ++n) {
@@ -943,61 +936,100 @@ __global__ void __launch_bounds__(256) stats_kernel(const FastPlan P, const floa
 // lanes of its quadrant x 256 columns, every lane keeps the totals of the (output, input) pairs it computes anyway in columns
 // of its own lane, and one tcgen05.ld / add / tcgen05.st round trip per group of 16 replaces the atomics (single owner, fixed
 // order: deterministic).  The totals are fp32 over the ~10^2 tiles a warp processes and go to the fp64 vector once, at the end.
+// tcgen05.ld / tcgen05.st of N consecutive 32-bit columns of the calling lane (32x32b shape: one TMEM lane per thread), N = 1, 2, 4, 8, 16
 template <int N>
-struct TmIo;
+struct TmPiece;
 template <>
-struct TmIo<1> {
-  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[1]) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(a) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    v[0] = __uint_as_float(r);
+struct TmPiece<1> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(a) : "memory");
   }
-  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[1]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(__float_as_uint(v[0])) : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(r[0]) : "memory");
   }
 };
 template <>
-struct TmIo<16> {
-  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[16]) {
-    uint32_t r[16];
+struct TmPiece<2> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a) : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(r[0]), "r"(r[1]) : "memory");
+  }
+};
+template <>
+struct TmPiece<4> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+  }
+};
+template <>
+struct TmPiece<8> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(a)
+                 : "memory");
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  }
+};
+template <>
+struct TmPiece<16> {
+  static __device__ __forceinline__ void ld(uint32_t a, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(a)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
   }
-  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[16]) {
+  static __device__ __forceinline__ void st(uint32_t a, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(a),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 };
-template <>
-struct TmIo<32> {
-  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[32]) {
-    float lo[16], hi[16];
-    TmIo<16>::ld(a, lo);
-    TmIo<16>::ld(a + 16, hi);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = lo[i], v[16 + i] = hi[i];
+// N columns as power-of-two pieces (16s first, then 8, 4, 2, 1), one wait at the end
+template <int N>
+struct TmIo {
+  template <int OFF, int REM>
+  static __device__ __forceinline__ void ld_pieces(uint32_t a, uint32_t* r) {
+    if constexpr (REM > 0) {
+      constexpr int P = REM >= 16 ? 16 : REM >= 8 ? 8 : REM >= 4 ? 4 : REM >= 2 ? 2 : 1;
+      TmPiece<P>::ld(a + OFF, r + OFF);
+      ld_pieces<OFF + P, REM - P>(a, r);
+    }
   }
-  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[32]) {
-    float lo[16], hi[16];
+  template <int OFF, int REM>
+  static __device__ __forceinline__ void st_pieces(uint32_t a, const uint32_t* r) {
+    if constexpr (REM > 0) {
+      constexpr int P = REM >= 16 ? 16 : REM >= 8 ? 8 : REM >= 4 ? 4 : REM >= 2 ? 2 : 1;
+      TmPiece<P>::st(a + OFF, r + OFF);
+      st_pieces<OFF + P, REM - P>(a, r);
+    }
+  }
+  static __device__ __forceinline__ void ld(uint32_t a, float (&v)[N]) {
+    uint32_t r[N];
+    ld_pieces<0, N>(a, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) lo[i] = v[i], hi[i] = v[16 + i];
-    TmIo<16>::st(a, lo);
-    TmIo<16>::st(a + 16, hi);
+    for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+  }
+  static __device__ __forceinline__ void st(uint32_t a, const float (&v)[N]) {
+    uint32_t r[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = __float_as_uint(v[i]);
+    st_pieces<0, N>(a, r);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
 };
 // totals[a .. a+N) += v
@@ -1013,7 +1045,7 @@ __device__ __forceinline__ void tm_add(uint32_t a, const float (&v)[N]) {
 // e = j * TI + i is kept by the half-warp e & 1, in slot e >> 1 of the group.
 template <int TO, int TI, int GS>
 __device__ __forceinline__ void tm_add_tile(uint32_t a, const float (&r)[TO][TI], int half) {
-  static_assert((TO * TI + 1) / 2 <= GS, "group too small");
+  static_assert((TO * TI + 1) / 2 == GS, "group size = ceil(entries / 2)");
   float v[GS];
 #pragma unroll
   for (int p = 0; p < GS; ++p) {
@@ -1024,7 +1056,6 @@ __device__ __forceinline__ void tm_add_tile(uint32_t a, const float (&r)[TO][TI]
   }
   tm_add<GS>(a, v);
 }
-__host__ __device__ constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : n <= 16 ? 16 : 32; }
 constexpr int kTmColsPerWarp = 256;
 
 // ------------------------------------------------------------------------------------------------ pass 2
@@ -1090,7 +1121,7 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
 // layer being reduced, then the flush buffer).  The first layer's weight gradient needs r and vhat of every frame as operand
 // rows once (s_1, G_1) exist, when the Z rows are free again: they are re-staged from global memory (L2: the warp read r and
 // wrote vhat a few microseconds earlier) in double-buffered column chunks, so no intermediate of pass 2 goes through HBM.
-template <int H, int NH>
+template <int H, int NH, int CW>
 __global__ void __launch_bounds__(256, 1)
 pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp,
              const float* __restrict__ seed_extra) {
@@ -1121,9 +1152,9 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   for (int i = lane; i < n_part; i += 32) part[i] = 0.0;
   // tensor-memory accumulators (see above): per network n_chunks groups for dW_1, NH - 1 groups for the hidden layers' dW,
   // four single slots (dWout | dbout by lane, db_NH .. db_1 by lane)
-  constexpr int CI1 = kDw1Chunk / 4;
-  constexpr int GS1 = pow2_at_least((TQ * CI1 + 1) / 2), GSH = pow2_at_least((TQ * TQ + 1) / 2);
-  const int n_chunks1 = inline_dw1 ? 1 : (d_r + kDw1Chunk - 1) / kDw1Chunk;
+  constexpr int CI1 = CW / 4;
+  constexpr int GS1 = (TQ * CI1 + 1) / 2, GSH = (TQ * TQ + 1) / 2, GSI = (TQ * 3 + 1) / 2;   // dW_1 chunk, hidden dW, 12-column dW_1
+  const int n_chunks1 = inline_dw1 ? 1 : (d_r + CW - 1) / CW;
   const int tm_hid = n_chunks1 * GS1, tm_sing = tm_hid + (NH - 1) * GSH, tm_per_net = tm_sing + 4;
   const int tm_nets = kTmColsPerWarp / tm_per_net < k ? kTmColsPerWarp / tm_per_net : k;   // further networks: fp64 atomics
   __shared__ uint32_t tmem_slot;
@@ -1392,14 +1423,14 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           }
         } else {
           // dW_1 = sum_f s_1 (x) r + (scale G_1) (x) vhat:  (s_1 | scale G_1) become X rows; r and vhat (the latter was written to
-          // global memory in place of u during layer 1) come back in column chunks of kDw1Chunk rows each, double-buffered in the
+          // global memory in place of u during layer 1) come back in column chunks of CW rows each, double-buffered in the
           // Z rows that the reverse sweep no longer needs
           __syncwarp();
 #pragma unroll
           for (int o = 0; o < H; ++o) Xr[o * RP + lane] = sl[o], Xr[(H + o) * RP + lane] = scale * gl[o];
           __syncwarp();
           if (!inline_dw1) {
-            constexpr int CW = kDw1Chunk, CI = CW / 4;      // columns per chunk, columns per lane (4 column groups)
+            constexpr int CI = CW / 4;      // columns per lane (4 column groups) of a chunk of CW columns
             const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
             const int n_chunks = (d_r + CW - 1) / CW;
             const float* Yt = P.Y + t * 32;
@@ -1471,7 +1502,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
               }
             __syncwarp();   // every lane has finished reading the X rows
             if (tm) {
-              tm_add_tile<TQ, 3, GS1>(tmn, r1, half);
+              tm_add_tile<TQ, 3, GSI>(tmn, r1, half);
             } else {
               if (half == 0) {
 #pragma unroll
@@ -1496,17 +1527,27 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
     for (int n = 0; n < tm_nets; ++n) {
       double* pn = part + (size_t)n * P.n_params;
       const uint32_t tmn = tmw + (uint32_t)(n * tm_per_net);
-      for (int c = 0; c < n_chunks1; ++c) {
-        float v[GS1];
-        TmIo<GS1>::ld(tmn + c * GS1, v);
-        const int ti = inline_dw1 ? 3 : CI1;
+      if (inline_dw1) {
+        float v[GSI];
+        TmIo<GSI>::ld(tmn, v);
 #pragma unroll
-        for (int p = 0; p < GS1; ++p) {
+        for (int p = 0; p < GSI; ++p) {
           const int e = 2 * p + half;
-          if (e >= TQ * ti) continue;
-          const int j = e / ti, i = e - j * ti;
-          const int col = inline_dw1 ? 4 * i + ig : c * kDw1Chunk + CI1 * ig + i;
+          if (e >= TQ * 3) continue;
+          const int j = e / 3, i = e - j * 3, col = 4 * i + ig;
           if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] = (double)v[p];
+        }
+      } else {
+        for (int c = 0; c < n_chunks1; ++c) {
+          float v[GS1];
+          TmIo<GS1>::ld(tmn + c * GS1, v);
+#pragma unroll
+          for (int p = 0; p < GS1; ++p) {
+            const int e = 2 * p + half;
+            if (e >= TQ * CI1) continue;
+            const int j = e / CI1, i = e - j * CI1, col = c * CW + CI1 * ig + i;
+            if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] = (double)v[p];
+          }
         }
       }
       for (int l = 2; l <= NH; ++l) {
@@ -1559,7 +1600,7 @@ static bool pass2_inline_dw1(int drp) { return drp == 12; }
 static int pass2_rows_per_warp(int drp, int H, int NH) {
   // Z rows (A_l | T_l of every layer; later two double-buffered chunks of r | vhat rows for dW_1) followed by the X rows;
   // the staging of layer 1 (r, u, Jacobian vectors) may overlap the X rows, which are not in use yet
-  const int z = 2 * NH * H > 4 * kDw1Chunk ? 2 * NH * H : 4 * kDw1Chunk;
+  const int z = 2 * NH * H > 4 * dw1_chunk_of(drp) ? 2 * NH * H : 4 * dw1_chunk_of(drp);
   const int need = z + 2 * H, stage = 2 * drp + 12;
   return (need > stage ? need : stage) + (pass2_inline_dw1(drp) ? 2 * drp : 0);
 }
@@ -1824,11 +1865,16 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
     return CVF_E_UNSUPPORTED;
   }
   const size_t smem2 = pass2_smem_bytes(k, P.img2_floats, P.geo_floats, P.d_rp, H, NH, nw);
-  CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
   const long long n_tiles = P.Bp / 32;
   long long grid = sm_count();
   if ((n_tiles + nw - 1) / nw < grid) grid = (n_tiles + nw - 1) / nw;
-  CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra));
+  if (dw1_chunk_of(P.d_rp) == 28) {
+    CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH, 28><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra));
+  } else {
+    CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH, 24><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra));
+  }
   CVF_CUDA(cudaGetLastError());
   const int n_part = k * np.n_params;
   CVF_LAUNCH(K_REDUCE, stream, reduce_partials_kernel<<<(n_part + 127) / 128, 128, 0, stream>>>(P.part, (int)grid, nw * n_part, 0, n_part, grad_out));
