@@ -588,19 +588,22 @@ eigen_tlag_combine_op.register_autograd(_tlag_combine_backward, setup_context=_t
 
 
 @torch.library.custom_op("cvf::eigen_loss", mutates_args=())
-def eigen_loss_op(X: torch.Tensor, w: torch.Tensor, params: torch.Tensor, handle: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """cvf::eigen_stats + cvf::eigen_combine in one operator (the generator branch of EigenFunctionTask.loss_func): the backward
-    pass reads the coefficient blocks straight out of the combine vector instead of going through d loss / d stats."""
+def eigen_loss_op(X: torch.Tensor, w: torch.Tensor, params: torch.Tensor, handle: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """cvf::eigen_stats + cvf::eigen_combine in one operator (the generator branch of EigenFunctionTask.loss_func) -> (y, combine
+    vector, loss as a float32 scalar).  The loss is an output of its own so that no slicing of the combine vector sits on the
+    autograd path, and the backward pass reads the coefficient blocks straight out of the combine vector."""
     ectx = _context(handle)
     y, stats = ectx.stats(X, w, params, 0)
     allreduce_sum_(stats)
-    return y, ectx.combine(stats)
+    comb = ectx.combine(stats)
+    return y, comb, comb[0].to(torch.float32)
 
 
 @eigen_loss_op.register_fake
 def _(X, w, params, handle):
     ectx = _context(handle)
-    return X.new_empty((ectx.k, X.shape[0]), dtype=torch.float32), X.new_empty((ectx.n_comb,), dtype=torch.float64)
+    return (X.new_empty((ectx.k, X.shape[0]), dtype=torch.float32), X.new_empty((ectx.n_comb,), dtype=torch.float64),
+            X.new_empty((), dtype=torch.float32))
 
 
 def _eigen_loss_setup(ctx, inputs, output):
@@ -611,31 +614,36 @@ def _eigen_loss_setup(ctx, inputs, output):
     ctx.serial = _context(handle).serial(0)
 
 
-def _eigen_loss_backward(ctx, g_y, g_comb):
+def _eigen_loss_backward(ctx, g_y, g_comb, g_loss):
     X, w, params, y, comb = ctx.saved_tensors
-    if g_comb is None and g_y is None:
-        return None, None, None, None
-    g = eigen_grad_op(X, w, y, params, comb, g_y, ctx.handle, 0, ctx.serial)
     if g_comb is not None:
-        g = g * g_comb[0].to(torch.float32)      # only the loss entry of the combine vector is differentiable
+        g_loss = g_comb[0].to(torch.float32) if g_loss is None else g_loss + g_comb[0].to(torch.float32)
+    if g_loss is None and g_y is None:
+        return None, None, None, None
+    if g_loss is None:      # only y was used downstream: zero coefficients, the seeds come from g_y alone
+        comb = torch.zeros_like(comb)
+    g = eigen_grad_op(X, w, y, params, comb, g_y, ctx.handle, 0, ctx.serial)
+    if g_loss is not None:
+        g = g * g_loss
     return None, None, g, None
 
 
 eigen_loss_op.register_autograd(_eigen_loss_backward, setup_context=_eigen_loss_setup)
 
 
-def _loss_outputs(comb, k):
-    out32 = comb[:3 + k].to(torch.float32)
-    loss, obj, pen, eig = out32[0], out32[1].detach(), out32[2].detach(), out32[3:3 + k].detach()
-    cvec = comb[3 + k:3 + 2 * k].detach().to(torch.int64)
-    return loss, eig, obj, pen, cvec
+def _loss_outputs(comb, k, loss=None):
+    d = comb.detach()
+    out32 = d[:3 + k].to(torch.float32)
+    if loss is None:
+        loss = comb[0].to(torch.float32)
+    return loss, out32[3:3 + k], out32[1], out32[2], d[3 + k:3 + 2 * k].to(torch.int64)
 
 
 def eigen_loss(ectx: EigenContext, X, weight):
     """EigenFunctionTask.loss_func, generator branch (reference core.py:387-457); ``loss.backward()`` = core.py:517."""
     X, weight = _check_batch(X, weight, "EigenFunctionTask.loss_func")
-    _, comb = eigen_loss_op(X, weight, ectx.packed_params(), ectx.handle)
-    return _loss_outputs(comb, ectx.k)
+    _, comb, loss = eigen_loss_op(X, weight, ectx.packed_params(), ectx.handle)
+    return _loss_outputs(comb, ectx.k, loss)
 
 
 def eigen_lag_loss(ectx: EigenContext, tau, X, weight, X_lagged, weight_lagged):

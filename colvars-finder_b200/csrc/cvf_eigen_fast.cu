@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(384, 2) jjt_kernel(const FastPlan P, int W) {
 // ------------------------------------------------------------------------------------------------ pass 1
 // One CTA per SM, 256 threads, tiles of 512 frames; thread t owns frames 2t, 2t+1 of the tile.
 template <int H, int NH>
-__global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, float* __restrict__ y_out) {
+__global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, float* __restrict__ y_out, int net_split) {
   extern __shared__ __align__(16) float sm[];
   typedef Img<H, NH> I;
   constexpr int F = kP1Frames, HP = H / 2;
@@ -675,7 +675,12 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
   for (int i = tid; i < k * P.img_floats + P.geo_floats; i += kP1Threads) sm[i] = P.img[i];
   const long long n_tiles = P.Bp / F;
   const int c0 = 2 * tid;
-  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  // work items: a tile with all its networks, or -- small batches, net_split -- one (tile, network) pair, so that a batch of a few
+  // dozen tiles still spreads over the SMs instead of running k networks in sequence on a quarter of them
+  const long long n_items = net_split ? n_tiles * k : n_tiles;
+  for (long long q = blockIdx.x; q < n_items; q += gridDim.x) {
+    const long long t = net_split ? q / k : q;
+    const int n_begin = net_split ? (int)(q - t * k) : 0, n_end = net_split ? n_begin + 1 : k;
     const long long f0 = t * F;
     __syncthreads();
     {
@@ -686,7 +691,7 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
       }
     }
     __syncthreads();
-    for (int n = 0; n < k; ++n) {
+    for (int n = n_begin; n < n_end; ++n) {
       const float* W = wsm + n * P.img_floats;
       float om[NH][2][H];   // 1 - A_l^2
       float a[2][H];        // current activations
@@ -1124,7 +1129,7 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
 template <int H, int NH, int CW>
 __global__ void __launch_bounds__(256, 1)
 pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp,
-             const float* __restrict__ seed_extra) {
+             const float* __restrict__ seed_extra, int net_split) {
   extern __shared__ __align__(16) float sm[];
   typedef Img<H, NH> I;
   constexpr int HP = H / 2, RP = kRowPad, TQ = H / 4;
@@ -1149,7 +1154,6 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   for (int i = tid; i < nw * rows_per_warp * RP; i += nt) rows0[i] = 0.0f;
   const int n_part = k * P.n_params;
   double* part = P.part + ((size_t)blockIdx.x * nw + warp) * n_part;
-  for (int i = lane; i < n_part; i += 32) part[i] = 0.0;
   // tensor-memory accumulators (see above): per network n_chunks groups for dW_1, NH - 1 groups for the hidden layers' dW,
   // four single slots (dWout | dbout by lane, db_NH .. db_1 by lane)
   constexpr int CI1 = CW / 4;
@@ -1157,6 +1161,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   const int n_chunks1 = inline_dw1 ? 1 : (d_r + CW - 1) / CW;
   const int tm_hid = n_chunks1 * GS1, tm_sing = tm_hid + (NH - 1) * GSH, tm_per_net = tm_sing + 4;
   const int tm_nets = kTmColsPerWarp / tm_per_net < k ? kTmColsPerWarp / tm_per_net : k;   // further networks: fp64 atomics
+  for (int i = tm_nets * P.n_params + lane; i < n_part; i += 32) part[i] = 0.0;            // ... to this warp's vector in global memory
   __shared__ uint32_t tmem_slot;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_slot)),
@@ -1180,14 +1185,18 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
   const double* c_a0 = comb + 2 * k + k * k;
 
   const long long n_tiles = P.Bp / 32;
-  for (long long t = (long long)blockIdx.x * nw + warp; t < n_tiles; t += (long long)gridDim.x * nw) {
+  // work items: a 32-frame tile with all its networks, or -- small batches, net_split -- one (tile, network) pair per item
+  const long long n_items = net_split ? n_tiles * k : n_tiles;
+  for (long long q = (long long)blockIdx.x * nw + warp; q < n_items; q += (long long)gridDim.x * nw) {
+    const long long t = net_split ? q / k : q;
+    const int n_begin = net_split ? (int)(q - t * k) : 0, n_end = net_split ? n_begin + 1 : k;
     const long long f = t * 32 + lane;
     const float wf = f < P.B ? __ldg(w + f) : 0.0f;
-    const long long t_next = t + (long long)gridDim.x * nw;
+    const long long t_next = net_split ? n_tiles : t + (long long)gridDim.x * nw;   // no look-ahead across work items when split
     float ysv[kMaxK];
 #pragma unroll
     for (int j = 0; j < kMaxK; ++j) ysv[j] = j < k ? __ldg(P.Ys + (size_t)j * P.Bp + f) : 0.0f;
-    for (int n = 0; n < k; ++n) {
+    for (int n = n_begin; n < n_end; ++n) {
       const float* W = wsm + n * P.img2_floats;
       double* pn = part + (size_t)n * P.n_params;
       const bool tm = n < tm_nets;                          // this network's totals live in tensor memory
@@ -1198,7 +1207,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       stage_rows(Su, Ut, d_r, P.Bp, lane);
       if (P.kind == 1) stage_rows(Sj, P.JQ + ((size_t)n * 12) * P.Bp + t * 32, 12, P.Bp, lane);
       // L2 prefetch of what is read next: the next network's u rows, or the next tile's r rows and first u rows
-      if (n + 1 < k) {
+      if (n + 1 < n_end) {
         prefetch_rows(P.U + ((size_t)(n + 1) * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
         if (P.kind == 1) prefetch_rows(P.JQ + ((size_t)(n + 1) * 12) * P.Bp + t * 32, 12, P.Bp, lane);
       } else if (t_next < n_tiles) {
@@ -1521,67 +1530,79 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       }
     }
   }
-  // tensor-memory totals -> this warp's fp64 vector (every entry has exactly one owning lane)
+  // ---- the CTA's gradient vector: the warps add their tensor-memory totals, one warp after the other (fixed order:
+  // deterministic), into an fp64 vector in the shared memory the operand rows no longer need; networks whose totals went to
+  // per-warp vectors in global memory by atomics (beyond tm_nets) are folded in after them; one vector per CTA leaves the SM
+  __syncthreads();
+  double* acc = reinterpret_cast<double*>(rows0);   // [tm_nets * n_params]: at most three networks' parameters, far below the rows' size
+  const int n_acc = tm_nets * P.n_params;
+  for (int i = tid; i < n_acc; i += nt) acc[i] = 0.0;
+  __syncthreads();
   {
     const int half = lane >> 4, l16 = lane & 15, og = l16 >> 2, ig = l16 & 3;
-    for (int n = 0; n < tm_nets; ++n) {
-      double* pn = part + (size_t)n * P.n_params;
-      const uint32_t tmn = tmw + (uint32_t)(n * tm_per_net);
-      if (inline_dw1) {
-        float v[GSI];
-        TmIo<GSI>::ld(tmn, v);
+    for (int qw = 0; qw < nw; ++qw) {
+      if (warp == qw) {
+        for (int n = 0; n < tm_nets; ++n) {
+          double* pn = acc + (size_t)n * P.n_params;
+          const uint32_t tmn = tmw + (uint32_t)(n * tm_per_net);
+          if (inline_dw1) {
+            float v[GSI];
+            TmIo<GSI>::ld(tmn, v);
 #pragma unroll
-        for (int p = 0; p < GSI; ++p) {
-          const int e = 2 * p + half;
-          if (e >= TQ * 3) continue;
-          const int j = e / 3, i = e - j * 3, col = 4 * i + ig;
-          if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] = (double)v[p];
-        }
-      } else {
-        for (int c = 0; c < n_chunks1; ++c) {
-          float v[GS1];
-          TmIo<GS1>::ld(tmn + c * GS1, v);
+            for (int p = 0; p < GSI; ++p) {
+              const int e = 2 * p + half;
+              if (e >= TQ * 3) continue;
+              const int j = e / 3, i = e - j * 3, col = 4 * i + ig;
+              if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] += (double)v[p];
+            }
+          } else {
+            for (int c = 0; c < n_chunks1; ++c) {
+              float v[GS1];
+              TmIo<GS1>::ld(tmn + c * GS1, v);
 #pragma unroll
-          for (int p = 0; p < GS1; ++p) {
-            const int e = 2 * p + half;
-            if (e >= TQ * CI1) continue;
-            const int j = e / CI1, i = e - j * CI1, col = c * CW + CI1 * ig + i;
-            if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] = (double)v[p];
+              for (int p = 0; p < GS1; ++p) {
+                const int e = 2 * p + half;
+                if (e >= TQ * CI1) continue;
+                const int j = e / CI1, i = e - j * CI1, col = c * CW + CI1 * ig + i;
+                if (col < d_r) pn[P.gw_off[0] + (4 * j + og) * d_r + col] += (double)v[p];
+              }
+            }
+          }
+          for (int l = 2; l <= NH; ++l) {
+            float v[GSH];
+            TmIo<GSH>::ld(tmn + tm_hid + (l - 2) * GSH, v);
+#pragma unroll
+            for (int p = 0; p < GSH; ++p) {
+              const int e = 2 * p + half;
+              if (e >= TQ * TQ) continue;
+              const int j = e / TQ, i = e - j * TQ;
+              pn[P.gw_off[l - 1] + (4 * j + og) * H + 4 * i + ig] += (double)v[p];
+            }
+          }
+          {
+            float v[1];
+            TmIo<1>::ld(tmn + tm_sing, v);
+            if (lane < H) pn[P.gw_off[NH] + lane] += (double)v[0];
+            else if (lane == H) pn[P.gb_off[NH]] += (double)v[0];
+            for (int l = NH; l >= 1; --l) {
+              TmIo<1>::ld(tmn + tm_sing + 1 + (NH - l), v);
+              if (lane < H) pn[P.gb_off[l - 1] + lane] += (double)v[0];
+            }
           }
         }
       }
-      for (int l = 2; l <= NH; ++l) {
-        float v[GSH];
-        TmIo<GSH>::ld(tmn + tm_hid + (l - 2) * GSH, v);
-#pragma unroll
-        for (int p = 0; p < GSH; ++p) {
-          const int e = 2 * p + half;
-          if (e >= TQ * TQ) continue;
-          const int j = e / TQ, i = e - j * TQ;
-          pn[P.gw_off[l - 1] + (4 * j + og) * H + 4 * i + ig] = (double)v[p];
-        }
-      }
-      {
-        float v[1];
-        TmIo<1>::ld(tmn + tm_sing, v);
-        if (lane < H) pn[P.gw_off[NH] + lane] = (double)v[0];
-        else if (lane == H) pn[P.gb_off[NH]] = (double)v[0];
-        for (int l = NH; l >= 1; --l) {
-          TmIo<1>::ld(tmn + tm_sing + 1 + (NH - l), v);
-          if (lane < H) pn[P.gb_off[l - 1] + lane] = (double)v[0];
-        }
-      }
+      __syncthreads();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  // fold the warps' fp64 partial vectors into the first one (fixed order: deterministic), so that the final reduction
-  // reads one vector per CTA
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
   double* cta_part = P.part + (size_t)blockIdx.x * nw * n_part;
   for (int i = tid; i < n_part; i += nt) {
     double sacc = 0.0;
-    for (int q = 0; q < nw; ++q) sacc += __ldcg(cta_part + (size_t)q * n_part + i);
+    if (i < n_acc) sacc = acc[i];
+    else
+      for (int q = 0; q < nw; ++q) sacc += __ldcg(cta_part + (size_t)q * n_part + i);
     cta_part[i] = sacc;
   }
 }
@@ -1788,8 +1809,10 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
   }
   CVF_CUDA(cudaFuncSetAttribute(pass1_kernel<H, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
   long long grid = sm_count();
-  if (P.Bp / kP1Frames < grid) grid = P.Bp / kP1Frames;
-  CVF_LAUNCH(K_FAST_PASS1, stream, pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out));
+  const long long n_tiles1 = P.Bp / kP1Frames;
+  const int split1 = n_tiles1 * P.k <= grid ? 1 : 0;      // fewer (tile, network) pairs than SMs: one pair per CTA
+  if ((split1 ? n_tiles1 * P.k : n_tiles1) < grid) grid = split1 ? n_tiles1 * P.k : n_tiles1;
+  CVF_LAUNCH(K_FAST_PASS1, stream, pass1_kernel<H, NH><<<(int)grid, kP1Threads, smem1, stream>>>(P, y_out, split1));
   CVF_CUDA(cudaGetLastError());
   if (P.kind == 2) {
     const int W = jjt_warps_per_net(P.k);
@@ -1865,15 +1888,22 @@ static int run_grad(const cvf_preproc* pp, const NetPlan& np, int k, const float
     return CVF_E_UNSUPPORTED;
   }
   const size_t smem2 = pass2_smem_bytes(k, P.img2_floats, P.geo_floats, P.d_rp, H, NH, nw);
+  if ((size_t)3 * np.n_params * sizeof(double) > (size_t)nw * pass2_rows_per_warp(P.d_rp, H, NH) * kRowPad * sizeof(float)) {
+    set_error("fast eigen path: the operand rows cannot hold the CTA's gradient vector");   // 3 networks at most keep totals in TMEM
+    return CVF_E_UNSUPPORTED;
+  }
   const long long n_tiles = P.Bp / 32;
   long long grid = sm_count();
-  if ((n_tiles + nw - 1) / nw < grid) grid = (n_tiles + nw - 1) / nw;
+  // small batches: (tile, network) pairs as work items, so that every warp of the chip gets at most two of them
+  const int split2 = n_tiles * k <= 2 * grid * nw ? 1 : 0;
+  const long long n_items2 = split2 ? n_tiles * k : n_tiles;
+  if ((n_items2 + nw - 1) / nw < grid) grid = (n_items2 + nw - 1) / nw;
   if (dw1_chunk_of(P.d_rp) == 28) {
     CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH, 28><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra));
+    CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH, 28><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra, split2));
   } else {
     CVF_CUDA(cudaFuncSetAttribute(pass2_kernel<H, NH, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH, 24><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra));
+    CVF_LAUNCH(K_FAST_PASS2A, stream, pass2_kernel<H, NH, 24><<<(int)grid, 32 * nw, smem2, stream>>>(P, w, combine, pass2_rows_per_warp(P.d_rp, H, NH), seed_extra, split2));
   }
   CVF_CUDA(cudaGetLastError());
   const int n_part = k * np.n_params;

@@ -171,7 +171,7 @@ def test_custom_operators_pass_opcheck(tmp_path):
     y2, st2 = torch.ops.cvf.eigen_stats(X, w, ectx.packed_params(), ectx.handle, 0)
     lb = torch.ops.cvf.eigen_combine(st2, ectx.handle)[0].to(torch.float32)
     gb = torch.autograd.grad(lb, list(model.parameters()))
-    assert torch.equal(la, lb)
+    assert torch.equal(la.detach(), lb.detach())
     for a_, b_ in zip(ga, gb):
         assert torch.allclose(a_, b_, rtol=1e-5, atol=1e-7 * float(a_.abs().max()))
     coef = torch.zeros(ectx.n_comb, dtype=torch.float64, device=DEV)
