@@ -110,5 +110,5 @@ def make_mlp(dims, acts) -> Mlp:
     for i, d in enumerate(dims):
         m.dims[i] = int(d)
     for i, a in enumerate(acts):
-        m.act[i] = 1 if a else 0
+        m.act[i] = int(a)
     return m

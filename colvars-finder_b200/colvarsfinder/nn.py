@@ -28,8 +28,28 @@ def create_sequential_nn(layer_dims, activation=torch.nn.Tanh()):
     return net
 
 
+def activation_kind(m) -> int:
+    """CVF_ACT_* (include/cvf.h) of an activation module; raises for modules outside the kernel envelope.  The kernels keep only a
+    layer's output, so they take the activations whose first two derivatives are functions of the output: Tanh (thread-private and
+    tensor-core kernels), Sigmoid, Softplus (beta 1, threshold 20), ELU (alpha 1), ReLU (general kernels)."""
+    if isinstance(m, torch.nn.Tanh):
+        return 1
+    if isinstance(m, torch.nn.Sigmoid):
+        return 2
+    if isinstance(m, torch.nn.Softplus) and m.beta == 1 and m.threshold == 20:
+        return 3
+    if isinstance(m, torch.nn.ELU) and m.alpha == 1.0:
+        return 4
+    if isinstance(m, torch.nn.ReLU):
+        return 5
+    raise RuntimeError(
+        f"activation {type(m).__name__} is outside the supported envelope of the CUDA step (torch.nn.Tanh, Sigmoid, "
+        "Softplus(beta=1), ELU(alpha=1), ReLU); there is no PyTorch fallback")
+
+
 def chain_spec(seq: torch.nn.Sequential):
-    """(dims, acts, linear modules) of a stack built by create_sequential_nn; raises outside the kernel envelope."""
+    """(dims, acts, linear modules) of a stack built by create_sequential_nn -- acts[l] is the CVF_ACT_* kind after layer l (0:
+    none); raises outside the kernel envelope."""
     dims, acts, lins = [], [], []
     mods = list(seq._modules.values())   # children() would drop the repeated (shared) activation instance
     i = 0
@@ -43,13 +63,9 @@ def chain_spec(seq: torch.nn.Sequential):
             dims.append(m.in_features)
         dims.append(m.out_features)
         lins.append(m)
-        act = False
+        act = 0
         if i + 1 < len(mods) and not isinstance(mods[i + 1], torch.nn.Linear):
-            if not isinstance(mods[i + 1], torch.nn.Tanh):
-                raise RuntimeError(
-                    f"activation {type(mods[i + 1]).__name__} is outside the supported envelope of the CUDA step "
-                    "(torch.nn.Tanh only); there is no PyTorch fallback")
-            act = True
+            act = activation_kind(mods[i + 1])
             i += 1
         acts.append(act)
         i += 1

@@ -112,7 +112,7 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
       const int nin = np.dims[l], nout = np.dims[l + 1];
       const float* in = rows + P.a_row[l] * FS;
       float* out = rows + P.a_row[l + 1] * FS;
-      const bool act = np.act[l] != 0;
+      const int act = np.act[l];
       const int items = ((nout + 3) >> 2) * FB;
       for (int it = tid; it < items; it += nt) {
         const int ob = it / FB, fb = it - ob * FB;
@@ -125,7 +125,7 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
             const float b = Wsm[np.b_off[l] + o];
             V v;
 #pragma unroll
-            for (int f = 0; f < FPL; ++f) v.v[f] = act ? cvf_tanh(acc[j][f] + b) : acc[j][f] + b;
+            for (int f = 0; f < FPL; ++f) v.v[f] = cvf_act(act, acc[j][f] + b);
             v.st(out + o * FS + FPL * fb);
           }
         }
@@ -176,7 +176,7 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
           float acc[4][FPL];
           tile_tr<FPL>(acc, Wsm + np.w_off[l], np.ld[l], 4 * ib, nout, S, FS, FPL * fb);
           float* Sout = rows + P.s_row[l] * FS;
-          const bool act = np.act[l - 1] != 0;
+          const int act = np.act[l - 1];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = 4 * ib + j;
@@ -185,7 +185,7 @@ ae_kernel(const AePlan P, const float* __restrict__ feat, const float* __restric
               if (act) {
                 const V a = V::ld(Ain + i * FS + FPL * fb);
 #pragma unroll
-                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f] * (1.f - a.v[f] * a.v[f]);
+                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f] * cvf_act_d1(act, a.v[f]);
               } else {
 #pragma unroll
                 for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f];
@@ -255,6 +255,11 @@ static int ae_path(const cvf_mlp* net, AePlan* P) {
     set_error("layer-wise autoencoder path: the chain must map R^d to R^d and end in a linear layer");
     return CVF_E_UNSUPPORTED;
   }
+  for (int l = 0; l < np.L; ++l)
+    if (np.act[l] != CVF_ACT_NONE && np.act[l] != CVF_ACT_TANH) {
+      set_error("layer-wise autoencoder path (chains too wide for shared memory): tanh only");
+      return CVF_E_UNSUPPORTED;
+    }
   return 0;
 }
 

@@ -83,7 +83,11 @@ inline int make_net_plan(const cvf_mlp* net, NetPlan* p) {
     p->dims[l] = net->dims[l];
   }
   for (int l = 0; l < p->L; ++l) {
-    p->act[l] = net->act[l] ? 1 : 0;
+    if (net->act[l] < CVF_ACT_NONE || net->act[l] > CVF_ACT_RELU) {
+      set_error("cvf_mlp: unknown activation kind %d after layer %d", net->act[l], l);
+      return CVF_E_UNSUPPORTED;
+    }
+    p->act[l] = net->act[l];
     p->ld[l] = round4(p->dims[l]);
     p->w_off[l] = so;
     so += p->dims[l + 1] * p->ld[l];
@@ -143,6 +147,37 @@ __device__ __forceinline__ float cvf_tanh(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   const float big = copysignf(fmaf(-2.0f, r, 1.0f), x);
   return ax < 0.55f ? small : big;
+}
+
+// ---- activations of the general kernels: value, f'(z) and f''(z) / f'(z), the last two as functions of the OUTPUT a = f(z) ----
+__device__ __forceinline__ float cvf_act(int kind, float z) {
+  switch (kind) {
+    case CVF_ACT_TANH: return cvf_tanh(z);
+    case CVF_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+    case CVF_ACT_SOFTPLUS: return z > 20.0f ? z : fmaxf(z, 0.0f) + log1pf(expf(-fabsf(z)));   // torch.nn.Softplus(beta=1, threshold=20)
+    case CVF_ACT_ELU: return z > 0.0f ? z : expm1f(z);
+    case CVF_ACT_RELU: return fmaxf(z, 0.0f);
+    default: return z;
+  }
+}
+__device__ __forceinline__ float cvf_act_d1(int kind, float a) {
+  switch (kind) {
+    case CVF_ACT_TANH: return fmaf(-a, a, 1.0f);
+    case CVF_ACT_SIGMOID: return a * (1.0f - a);
+    case CVF_ACT_SOFTPLUS: return a > 20.0f ? 1.0f : -expm1f(-a);   // sigmoid(z) = 1 - exp(-softplus(z))
+    case CVF_ACT_ELU: return a > 0.0f ? 1.0f : a + 1.0f;
+    case CVF_ACT_RELU: return a > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+__device__ __forceinline__ float cvf_act_r2(int kind, float a) {
+  switch (kind) {
+    case CVF_ACT_TANH: return -2.0f * a;
+    case CVF_ACT_SIGMOID: return fmaf(-2.0f, a, 1.0f);
+    case CVF_ACT_SOFTPLUS: return a > 20.0f ? 0.0f : expf(-a);       // 1 - sigmoid(z)
+    case CVF_ACT_ELU: return a > 0.0f ? 0.0f : 1.0f;
+    default: return 0.0f;
+  }
 }
 
 // acc[j][f] = sum_i W[o0+j][i] * in[i][f0+f]      (rows of W clamped to n_out-1 for the tail block)

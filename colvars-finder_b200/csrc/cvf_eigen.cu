@@ -98,8 +98,8 @@ static int build_plan(const cvf_preproc* pp, const cvf_mlp* net, int k, EigenPla
     return CVF_E_ARG;
   }
   for (int l = 0; l < np.L; ++l)
-    if (np.act[l] != (l < np.L - 1 ? 1 : 0)) {
-      set_error("eigenfunction networks: tanh after every layer but the last");
+    if ((l < np.L - 1) ? (np.act[l] == CVF_ACT_NONE || np.act[l] != np.act[0]) : (np.act[l] != CVF_ACT_NONE)) {
+      set_error("eigenfunction networks: one activation after every layer but the last");
       return CVF_E_UNSUPPORTED;
     }
   P->k = k;
@@ -570,6 +570,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
     float* netrows = rows + P.row_net * FS;
     const float* r_in = rows + P.row_r * FS;
 
+    const int akind = np.L > 1 ? np.act[0] : CVF_ACT_NONE;   // the one activation of the chain (nn.py:29,56)
     for (int n = 0; n < k; ++n) {
       const float* Wn = Wsm + n * np.smem_floats;
       // ---- forward (nn.py:52-57): A_l = tanh(W_l A_{l-1} + b_l), y = W_L A_{L-1} + b_L
@@ -590,7 +591,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
               const float b = Wn[np.b_off[l] + o];
               V v;
 #pragma unroll
-              for (int f = 0; f < FPL; ++f) v.v[f] = last ? acc[j][f] + b : cvf_tanh(acc[j][f] + b);
+              for (int f = 0; f < FPL; ++f) v.v[f] = last ? acc[j][f] + b : cvf_act(akind, acc[j][f] + b);
               v.st(out + o * FS + FPL * fb);
             }
           }
@@ -617,7 +618,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
               if (l > 0) {
                 const V a = V::ld(A + i * FS + FPL * fb);
 #pragma unroll
-                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f] * (1.f - a.v[f] * a.v[f]);
+                for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f] * cvf_act_d1(akind, a.v[f]);
               } else {
 #pragma unroll
                 for (int f = 0; f < FPL; ++f) v.v[f] = acc[j][f];
@@ -670,8 +671,8 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
                 V t, e;
 #pragma unroll
                 for (int f = 0; f < FPL; ++f) {
-                  t.v[f] = (1.f - a.v[f] * a.v[f]) * acc[j][f];
-                  e.v[f] = -2.f * a.v[f] * g.v[f] * acc[j][f];
+                  t.v[f] = cvf_act_d1(akind, a.v[f]) * acc[j][f];
+                  e.v[f] = cvf_act_r2(akind, a.v[f]) * g.v[f] * acc[j][f];
                 }
                 t.st(T + o * FS + FPL * fb);
                 e.st(S + o * FS + FPL * fb);
@@ -709,7 +710,7 @@ eigen_kernel(const EigenPlan P, const float* __restrict__ x, const float* __rest
                 const V a = V::ld(A + i * FS + FPL * fb);
                 V e = V::ld(S + i * FS + FPL * fb);
 #pragma unroll
-                for (int f = 0; f < FPL; ++f) e.v[f] = fmaf(acc[j][f], 1.f - a.v[f] * a.v[f], e.v[f]);
+                for (int f = 0; f < FPL; ++f) e.v[f] = fmaf(acc[j][f], cvf_act_d1(akind, a.v[f]), e.v[f]);
                 e.st(S + i * FS + FPL * fb);
               }
             }

@@ -66,6 +66,23 @@ __device__ __forceinline__ void store_rows(float* dst, const float* src, int nro
   for (int r = lane >> 3; r < nrows; r += 4)
     *reinterpret_cast<float4*>(dst + (size_t)r * Bp + c4) = *reinterpret_cast<const float4*>(src + r * kRowPad + c4);
 }
+// bounded mbarrier wait: a byte count that does not add up must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
 __device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // warp prefetch of `nrows` row segments (one 128-byte line each: 32 frames of a frame-minor row)
 __device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long long Bp, int lane) {
@@ -322,32 +339,40 @@ __global__ void pack_kernel(const FastPlan P, const float* __restrict__ params) 
 
 // ------------------------------------------------------------------------------------------------ prep
 // kind 1: Kabsch per frame (thread per frame on a coalesced shared-memory tile), frame-minor output.
-__global__ void __launch_bounds__(128, 6) prep_align_kernel(const FastPlan P, const float* __restrict__ x) {
-  extern __shared__ __align__(16) float st[];
+__global__ void __launch_bounds__(128, 6) prep_align_kernel(const FastPlan P, const float* __restrict__ x, int bulk) {
+  extern __shared__ __align__(128) float st[];
+  __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x;
-  const int fl = 3 * P.n_atoms, S = fl | 1;   // odd stride: conflict-free column access
-  float* kin = st + 128 * S;                  // [6][128]
+  // bulk (TMA): a full tile of 128 raw frames is one contiguous block of global memory (128 * 12 N bytes, a multiple of 16) and
+  // arrives by ONE cp.async.bulk into rows of stride 3N; otherwise (tail tile, unaligned x) cooperative loads into rows of odd stride
+  const int fl = 3 * P.n_atoms, S = bulk ? fl : (fl | 1);
+  float* kin = st + 128 * (fl | 1);           // [6][128]
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
   const long long n_tiles = P.Bp / 128;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long f0 = tile * 128;
-    if (f0 + 128 <= P.B) {
-      // contiguous tile: element i = tid + 128 m belongs to frame i / fl; (frame, coordinate) advance incrementally
-      const float* src = x + (size_t)f0 * fl;
-      const int df = 128 / fl, dj = 128 - df * fl;
-      int f = tid / fl, j = tid - f * fl;
-      for (int i = tid; i < 128 * fl; i += 128) {
-        st[f * S + j] = __ldg(src + i);
-        f += df, j += dj;
-        if (j >= fl) j -= fl, ++f;
+    if (bulk && f0 + 128 <= P.B) {
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(128 * fl * sizeof(float));
+        fence_proxy_async();   // the previous tile's ordinary reads / writes of the buffer precede the copy
+        mbar_expect_tx(&bar, bytes);
+        bulk_g2s(st, x + (size_t)f0 * fl, bytes, &bar);
       }
+      mbar_wait_bounded(&bar, phase);
+      phase ^= 1;
     } else {
       for (int i = tid; i < 128 * fl; i += 128) {
         const int f = i / fl;
         const long long fr = min(f0 + f, P.B - 1);   // padding frames repeat the last frame (their weight is 0)
         st[f * S + (i - f * fl)] = __ldg(x + (size_t)fr * fl + (i - f * fl));
       }
+      __syncthreads();
     }
-    __syncthreads();
     {
       float* fr = st + tid * S;
       double cx = 0, cy = 0, cz = 0;
@@ -1682,6 +1707,8 @@ static bool supported_shape(const NetPlan& np, Shape* s) {
   for (int l = 1; l < np.L; ++l)
     if (np.dims[l] != H) return false;
   if (np.dims[np.L] != 1) return false;
+  for (int l = 0; l < np.L - 1; ++l)
+    if (np.act[l] != CVF_ACT_TANH) return false;   // the thread-private kernels are tanh-only
   s->H = H, s->NH = np.L - 1;
   return (H == 20 && (s->NH == 3 || s->NH == 2)) || (H == 32 && s->NH == 3) || (H == 16 && s->NH == 3);
 }
@@ -1795,7 +1822,8 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
     per_sm = per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm;
     long long grid = (long long)sm_count() * per_sm;
     if (P.Bp / 128 < grid) grid = P.Bp / 128;
-    CVF_LAUNCH(K_FAST_PREP, stream, prep_align_kernel<<<(int)grid, 128, smem, stream>>>(P, x));
+    const int bulk = ((uintptr_t)x & 15) == 0 ? 1 : 0;   // 128 frames are 128 * 12 N bytes: always a multiple of 16
+    CVF_LAUNCH(K_FAST_PREP, stream, prep_align_kernel<<<(int)grid, 128, smem, stream>>>(P, x, bulk));
   } else {
     long long grid = (long long)sm_count() * 8;
     if ((P.Bp + 255) / 256 < grid) grid = (P.Bp + 255) / 256;

@@ -74,10 +74,20 @@ typedef struct cvf_preproc {
 
 /* Linear+activation chain built by nn.create_sequential_nn (nn.py:29-59).  For nn.AutoEncoder the
  * chain is encoder followed by decoder (nn.py:114). */
+/* activation after a layer (nn.py:29-59 takes any torch.nn.Module; these are the ones whose first and second derivatives are
+ * functions of the activation's output, which is all the kernels keep).  One kind per chain, as in the reference (the same module
+ * instance follows every layer but the last).  The thread-private / tensor-core kernels are tanh-only; other kinds run on the
+ * general kernels. */
+#define CVF_ACT_NONE 0
+#define CVF_ACT_TANH 1
+#define CVF_ACT_SIGMOID 2
+#define CVF_ACT_SOFTPLUS 3   /* beta = 1 */
+#define CVF_ACT_ELU 4        /* alpha = 1 */
+#define CVF_ACT_RELU 5
 typedef struct cvf_mlp {
   int32_t n_layers;
   int32_t dims[CVF_MAX_LAYERS + 1];
-  int32_t act[CVF_MAX_LAYERS];   /* 1: tanh after this layer, 0: none */
+  int32_t act[CVF_MAX_LAYERS];   /* CVF_ACT_* after this layer */
 } cvf_mlp;
 
 int cvf_version(void);

@@ -921,7 +921,7 @@ def test_save_model_and_unsupported(tmp_path):
         core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1), str(tmp_path), 1.0, [1.0],
                                lag_tau=0.25, device=DEV, verbose=False)
     with pytest.raises(RuntimeError, match="Tanh"):
-        core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1, torch.nn.ReLU()), str(tmp_path), 1.0,
+        core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1, torch.nn.GELU()), str(tmp_path), 1.0,
                                [1.0], device=DEV, verbose=False)
 
 

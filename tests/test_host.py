@@ -236,7 +236,10 @@ def test_tasks_refuse_cpu_and_unsupported_configs(tmp_path):
         core.EigenFunctionTask(traj, torch.nn.Identity(), nn.EigenFunctions([2, 4, 1], 1), str(tmp_path), 1.0, [1.0],
                                device=torch.device("cpu"), verbose=False)
     with pytest.raises(RuntimeError, match="Tanh"):
-        nn.chain_spec(nn.create_sequential_nn([2, 3, 1], torch.nn.ReLU()))
+        nn.chain_spec(nn.create_sequential_nn([2, 3, 1], torch.nn.GELU()))
+    with pytest.raises(RuntimeError, match="Tanh"):
+        nn.chain_spec(nn.create_sequential_nn([2, 3, 1], torch.nn.ELU(alpha=0.5)))
+    assert nn.chain_spec(nn.create_sequential_nn([2, 3, 3, 1], torch.nn.Softplus()))[1] == [3, 3, 0]
 
 
 def test_weighted_trajectory_text_and_weights(tmp_path):

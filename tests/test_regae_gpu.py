@@ -223,3 +223,51 @@ def test_weight_filter_on_device_matches_reference_semantics(n, tmp_path):
         assert task._traj.shape == (int(keep.sum()), 2)
         loss = task.loss_func(task._traj, task._weights)[0]
         assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("act", ["sigmoid", "softplus", "elu", "relu"])
+def test_other_activations_match_reference_golden(act, tmp_path):
+    """Activations other than Tanh (the reference takes any module, nn.py:29-59): generator loss on 2-d data and on aligned
+    frames with a feature map, autoencoder loss -- against the unmodified reference (oracle/gen_golden_activations.py), fp64 gold
+    with the reference's fp32 run as the floor.  These run on the general kernels (the thread-private ones are tanh-only)."""
+    from colvarsfinder import core, nn, utils
+    d = C.load("activations")
+    make = {"sigmoid": torch.nn.Sigmoid, "softplus": torch.nn.Softplus, "elu": torch.nn.ELU, "relu": torch.nn.ReLU}[act]
+    feats = [(str(t), [int(a) for a in row if a >= 0]) for t, row in zip(d["feat_types"], d["feat_atoms"])]
+    cases = (("e2d", [2, 12, 12, 1], torch.nn.Identity(), 10.0, [1.0, 0.5]),
+             ("emol", [12, 14, 14, 1], utils.Preprocessing(utils.Align(d["emol_ref"], d["emol_align"]), utils.FeatureMap(feats)), 10.0, [1.0, 0.4]))
+    for tag, dims, pp, alpha, eig_w in cases:
+        model = nn.EigenFunctions(dims, 2, make())
+        with torch.no_grad():
+            for i in range(2):
+                for j, p in enumerate(model.eigen_funcs[i].parameters()):
+                    p.copy_(torch.as_tensor(d[f"{tag}_p_{i}_{j}"]))
+        X, w = d[f"{tag}_X"], d[f"{tag}_w"]
+        task = core.EigenFunctionTask(FakeTrajectory(X, w.astype(np.float64)), pp, model, str(tmp_path), alpha, eig_w, k=2, device=DEV,
+                                      verbose=False, debug_mode=False)
+        assert not task._ctx.fast_path
+        loss, eig, obj, pen, cvec = task.loss_func(task._traj, task._weights)
+        loss.backward()
+        g64l, r32l = float(d[f"{act}_{tag}_g64_loss"]), float(d[f"{act}_{tag}_r32_loss"])
+        assert list(cvec.cpu().numpy()) == list(d[f"{act}_{tag}_g64_cvec"]), (act, tag)
+        assert abs(float(loss) - g64l) <= C.tol(g64l, r32l), (act, tag, float(loss), g64l, r32l)
+        for i in range(2):
+            ge, re_ = d[f"{act}_{tag}_g64_eig"][i], d[f"{act}_{tag}_r32_eig"][i]
+            assert abs(float(eig[i]) - ge) <= C.tol(ge, re_), (act, tag, "eig", i)
+            for j, p in enumerate(model.eigen_funcs[i].parameters()):
+                a, b = d[f"{act}_{tag}_g64_g_{i}_{j}"], d[f"{act}_{tag}_r32_g_{i}_{j}"]
+                if np.abs(a).max() < 1e-12:
+                    continue
+                assert C.rel_l2(p.grad.cpu().numpy(), a) <= max(2e-5, C.rel_l2(b, a)), (act, tag, i, j, C.rel_l2(p.grad.cpu().numpy(), a), C.rel_l2(b, a))
+    ae = nn.AutoEncoder([2, 16, 16, 1], [1, 16, 2], make())
+    with torch.no_grad():
+        for j, p in enumerate(list(ae.encoder.parameters()) + list(ae.decoder.parameters())):
+            p.copy_(torch.as_tensor(d[f"ae_p_{j}"]))
+    task = core.AutoEncoderTask(FakeTrajectory(d["ae_F"], d["ae_w"].astype(np.float64)), torch.nn.Identity(), ae, str(tmp_path), device=DEV,
+                                verbose=False, debug_mode=False)
+    loss = task.weighted_MSE_loss(task._feature_traj, task._weights)
+    loss.backward()
+    assert abs(float(loss) - float(d[f"{act}_ae_g64_loss"])) <= C.tol(float(d[f"{act}_ae_g64_loss"]), float(d[f"{act}_ae_r32_loss"]))
+    for j, p in enumerate(list(ae.encoder.parameters()) + list(ae.decoder.parameters())):
+        a, b = d[f"{act}_ae_g64_g_{j}"], d[f"{act}_ae_r32_g_{j}"]
+        assert C.rel_l2(p.grad.cpu().numpy(), a) <= max(2e-5, C.rel_l2(b, a)), (act, "ae", j)
