@@ -7,11 +7,15 @@
 //   backward  delta_{l-1} = (delta_l W_l) .* (1 - A_{l-1}^2)  C[M x K] = A[M x N] B[N x K]       epilogue: * (1 - act^2)
 //   gradient  [dW_l | db_l] = delta_l^T [A_{l-1} | 1]         C[N x (K+1)] = sum over frames, split over the frames
 //
-// One SGEMM kernel serves the three products (operands described by which of their two dimensions is contiguous): 128 x 128
-// x 16 CTA tiles, 8 x 8 register tiles with packed FFMA2, operands staged through shared memory k-major so that the inner
-// loop is two 128-bit loads per operand and 32 FFMA2, global loads of tile i+1 in flight during the products of tile i.
-// These are plain fp32 SIMT products: the tcgen05 tensor-core path this shape really wants (with an error-compensated split to
-// keep fp32 parity) is not built yet -- see DESIGN.md.
+// Two implementations of the three products (cvf_ae_set_wide_path):
+//   * tensor cores (default): cvf_gemm_tc.cu, tcgen05 with the 3 x TF32 split.  Every operand of every product is a "tile image"
+//     (cvf_gemm.cuh) filled by one bulk copy per stage: the weights' images are built once per step, and every activation /
+//     delta is written as images by the epilogue of the product that computes it (K-major for the next layer's product,
+//     transposed -- K = frame -- for the weight-gradient product), so no product stages an operand through registers and no
+//     separate pass re-reads an activation.  Only the input features and delta_L (written by the loss kernel) go through
+//     tile_image_kernel.
+//   * fp32 SIMT (mode 1, kept as the cross-check of the tests): one SGEMM kernel, 128 x 128 x 16 CTA tiles, 8 x 8 register tiles
+//     with packed FFMA2, operands staged through shared memory k-major, global loads of tile i+1 in flight during tile i.
 //
 // Every matrix the products touch lives in the caller's workspace with a leading dimension padded to a multiple of 4 floats
 // and zero padding, so all global accesses are aligned 128-bit.  Activation buffers carry one extra column of ones, which
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(256) pad_weights_kernel(const float* __restric
 
 // e = out - in; delta = 2 w e (written over `out`); per-block partial sums of w |e|^2 and w
 __global__ void __launch_bounds__(256) loss_delta_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ w,
-                                                         long long f0, int M, int d, int ld, double* __restrict__ part) {
+                                                         long long f0, int M, int d, int ld, int ld_in, double* __restrict__ part) {
   __shared__ double red[2][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s2 = 0.0, s0 = 0.0;
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(256) loss_delta_kernel(float* __restrict__ out
     const float wf = __ldg(w + f0 + m);
     float accf = 0.f;
     for (int c = lane; c < d; c += 32) {
-      const float e = out[(size_t)m * ld + c] - in[(size_t)m * ld + c];
+      const float e = out[(size_t)m * ld + c] - in[(size_t)m * ld_in + c];
       accf = fmaf(e, e, accf);
       out[(size_t)m * ld + c] = 2.0f * wf * e;
     }
@@ -280,6 +284,9 @@ struct WidePlan {
   // back-propagation products (wb), and per frame the floats of the two operand images of a weight-gradient product
   size_t wf_off[kMaxLayers], wb_off[kMaxLayers];
   size_t wimg_floats;
+  // per frame: K-major images of A_0 .. A_{L-1} (ak_off), transposed images with the ones row (at_off), and two ping-pong pairs
+  // (K-major, transposed) for the deltas
+  size_t ak_off[kMaxLayers], at_off[kMaxLayers], dk_floats, dt_floats;
   size_t img_floats_per_frame;
 };
 
@@ -306,15 +313,21 @@ static void make_plan(const NetPlan& np, WidePlan* P) {
   P->w_floats = wf;
   P->delta_floats_per_frame = 2 * (size_t)maxld;
   size_t wi = 0;
-  int maxrows = 0;
   for (int l = 0; l < np.L; ++l) {
     P->wf_off[l] = wi, wi += tile_image_floats(np.dims[l + 1], np.dims[l]);
     P->wb_off[l] = wi, wi += tile_image_floats(np.dims[l], np.dims[l + 1]);
-    if (np.dims[l + 1] > maxrows) maxrows = np.dims[l + 1];
-    if (np.dims[l] + 1 > maxrows) maxrows = np.dims[l] + 1;
   }
   P->wimg_floats = wi;
-  P->img_floats_per_frame = 2 * (size_t)((maxrows + 127) / 128 * 128) * 2;   // two operands, hi + lo, rows padded to the tile
+  size_t fi = 0;
+  int maxd = 0;
+  for (int l = 0; l < np.L; ++l) {
+    P->ak_off[l] = fi, fi += 2 * (size_t)((np.dims[l] + 31) / 32 * 32);          // hi + lo, K padded to the k-block
+    P->at_off[l] = fi, fi += 2 * (size_t)((np.dims[l] + 1 + 127) / 128 * 128);   // hi + lo, rows (+ ones row) padded to the tile
+    if (np.dims[l + 1] > maxd) maxd = np.dims[l + 1];
+  }
+  P->dk_floats = 2 * (size_t)((maxd + 31) / 32 * 32);
+  P->dt_floats = 2 * (size_t)((maxd + 127) / 128 * 128);
+  P->img_floats_per_frame = fi + 2 * (P->dk_floats + P->dt_floats);
 }
 
 constexpr int kMaxSplits = 32;
@@ -386,8 +399,21 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   float* dbuf = (float*)take((size_t)chunk * P.delta_floats_per_frame * sizeof(float));
   float* delta[2] = {dbuf, dbuf + (size_t)chunk * (P.delta_floats_per_frame / 2)};
   float* ibuf = (float*)take((size_t)chunk * P.img_floats_per_frame * sizeof(float));
-  float* opimg[2] = {ibuf, ibuf + (size_t)chunk * (P.img_floats_per_frame / 2)};
   const bool tc = g_wide_mode == 0;
+  // operand images of this chunk (tensor-core path): activations K-major / transposed, deltas as two ping-pong pairs
+  float *imgK[kMaxLayers], *imgT[kMaxLayers], *dK[2], *dT[2];
+  {
+    size_t o = 0;
+    for (int l = 0; l < L; ++l) imgK[l] = ibuf + (size_t)chunk * P.ak_off[l], imgT[l] = ibuf + (size_t)chunk * P.at_off[l];
+    o = (size_t)chunk * (P.img_floats_per_frame - 2 * (P.dk_floats + P.dt_floats));
+    for (int b = 0; b < 2; ++b) {
+      dK[b] = ibuf + o, o += (size_t)chunk * P.dk_floats;
+      dT[b] = ibuf + o, o += (size_t)chunk * P.dt_floats;
+    }
+  }
+  // the tensor-core path reads the caller's features in place when their rows are 16-byte aligned; the SIMT products want the
+  // padded copy with the ones column
+  const bool in_place = tc && P.dims[0] % 4 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
 
   for (int l = 0; l < L; ++l) {
     const int n = P.dims[l + 1] * P.ld[l];
@@ -397,10 +423,10 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   }
   if (tc) {   // weight images: B operand of the forward products and (layers >= 1, training only) of the back-propagation products
     for (int l = 0; l < L; ++l) {
-      int e = launch_tile_image(Wp + P.w_off[l], P.ld[l], 1, P.dims[l + 1], P.dims[l], Wimg + P.wf_off[l], stream);
+      int e = launch_tile_image(Wp + P.w_off[l], P.ld[l], 1, P.dims[l + 1], P.dims[l], 0, Wimg + P.wf_off[l], stream);
       if (e) return e;
       if (grad_out && l >= 1) {
-        e = launch_tile_image(Wp + P.w_off[l], P.ld[l], 0, P.dims[l], P.dims[l + 1], Wimg + P.wb_off[l], stream);
+        e = launch_tile_image(Wp + P.w_off[l], P.ld[l], 0, P.dims[l], P.dims[l + 1], 0, Wimg + P.wb_off[l], stream);
         if (e) return e;
       }
     }
@@ -411,26 +437,45 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   bool first = true;
   for (long long f0 = 0; f0 < B; f0 += chunk) {
     const int M = (int)(B - f0 < chunk ? B - f0 : chunk);
-    {
+    const int fblocks = (M + 31) / 32;   // k-blocks of an operand whose K index is the frame
+    const float* in0 = in_place ? feat + (size_t)f0 * P.dims[0] : acts[0];
+    const int ld0 = in_place ? P.dims[0] : P.ld[0];
+    if (!in_place) {
       const long long n = (long long)M * P.ld[0];
       const int grid = (int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
       CVF_LAUNCH(K_AE_STEP, stream, stage_input_kernel<<<grid, 256, 0, stream>>>(feat, f0, M, P.dims[0], acts[0], P.ld[0]));
     }
-    for (int l = 1; l < L; ++l) {   // ones column / zero padding of the hidden activation buffers
-      const long long n = (long long)M * (P.ld[l] - P.dims[l]);
-      const int grid = (int)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256);
-      CVF_LAUNCH(K_AE_STEP, stream, set_pad_kernel<<<grid, 256, 0, stream>>>(acts[l], M, P.dims[l], P.ld[l]));
+    if (tc) {   // the input as the A operand of the first product and (training) as the B operand of dW_1, with its ones row
+      int e = launch_tile_image(in0, ld0, 1, M, P.dims[0], 0, imgK[0], stream);
+      if (e) return e;
+      if (grad_out) {
+        e = launch_tile_image(in0, ld0, 0, P.dims[0], M, P.dims[0], imgT[0], stream);
+        if (e) return e;
+      }
+    } else {
+      for (int l = 1; l < L; ++l) {   // ones column / zero padding of the hidden activation buffers
+        const long long n = (long long)M * (P.ld[l] - P.dims[l]);
+        const int grid = (int)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256);
+        CVF_LAUNCH(K_AE_STEP, stream, set_pad_kernel<<<grid, 256, 0, stream>>>(acts[l], M, P.dims[l], P.ld[l]));
+      }
     }
     for (int l = 0; l < L; ++l) {   // forward
       Gemm g;
       memset(&g, 0, sizeof(g));
-      g.A = acts[l], g.lda = P.ld[l], g.a_kcontig = 1;
+      g.A = l == 0 ? in0 : acts[l], g.lda = l == 0 ? ld0 : P.ld[l], g.a_kcontig = 1;
       g.B = Wp + P.w_off[l], g.ldb = P.ld[l], g.b_kcontig = 1;
       g.C = acts[l + 1], g.ldc = P.ld[l + 1];
       g.M = M, g.N = P.dims[l + 1], g.K = P.dims[l], g.k_per_split = g.K;
       g.epi = P.act[l] ? EPI_BIAS_TANH : EPI_BIAS;
       g.bias = params + P.gb_off[l];
-      if (tc) g.b_img = Wimg + P.wf_off[l], g.b_img_kblocks = (P.dims[l] + 31) / 32;
+      if (tc) {
+        g.a_img = imgK[l], g.a_img_kblocks = (P.dims[l] + 31) / 32;
+        g.b_img = Wimg + P.wf_off[l], g.b_img_kblocks = (P.dims[l] + 31) / 32;
+        if (l + 1 < L) {
+          g.c_img_k = imgK[l + 1], g.c_img_k_kblocks = (P.dims[l + 1] + 31) / 32;
+          if (grad_out) g.c_img_t = imgT[l + 1], g.c_img_t_kblocks = fblocks, g.c_img_t_ones = P.dims[l + 1];
+        }
+      }
       int e = launch_gemm(g, 1, stream);
       if (e) return e;
     }
@@ -438,15 +483,23 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
       int grid = sm_count() * 8;
       if ((M + 7) / 8 < grid) grid = (M + 7) / 8;
       CVF_LAUNCH(K_AE_STEP, stream,
-                 loss_delta_kernel<<<grid, 256, 0, stream>>>(acts[L], acts[0], w, f0, M, P.dims[L], P.ld[L], part));
+                 loss_delta_kernel<<<grid, 256, 0, stream>>>(acts[L], in0, w, f0, M, P.dims[L], P.ld[L], ld0, part));
       CVF_LAUNCH(K_REDUCE, stream, add_sums_kernel<<<1, 32, 0, stream>>>(part, grid, sums_out, first ? 1 : 0));
       CVF_CUDA(cudaGetLastError());
     }
     first = false;
     if (!grad_out) continue;
-    // backward: delta_L lives in acts[L]; lower deltas ping-pong in dbuf
+    // backward: delta_L lives in acts[L]; lower deltas ping-pong in dbuf (SIMT path) / in the image pairs (tensor-core path)
     const float* dcur = acts[L];
-    int cur_ld = P.ld[L];
+    int cur_ld = P.ld[L], cur = 0;
+    if (tc) {
+      int e = launch_tile_image(dcur, cur_ld, 0, P.dims[L], M, 0, dT[0], stream);
+      if (e) return e;
+      if (L >= 2) {
+        e = launch_tile_image(dcur, cur_ld, 1, M, P.dims[L], 0, dK[0], stream);
+        if (e) return e;
+      }
+    }
     for (int l = L - 1; l >= 0; --l) {
       // [dW | db] = delta^T [A_l | 1], split over the frames
       {
@@ -460,13 +513,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         memset(&g, 0, sizeof(g));
         g.A = dcur, g.lda = cur_ld, g.a_kcontig = 0;          // Aop[i][f] = delta[f][i]
         g.B = acts[l], g.ldb = P.ld[l], g.b_kcontig = 0;      // Bop[f][j] = A_l[f][j]
-        if (tc) {   // both operands as tile images over the frames (split, transposed and swizzled once, read by bulk copies)
-          int e = launch_tile_image(dcur, cur_ld, 0, rows, M, opimg[0], stream);
-          if (e) return e;
-          e = launch_tile_image(acts[l], P.ld[l], 0, cols, M, opimg[1], stream);
-          if (e) return e;
-          g.a_img = opimg[0], g.b_img = opimg[1], g.a_img_kblocks = g.b_img_kblocks = (M + 31) / 32;
-        }
+        if (tc) g.a_img = dT[cur], g.b_img = imgT[l], g.a_img_kblocks = g.b_img_kblocks = fblocks;
         g.C = dWp, g.ldc = P.ld[l], g.c_split_stride = (long long)rows * P.ld[l];
         g.M = rows, g.N = cols, g.K = M, g.k_per_split = kps;
         g.epi = EPI_NONE;
@@ -486,14 +533,20 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         memset(&g, 0, sizeof(g));
         g.A = dcur, g.lda = cur_ld, g.a_kcontig = 1;                    // Aop[f][i] = delta[f][i]
         g.B = Wp + P.w_off[l], g.ldb = P.ld[l], g.b_kcontig = 0;        // Bop[i][j] = W[i][j]
-        if (tc) g.b_img = Wimg + P.wb_off[l], g.b_img_kblocks = (P.dims[l + 1] + 31) / 32;
         g.C = dnext, g.ldc = P.ld[l];
         g.M = M, g.N = P.dims[l], g.K = P.dims[l + 1], g.k_per_split = g.K;
         g.epi = P.act[l - 1] ? EPI_MUL_OM : EPI_NONE;
         g.act = acts[l];
+        if (tc) {   // the new delta leaves the product as images only: nothing reads it as a row-major matrix
+          g.a_img = dK[cur], g.a_img_kblocks = (P.dims[l + 1] + 31) / 32;
+          g.b_img = Wimg + P.wb_off[l], g.b_img_kblocks = (P.dims[l + 1] + 31) / 32;
+          g.C = nullptr;
+          g.c_img_t = dT[cur ^ 1], g.c_img_t_kblocks = fblocks;
+          if (l >= 2) g.c_img_k = dK[cur ^ 1], g.c_img_k_kblocks = (P.dims[l] + 31) / 32;
+        }
         int e = launch_gemm(g, 1, stream);
         if (e) return e;
-        dcur = dnext, cur_ld = P.ld[l];
+        dcur = dnext, cur_ld = P.ld[l], cur ^= 1;
       }
     }
   }

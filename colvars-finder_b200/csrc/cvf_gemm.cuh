@@ -31,6 +31,16 @@ struct Gemm {
   const float* a_img;
   const float* b_img;
   int a_img_kblocks, b_img_kblocks;
+  // Tensor-core path only, single split: the epilogue also writes C as operand images for the products that consume it, so
+  // that no product stages an operand through registers and no separate pass re-reads C to build an image:
+  //   c_img_k  C as an operand with rows = m and K = n (the A operand of the next layer's product); k-blocks = ceil(N / 32)
+  //   c_img_t  C^T as an operand with rows = n and K = m (an operand of a weight-gradient product, whose K index is the
+  //            frame); k-blocks = ceil(M / 32).  c_img_t_ones > 0 adds a row of ones (for m < M) at that row index (= N), which
+  //            turns the bias gradient into one more column of the weight-gradient product.
+  // Entries outside the matrix are written as zeros.  C itself is not stored when C is NULL.
+  float* c_img_k;
+  float* c_img_t;
+  int c_img_k_kblocks, c_img_t_kblocks, c_img_t_ones;
 };
 
 // cvf_gemm_tc.cu: the same product on the 5th-generation tensor cores; grid = (ceil(N/128), ceil(M/128), splits), k_per_split
@@ -38,8 +48,9 @@ struct Gemm {
 int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream);
 // floats of the image of an operand with `rows` rows and K columns
 inline size_t tile_image_floats(int rows, int K) { return (size_t)((rows + 127) / 128) * ((K + 31) / 32) * 8192; }
-// builds the image of Xop[row][k] = kcontig ? X[row * ld + k] : X[k * ld + row]
-int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K, float* img, cudaStream_t stream);
+// builds the image of Xop[row][k] = kcontig ? X[row * ld + k] : X[k * ld + row], row < rows; ones_row > 0 (>= rows): one more
+// row, all ones for k < K
+int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K, int ones_row, float* img, cudaStream_t stream);
 
 }  // namespace wide
 }  // namespace cvf

@@ -322,9 +322,13 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
   }
   // every group has been added onto the master tile (each drain waited for the commit that covers the group's MMAs)
 
-  // epilogue: warp w reads lanes 32 (w % 4) .. +31 (rows) and columns 64 (w / 4) .. +63
-  float* C = g.C + (size_t)blockIdx.z * g.c_split_stride;
+  // epilogue: warp w reads lanes 32 (w % 4) .. +31 (rows) and columns 64 (w / 4) .. +63.  Besides C (row-major fp32) it writes the
+  // operand images of C that later products read (cvf_gemm.cuh): the thread's 32 values of a row are one 128-byte row of a K-major
+  // tile (eight 16-byte chunks at their swizzled places), and for a fixed column the warp's 32 rows are one 128-byte row of the
+  // transposed tile (32 scalar stores = one full line).
+  float* C = g.C ? g.C + (size_t)blockIdx.z * g.c_split_stride : nullptr;
   const int row = m0 + 32 * (warp & 3) + lane;
+  const bool row_ok = row < g.M;
 #pragma unroll 1
   for (int cb = 0; cb < (warp < 8 ? 2 : 0); ++cb) {
     const int col0 = 64 * (warp >> 2) + 32 * cb;
@@ -341,12 +345,11 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] = 0.0f;
     }
-    if (row < g.M) {
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const int n = n0 + col0 + 4 * c4;
-        if (n >= g.N) continue;
-        float o[4] = {v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]};
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const int n = n0 + col0 + 4 * c4;
+      float o[4] = {v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]};
+      if (row_ok && n < g.N) {
         if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -358,12 +361,57 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
           const float4 a4 = *reinterpret_cast<const float4*>(g.act + (size_t)row * g.ldc + n);
           o[0] *= fmaf(-a4.x, a4.x, 1.0f), o[1] *= fmaf(-a4.y, a4.y, 1.0f), o[2] *= fmaf(-a4.z, a4.z, 1.0f), o[3] *= fmaf(-a4.w, a4.w, 1.0f);
         }
-        if (n + 3 < g.N) {
-          *reinterpret_cast<float4*>(C + (size_t)row * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
+        if (C != nullptr) {
+          if (n + 3 < g.N) {
+            *reinterpret_cast<float4*>(C + (size_t)row * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (n + c < g.N) C[(size_t)row * g.ldc + n + c] = o[c];
+            for (int c = 0; c < 4; ++c)
+              if (n + c < g.N) C[(size_t)row * g.ldc + n + c] = o[c];
+          }
+        }
+      }
+      // what lies outside the matrix is zero in the images
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[4 * c4 + c] = (row_ok && n + c < g.N) ? o[c] : 0.0f;
+    }
+    if (g.c_img_k != nullptr) {
+      const int kb = (n0 + col0) >> 5;
+      if (kb < g.c_img_k_kblocks) {
+        uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_k + ((size_t)blockIdx.y * g.c_img_k_kblocks + kb) * (2 * kTileBytes / 4));
+        const int r = 32 * (warp & 3) + lane;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          float h[4], l[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_tf32(v[4 * ch + c], h[c], l[c]);
+          const uint32_t o = sw_off(r, ch);
+          *reinterpret_cast<float4*>(tile + o) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(tile + kTileBytes + o) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    }
+    if (g.c_img_t != nullptr) {
+      const int kbt = (m0 >> 5) + (warp & 3);
+      if (kbt < g.c_img_t_kblocks) {
+        uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_t + ((size_t)blockIdx.x * g.c_img_t_kblocks + kbt) * (2 * kTileBytes / 4));
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int nl = col0 + c;
+          float x = v[c];
+          if (g.c_img_t_ones > 0 && n0 + nl == g.c_img_t_ones && row_ok) x = 1.0f;
+          float h, l;
+          split_tf32(x, h, l);
+          const uint32_t o = sw_off(nl, lane >> 2) + 4 * (lane & 3);
+          *reinterpret_cast<float*>(tile + o) = h;
+          *reinterpret_cast<float*>(tile + kTileBytes + o) = l;
+        }
+        // the row of ones starts a row tile of its own when N is a multiple of 128: the last column tile's CTAs write it
+        if (g.c_img_t_ones == n0 + TN && col0 == 0) {
+          uint8_t* t2 = reinterpret_cast<uint8_t*>(g.c_img_t + ((size_t)(blockIdx.x + 1) * g.c_img_t_kblocks + kbt) * (2 * kTileBytes / 4));
+          const uint32_t o = sw_off(0, lane >> 2) + 4 * (lane & 3);
+          *reinterpret_cast<float*>(t2 + o) = row_ok ? 1.0f : 0.0f;
+          *reinterpret_cast<float*>(t2 + kTileBytes + o) = 0.0f;
         }
       }
     }
@@ -377,18 +425,25 @@ __global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
 }
 
 // One CTA per (row tile, k-block): the same load / split / swizzled store as the product kernel's staging, into shared memory,
-// then the finished 32 KB image (hi tile | lo tile) goes out as coalesced 16-byte stores.
+// then the finished 32 KB image (hi tile | lo tile) goes out as coalesced 16-byte stores.  ones_row > 0: the operand has one more
+// row, all ones (k < K), at that index (>= rows).
 __global__ void __launch_bounds__(256) tile_image_kernel(const float* __restrict__ X, long long ld, int kcontig, int rows, int K,
-                                                         int kblocks, float* __restrict__ img) {
+                                                         int kblocks, int row_tiles, int ones_row, float* __restrict__ img) {
   __shared__ __align__(1024) uint8_t buf[2 * kTileBytes];
   const int tid = threadIdx.x;
-  const long long n_items = (long long)((rows + TM - 1) / TM) * kblocks;
+  const long long n_items = (long long)row_tiles * kblocks;
   for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int rt = (int)(it / kblocks), kb = (int)(it - (long long)rt * kblocks);
     Stage4 r;
     tc_load(r, X, ld, kcontig, rt * TM, rows, kb * TK, K, tid);
     __syncthreads();   // the previous item's copy-out has finished reading buf
     tc_store(buf, buf + kTileBytes, r, kcontig, tid);
+    __syncthreads();
+    if (ones_row > 0 && ones_row / TM == rt && tid < TK) {   // after the zero padding of the rows beyond `rows` has been stored
+      const int k = kb * TK + tid;
+      const uint32_t o = sw_off(ones_row - rt * TM, tid >> 2) + 4 * (tid & 3);
+      *reinterpret_cast<float*>(buf + o) = k < K ? 1.0f : 0.0f;
+    }
     __syncthreads();
     float4* dst = reinterpret_cast<float4*>(img + (size_t)it * (2 * kTileBytes / 4));
     const float4* src = reinterpret_cast<const float4*>(buf);
@@ -397,11 +452,12 @@ __global__ void __launch_bounds__(256) tile_image_kernel(const float* __restrict
   }
 }
 
-int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K, float* img, cudaStream_t stream) {
+int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K, int ones_row, float* img, cudaStream_t stream) {
   const int kblocks = (K + TK - 1) / TK;
-  const long long n_items = (long long)((rows + TM - 1) / TM) * kblocks;
+  const int row_tiles = ((ones_row > 0 ? ones_row + 1 : rows) + TM - 1) / TM;
+  const long long n_items = (long long)row_tiles * kblocks;
   const int grid = (int)(n_items > 148 * 16 ? 148 * 16 : n_items);
-  CVF_LAUNCH(K_AE_STEP, stream, tile_image_kernel<<<grid, 256, 0, stream>>>(X, ld, kcontig, rows, K, kblocks, img));
+  CVF_LAUNCH(K_AE_STEP, stream, tile_image_kernel<<<grid, 256, 0, stream>>>(X, ld, kcontig, rows, K, kblocks, row_tiles, ones_row, img));
   CVF_CUDA(cudaGetLastError());
   return 0;
 }
