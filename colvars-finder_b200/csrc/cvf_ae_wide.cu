@@ -257,12 +257,18 @@ __global__ void __launch_bounds__(256) accumulate_grad_kernel(const float* __res
   }
 }
 
-__global__ void add_sums_kernel(const double* __restrict__ part, int n_blocks, double* __restrict__ sums, int first) {
-  if (threadIdx.x < 2 && blockIdx.x == 0) {
-    double t = first ? 0.0 : sums[threadIdx.x];
-    for (int b = 0; b < n_blocks; ++b) t += part[(size_t)b * 2 + threadIdx.x];
-    sums[threadIdx.x] = t;
+// sums[c] (+)= sum_b part[2 b + c], c = 0, 1: strided partial sums per thread, then a tree over the block (fixed order)
+__global__ void __launch_bounds__(256) add_sums_kernel(const double* __restrict__ part, int n_blocks, double* __restrict__ sums, int first) {
+  __shared__ double red[2][256];
+  double t0 = 0.0, t1 = 0.0;
+  for (int b = threadIdx.x; b < n_blocks; b += 256) t0 += part[(size_t)b * 2], t1 += part[(size_t)b * 2 + 1];
+  red[0][threadIdx.x] = t0, red[1][threadIdx.x] = t1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[0][threadIdx.x] += red[0][threadIdx.x + o], red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x < 2) sums[threadIdx.x] = (first ? 0.0 : sums[threadIdx.x]) + red[threadIdx.x][0];
 }
 
 __global__ void zero_doubles_kernel(double* p, long long n) {
@@ -331,6 +337,13 @@ static void make_plan(const NetPlan& np, WidePlan* P) {
 }
 
 constexpr int kMaxSplits = 32;
+constexpr long long kChunkFrames = 32768;
+// slots of (sum w |e|^2, sum w) partial sums: one per block of the loss kernel, or one per output tile of the last product
+static size_t part_slots(const WidePlan& P) {
+  const size_t tiles = (size_t)((P.dims[P.L] + 127) / 128) * (size_t)(kChunkFrames / 128);
+  const size_t blocks = (size_t)sm_count() * 8;
+  return tiles > blocks ? tiles : blocks;
+}
 std::atomic<int> g_wide_mode{0};   // 0: tensor-core products (tcgen05, 3 x TF32; default), 1: fp32 SIMT products
 
 static int launch_gemm(const Gemm& g, int splits, cudaStream_t stream) {
@@ -353,11 +366,11 @@ int wide_ae_set_mode(int mode) {
 size_t wide_ae_workspace_bytes(const NetPlan& np, long long B) {
   wide::WidePlan P;
   wide::make_plan(np, &P);
-  long long chunk = B < 32768 ? B : 32768;
+  long long chunk = B < wide::kChunkFrames ? B : wide::kChunkFrames;
   chunk = (chunk + 127) / 128 * 128;
   const size_t per_frame = (P.act_floats_per_frame + P.delta_floats_per_frame + P.img_floats_per_frame) * sizeof(float);
   return 8192 + (P.w_floats + P.wimg_floats) * sizeof(float) + (size_t)wide::kMaxSplits * P.dw_max_floats * sizeof(float) +
-         (size_t)chunk * per_frame + (size_t)sm_count() * 8 * 2 * sizeof(double);
+         (size_t)chunk * per_frame + wide::part_slots(P) * 2 * sizeof(double) + 4096;
 }
 
 int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long B, const float* params, double* sums_out,
@@ -374,7 +387,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
     off += (bytes + 255) & ~(size_t)255;
     return p;
   };
-  double* part = (double*)take((size_t)sm_count() * 8 * 2 * sizeof(double));
+  double* part = (double*)take(part_slots(P) * 2 * sizeof(double));
   float* Wp = (float*)take(P.w_floats * sizeof(float));
   float* Wimg = (float*)take(P.wimg_floats * sizeof(float));
   float* dWp = (float*)take((size_t)kMaxSplits * P.dw_max_floats * sizeof(float));
@@ -385,7 +398,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
   const size_t per_frame = (P.act_floats_per_frame + P.delta_floats_per_frame + P.img_floats_per_frame) * sizeof(float);
   long long chunk = (long long)((ws_bytes - off - 2048) / per_frame);
   chunk = chunk / 128 * 128;
-  if (chunk > 32768) chunk = 32768;
+  if (chunk > kChunkFrames) chunk = kChunkFrames;
   if (chunk < 128) {
     set_error("workspace too small for the layer-wise autoencoder path: %zu bytes leave no room for a 128-frame chunk", ws_bytes);
     return CVF_E_WORKSPACE;
@@ -459,6 +472,9 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         CVF_LAUNCH(K_AE_STEP, stream, set_pad_kernel<<<grid, 256, 0, stream>>>(acts[l], M, P.dims[l], P.ld[l]));
       }
     }
+    // the tensor-core path folds the loss into the last product's epilogue: delta_L leaves it as images, A_L is never stored
+    const bool fused_loss = tc && !P.act[L - 1];
+    int loss_slots = 0;
     for (int l = 0; l < L; ++l) {   // forward
       Gemm g;
       memset(&g, 0, sizeof(g));
@@ -474,25 +490,34 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
         if (l + 1 < L) {
           g.c_img_k = imgK[l + 1], g.c_img_k_kblocks = (P.dims[l + 1] + 31) / 32;
           if (grad_out) g.c_img_t = imgT[l + 1], g.c_img_t_kblocks = fblocks, g.c_img_t_ones = P.dims[l + 1];
+        } else if (fused_loss) {
+          g.epi = EPI_BIAS_LOSS;
+          g.loss_in = in0, g.loss_ld = ld0, g.loss_w = w + f0, g.loss_part = part;
+          g.C = nullptr;
+          loss_slots = gemm_tc_tiles(g, 1);
+          if (grad_out) {
+            g.c_img_t = dT[0], g.c_img_t_kblocks = fblocks;
+            if (L >= 2) g.c_img_k = dK[0], g.c_img_k_kblocks = (P.dims[L] + 31) / 32;
+          }
         }
       }
       int e = launch_gemm(g, 1, stream);
       if (e) return e;
     }
-    {
-      int grid = sm_count() * 8;
-      if ((M + 7) / 8 < grid) grid = (M + 7) / 8;
+    if (!fused_loss) {
+      loss_slots = sm_count() * 8;
+      if ((M + 7) / 8 < loss_slots) loss_slots = (M + 7) / 8;
       CVF_LAUNCH(K_AE_STEP, stream,
-                 loss_delta_kernel<<<grid, 256, 0, stream>>>(acts[L], in0, w, f0, M, P.dims[L], P.ld[L], ld0, part));
-      CVF_LAUNCH(K_REDUCE, stream, add_sums_kernel<<<1, 32, 0, stream>>>(part, grid, sums_out, first ? 1 : 0));
-      CVF_CUDA(cudaGetLastError());
+                 loss_delta_kernel<<<loss_slots, 256, 0, stream>>>(acts[L], in0, w, f0, M, P.dims[L], P.ld[L], ld0, part));
     }
+    CVF_LAUNCH(K_REDUCE, stream, add_sums_kernel<<<1, 256, 0, stream>>>(part, loss_slots, sums_out, first ? 1 : 0));
+    CVF_CUDA(cudaGetLastError());
     first = false;
     if (!grad_out) continue;
     // backward: delta_L lives in acts[L]; lower deltas ping-pong in dbuf (SIMT path) / in the image pairs (tensor-core path)
     const float* dcur = acts[L];
     int cur_ld = P.ld[L], cur = 0;
-    if (tc) {
+    if (tc && !fused_loss) {
       int e = launch_tile_image(dcur, cur_ld, 0, P.dims[L], M, 0, dT[0], stream);
       if (e) return e;
       if (L >= 2) {

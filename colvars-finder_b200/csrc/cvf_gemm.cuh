@@ -6,7 +6,7 @@
 namespace cvf {
 namespace wide {
 
-enum Epilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2, EPI_MUL_OM = 3 };
+enum Epilogue { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2, EPI_MUL_OM = 3, EPI_BIAS_LOSS = 4 };
 
 struct Gemm {
   // C[m][n] = sum_k Aop[m][k] Bop[k][n],  m < M, n < N, k in this split's range.  Every matrix has a leading dimension that
@@ -41,11 +41,19 @@ struct Gemm {
   float* c_img_k;
   float* c_img_t;
   int c_img_k_kblocks, c_img_t_kblocks, c_img_t_ones;
+  // EPI_BIAS_LOSS (tensor-core path, last layer of the autoencoder): with out = product + bias, e = out - loss_in[m][n],
+  // C / the images receive delta = 2 w[m] e, and every output tile t (column tile fastest) writes its share of
+  // (sum w |e|^2, sum w) to loss_part[2 t], loss_part[2 t + 1]
+  const float* loss_in;
+  long long loss_ld;
+  const float* loss_w;
+  double* loss_part;
 };
 
-// cvf_gemm_tc.cu: the same product on the 5th-generation tensor cores; grid = (ceil(N/128), ceil(M/128), splits), k_per_split
-// a multiple of 32 when splits > 1
+// cvf_gemm_tc.cu: the same product on the 5th-generation tensor cores; both operands as tile images; ceil(N/128) x ceil(M/128) x
+// splits output tiles walked by one persistent CTA per SM; k_per_split a multiple of 32 when splits > 1
 int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream);
+inline int gemm_tc_tiles(const Gemm& g, int splits) { return ((g.N + 127) / 128) * ((g.M + 127) / 128) * splits; }
 // floats of the image of an operand with `rows` rows and K columns
 inline size_t tile_image_floats(int rows, int K) { return (size_t)((rows + 127) / 128) * ((K + 31) / 32) * 8192; }
 // builds the image of Xop[row][k] = kcontig ? X[row * ld + k] : X[k * ld + row], row < rows; ones_row > 0 (>= rows): one more

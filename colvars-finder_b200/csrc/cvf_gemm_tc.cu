@@ -1,22 +1,23 @@
 // cvf_gemm_tc.cu -- C[M x N] = Aop[M x K] Bop[K x N] in fp32 accuracy on the 5th-generation tensor cores (tcgen05).
 //
-// fp32 operands are split while they are staged into shared memory, x = hi + lo with hi = x truncated to TF32 (10-bit
-// mantissa), and every 128 x 128 x 32 block is three kind::tf32 products accumulated in fp32 in tensor memory:
+// fp32 operands are split, x = hi + lo with hi = x truncated to TF32 (10-bit mantissa), and every 128 x 128 x 32 block is three
+// kind::tf32 products accumulated in fp32 in tensor memory:
 //     D += Ahi Bhi + Alo Bhi + Ahi Blo          (the dropped lo*lo term is 2^-20 relative)
 // which keeps the 1e-5 parity target of the training step that a single TF32 pass (2^-11) cannot.
 //
-//   * operands: both tiles are staged K-major ([row][32 k] = 128-byte rows) in the canonical 128-byte-swizzled layout the
-//     UMMA shared-memory descriptor expects (8-row groups of 1024 bytes, 16-byte chunk index XOR row mod 8); the staging threads
-//     transpose on the fly when the global operand is contiguous along the other dimension;
-//   * a ninth warp does nothing but issue the MMAs (one thread; M = 128, N = 128, K = 8 per instruction; 12 per stage) as the
-//     stages fill (mbarrier per stage, 256 arrivals) and commit them (tcgen05.commit on a second mbarrier per stage, which
-//     returns the stage); three stages, and the staging threads' global loads run two blocks ahead of their stores, so load
-//     latency, staging and the tensor core overlap;
+//   * operands: both operands arrive as "tile images" (cvf_gemm.cuh): already split into hi / lo and laid out K-major ([row][32 k] =
+//     128-byte rows) in the canonical 128-byte-swizzled layout the UMMA shared-memory descriptor expects (8-row groups of 1024
+//     bytes, 16-byte chunk index XOR row mod 8), so a stage (Ahi | Alo | Bhi | Blo, 64 KB) is filled by two 1-D bulk copies (TMA)
+//     issued by one thread; weights' images are built once per step (tile_image_kernel), activations' and deltas' images are
+//     written by the epilogue of the product that computes them;
+//   * persistent, warp-specialised (see the kernel): a copy thread, an MMA thread (M = 128, N = 128, K = 8 per instruction; 12 per
+//     stage; three stages handed over through mbarriers) and eight drain / epilogue warps; the epilogue of a tile overlaps the
+//     first two chains of the next tile;
 //   * the 128 x 128 fp32 accumulator lives in tensor memory and is read back with tcgen05.ld (32 lanes x 32 columns per warp
 //     instruction).  The tensor core adds into it with truncation, not round-to-nearest: the error is a bias that grows with
 //     the number of accumulated MMAs (measured: 3e-5 relative after the 1128 MMAs of a K = 3000 product, which broke the 2e-5
 //     gradient bar at the real C5 shape).  So a chain is at most kGroup k-blocks (96 MMAs) long: two chain buffers (2 x 128
-//     columns) alternate, and while the tensor core fills one the staging warps add the other, 16 columns at a time and with
+//     columns) alternate, and while the tensor core fills one the drain warps add the other, 16 columns at a time and with
 //     ordinary round-to-nearest additions in registers, onto a third 128-column "master" tile that also lives in tensor
 //     memory (register pressure stays what it was); the fused epilogue (bias / tanh / multiplication by 1 - act^2) reads the
 //     master tile.
@@ -111,6 +112,283 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// ---------------------------------------------------------------------------------------------------- the product kernel
+// Persistent: one CTA per SM walks over the output tiles (column tile fastest, so that the CTAs running at one time share A row
+// tiles in L2).  Ten warps:
+//   warp 9   one thread issues the bulk copies (TMA) that fill the stages from the operand images, as far ahead as the ring allows;
+//   warp 8   one thread issues the MMAs of every filled stage, commits the stage back to the copy thread, and commits every chain
+//            of kGroup k-blocks to the drain warps;
+//   warps 0-7  add finished chains onto the master tile (tensor memory) and, after a tile's last chain, run its epilogue -- while
+//            the tensor core is already working on the next tile's first two chains (the two chain buffers).
+// The stage ring, the chain buffers and their mbarrier phases run on across tiles.
+constexpr int kGemmThreads = 320;
+
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const Gemm g, int nx, int ny, int n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_done[kStages];   // tensor core has finished reading the stage
+  __shared__ __align__(8) uint64_t full[kStages];       // the stage's bulk copies have landed
+  __shared__ __align__(8) uint64_t acc_full[2];         // the MMAs of a chain have all landed in chain buffer b
+  __shared__ __align__(8) uint64_t acc_free[2];         // the 256 draining threads have read chain buffer b
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ double red[2][8];
+  // 1024-byte aligned operand area (the swizzle pattern is a function of the absolute address bits)
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&mma_done[s], 1), mbar_init(&full[s], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_free[b], 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = tmem_base_slot;
+  constexpr size_t kImgTile = 2 * kTileBytes / 4;   // floats of one (row tile, k-block) of an image: hi | lo
+
+  // tile t of this product: column tile x (fastest), row tile y, k-split z; its k-blocks
+  auto tile_blocks = [&](int t, int& x, int& y, int& z, int& kbeg) {
+    x = t % nx;
+    const int r = t / nx;
+    y = r % ny, z = r / ny;
+    kbeg = z * g.k_per_split;
+    const int kend = min(g.K, kbeg + g.k_per_split);
+    return (kend - kbeg + TK - 1) / TK;
+  };
+
+  if (warp == 9) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int x, y, z, kbeg;
+        const int n_blocks = tile_blocks(t, x, y, z, kbeg);
+        const float* a_img = g.a_img + ((size_t)y * g.a_img_kblocks + kbeg / TK) * kImgTile;
+        const float* b_img = g.b_img + ((size_t)x * g.b_img_kblocks + kbeg / TK) * kImgTile;
+        for (int blk = 0; blk < n_blocks; ++blk, ++it) {
+          const uint32_t s = it % kStages, use = it / kStages;
+          if (use >= 1) mbar_wait(&mma_done[s], (use - 1) & 1);   // the MMAs that last read this stage have finished
+          uint8_t* st = tiles + (size_t)s * kStageBytes;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"((uint32_t)(4 * kTileBytes))
+                       : "memory");
+          bulk_g2s(st, a_img + (size_t)blk * kImgTile, 2 * kTileBytes, &full[s]);
+          bulk_g2s(st + 2 * kTileBytes, b_img + (size_t)blk * kImgTile, 2 * kTileBytes, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      uint32_t it = 0, gi = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int x, y, z, kbeg;
+        const int n_blocks = tile_blocks(t, x, y, z, kbeg);
+        for (int blk = 0; blk < n_blocks; ++blk, ++it) {
+          const uint32_t s = it % kStages, use = it / kStages;
+          const int kb = blk % kGroup;
+          const uint32_t ab = gi & 1;
+          // a chain buffer is reused by chain gi + 2: its previous contents (chain gi - 2) must have been drained
+          if (kb == 0 && gi >= 2) mbar_wait(&acc_free[ab], ((gi >> 1) - 1) & 1);
+          mbar_wait(&full[s], use & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_acc = tmem_d + 128u * ab;
+          const uint32_t a_hi = smem_u32(tiles + (size_t)s * kStageBytes);
+          const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + kTileBytes), db_hi = umma_desc(a_hi + 2 * kTileBytes),
+                         db_lo = umma_desc(a_hi + 3 * kTileBytes);
+#pragma unroll
+          for (int kk = 0; kk < TK / 8; ++kk) {
+            const uint64_t ko = (uint64_t)(kk * 32 >> 4);   // 8 TF32 = 32 bytes along K inside the swizzle row (address field: >> 4)
+            umma_tf32(tmem_acc, da_hi + ko, db_hi + ko, (kb | kk) != 0);
+            umma_tf32(tmem_acc, da_lo + ko, db_hi + ko, 1);
+            umma_tf32(tmem_acc, da_hi + ko, db_lo + ko, 1);
+          }
+          umma_commit(&mma_done[s]);
+          if (kb == kGroup - 1 || blk == n_blocks - 1) {
+            umma_commit(&acc_full[ab]);
+            ++gi;
+          }
+        }
+      }
+    }
+  } else {
+    // chain gi sits in chain buffer gi & 1; its use number gi >> 1 gives the phase of the buffer's barriers.  A thread owns lanes
+    // 32 (warp % 4) .. +31 (rows) x columns 64 (warp / 4) .. +63 of the tile, in the chain buffers and in the master tile alike,
+    // so the drains and the epilogue of one thread never touch another thread's part: no barrier between them.
+    uint32_t gi = 0;
+    const uint32_t lane_base = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      int x, y, z, kbeg;
+      const int n_blocks = tile_blocks(t, x, y, z, kbeg);
+      const int n_groups = (n_blocks + kGroup - 1) / kGroup;
+      for (int grp = 0; grp < n_groups; ++grp, ++gi) {
+        const uint32_t b = gi & 1;
+        mbar_wait(&acc_full[b], (gi >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int piece = 0; piece < 4; ++piece) {
+          uint32_t c[16], m[16];
+          ld16(lane_base + 128u * b + (uint32_t)(16 * piece), c);
+          if (grp > 0) ld16(lane_base + kMasterCol + (uint32_t)(16 * piece), m);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (grp > 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = __float_as_uint(__uint_as_float(c[i]) + __uint_as_float(m[i]));
+          }
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+                  lane_base + kMasterCol + (uint32_t)(16 * piece)),
+              "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(c[8]), "r"(c[9]), "r"(c[10]),
+              "r"(c[11]), "r"(c[12]), "r"(c[13]), "r"(c[14]), "r"(c[15])
+              : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&acc_free[b]);
+      }
+
+      // ---- epilogue of tile (x, y, z).  Besides C (row-major fp32) it writes the operand images of C that later products read
+      // (cvf_gemm.cuh): the thread's 32 values of a row are one 128-byte row of a K-major tile (eight 16-byte chunks at their
+      // swizzled places), and for a fixed column the warp's 32 rows are one 128-byte row of the transposed tile (32 scalar stores
+      // = one full line).
+      const int m0 = y * TM, n0 = x * TN;
+      float* C = g.C ? g.C + (size_t)z * g.c_split_stride : nullptr;
+      const int row = m0 + 32 * (warp & 3) + lane;
+      const bool row_ok = row < g.M;
+      float wf = 0.0f, e2 = 0.0f;
+      if (g.epi == EPI_BIAS_LOSS && row_ok) wf = __ldg(g.loss_w + row);
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        const int col0 = 64 * (warp >> 2) + 32 * cb;
+        float v[32];
+        {
+          uint32_t lo[16], hi[16];
+          const uint32_t taddr = lane_base + kMasterCol + (uint32_t)(32 * cb);
+          ld16(taddr, lo);
+          ld16(taddr + 16, hi);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(lo[c]), v[16 + c] = __uint_as_float(hi[c]);
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const int n = n0 + col0 + 4 * c4;
+          float o[4] = {v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]};
+          if (row_ok && n < g.N) {
+            if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH || g.epi == EPI_BIAS_LOSS) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (n + c < g.N) {
+                  o[c] += g.bias[n + c];
+                  if (g.epi == EPI_BIAS_TANH) o[c] = cvf_tanh(o[c]);
+                }
+              if (g.epi == EPI_BIAS_LOSS) {   // e = out - in, sum of e^2 per row, delta = 2 w e
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (n + c < g.N) {
+                    const float e = o[c] - __ldg(g.loss_in + (size_t)row * g.loss_ld + n + c);
+                    e2 = fmaf(e, e, e2);
+                    o[c] = 2.0f * wf * e;
+                  }
+              }
+            } else if (g.epi == EPI_MUL_OM) {
+              const float4 a4 = *reinterpret_cast<const float4*>(g.act + (size_t)row * g.ldc + n);
+              o[0] *= fmaf(-a4.x, a4.x, 1.0f), o[1] *= fmaf(-a4.y, a4.y, 1.0f), o[2] *= fmaf(-a4.z, a4.z, 1.0f), o[3] *= fmaf(-a4.w, a4.w, 1.0f);
+            }
+            if (C != nullptr) {
+              if (n + 3 < g.N) {
+                *reinterpret_cast<float4*>(C + (size_t)row * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (n + c < g.N) C[(size_t)row * g.ldc + n + c] = o[c];
+              }
+            }
+          }
+          // what lies outside the matrix is zero in the images
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[4 * c4 + c] = (row_ok && n + c < g.N) ? o[c] : 0.0f;
+        }
+        if (g.c_img_k != nullptr) {
+          const int kb = (n0 + col0) >> 5;
+          if (kb < g.c_img_k_kblocks) {
+            uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_k + ((size_t)y * g.c_img_k_kblocks + kb) * kImgTile);
+            const int r = 32 * (warp & 3) + lane;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              float h[4], l[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) split_tf32(v[4 * ch + c], h[c], l[c]);
+              const uint32_t o = sw_off(r, ch);
+              *reinterpret_cast<float4*>(tile + o) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(tile + kTileBytes + o) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        }
+        if (g.c_img_t != nullptr) {
+          const int kbt = (m0 >> 5) + (warp & 3);
+          if (kbt < g.c_img_t_kblocks) {
+            uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_t + ((size_t)x * g.c_img_t_kblocks + kbt) * kImgTile);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int nl = col0 + c;
+              float xv = v[c];
+              if (g.c_img_t_ones > 0 && n0 + nl == g.c_img_t_ones && row_ok) xv = 1.0f;
+              float h, l;
+              split_tf32(xv, h, l);
+              const uint32_t o = sw_off(nl, lane >> 2) + 4 * (lane & 3);
+              *reinterpret_cast<float*>(tile + o) = h;
+              *reinterpret_cast<float*>(tile + kTileBytes + o) = l;
+            }
+            // the row of ones starts a row tile of its own when N is a multiple of 128: the last column tile's CTAs write it
+            if (g.c_img_t_ones == n0 + TN && col0 == 0) {
+              uint8_t* t2 = reinterpret_cast<uint8_t*>(g.c_img_t + ((size_t)(x + 1) * g.c_img_t_kblocks + kbt) * kImgTile);
+              const uint32_t o = sw_off(0, lane >> 2) + 4 * (lane & 3);
+              *reinterpret_cast<float*>(t2 + o) = row_ok ? 1.0f : 0.0f;
+              *reinterpret_cast<float*>(t2 + kTileBytes + o) = 0.0f;
+            }
+          }
+        }
+      }
+      if (g.epi == EPI_BIAS_LOSS) {
+        // this tile's share of (sum w |e|^2, sum w): fixed order (lanes by shuffle, then the eight warps), one slot per tile
+        double s2 = (double)wf * (double)e2, s0 = (x == 0 && (warp >> 2) == 0) ? (double)wf : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o), s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        if (lane == 0) red[0][warp] = s2, red[1][warp] = s0;
+        bar_sync_epilogue();
+        if (tid < 2) {
+          double tsum = 0.0;
+          for (int q = 0; q < 8; ++q) tsum += red[tid][q];
+          g.loss_part[(size_t)t * 2 + tid] = tsum;
+        }
+        bar_sync_epilogue();
+      }
+    }
+  }
+  // every warp's tensor-memory reads are done before the allocation is returned
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------- image builder
 struct Stage4 {
   float4 v[4];
 };
@@ -176,254 +454,6 @@ __device__ __forceinline__ void tc_store(uint8_t* hi_tile, uint8_t* lo_tile, con
   }
 }
 
-__global__ void __launch_bounds__(288, 1) tc_gemm_kernel(const Gemm g) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_done[kStages];   // tensor core has finished reading the stage
-  __shared__ __align__(8) uint64_t full[kStages];       // the 256 staging threads have filled the stage
-  __shared__ __align__(8) uint64_t acc_full[2];         // the MMAs of a group have all landed in accumulator buffer b
-  __shared__ __align__(8) uint64_t acc_free[2];         // the 256 draining threads have read accumulator buffer b
-  __shared__ uint32_t tmem_base_slot;
-  // 1024-byte aligned operand area (the swizzle pattern is a function of the absolute address bits)
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-  const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
-  const int n_blocks = (kend - kbeg + TK - 1) / TK;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&mma_done[s], 1), mbar_init(&full[s], 256);
-    for (int b = 0; b < 2; ++b) mbar_init(&acc_full[b], 1), mbar_init(&acc_free[b], 256);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_slot;
-
-  // Warp-specialised pipeline.  Warps 0-7 (256 threads) stage: their global loads run two k-blocks ahead of their staging
-  // stores (two register sets, alternating), and the stores run up to three blocks ahead of the tensor core (three
-  // shared-memory stages, handed over through the `full` mbarriers).  Warp 8 only issues the MMAs of every filled stage and
-  // commits them to `mma_done`, which hands the stage back.
-  uint32_t phase[kStages] = {0, 0, 0};
-  // image of this CTA's row tile of each operand (k-block 0), or null
-  const float* a_img = g.a_img ? g.a_img + (size_t)blockIdx.y * g.a_img_kblocks * (2 * kTileBytes / 4) : nullptr;
-  const float* b_img = g.b_img ? g.b_img + (size_t)blockIdx.x * g.b_img_kblocks * (2 * kTileBytes / 4) : nullptr;
-  const int n_groups = (n_blocks + kGroup - 1) / kGroup;
-  // group g sits in chain buffer g & 1; its i-th use (i = g >> 1) completes phase i & 1 of the buffer's barriers.  A thread
-  // owns lanes 32 (warp % 4) .. +31 (rows) x columns 64 (warp / 4) .. +63 of the tile.
-  auto ld16 = [&](uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-  };
-  auto drain = [&](int grp) {
-    const int b = grp & 1;
-    mbar_wait(&acc_full[b], (uint32_t)((grp >> 1) & 1));
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t lane_base = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
-#pragma unroll 1
-    for (int piece = 0; piece < 4; ++piece) {
-      uint32_t c[16], m[16];
-      ld16(lane_base + (uint32_t)(128 * b + 16 * piece), c);
-      if (grp > 0) ld16(lane_base + kMasterCol + (uint32_t)(16 * piece), m);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (grp > 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) c[i] = __float_as_uint(__uint_as_float(c[i]) + __uint_as_float(m[i]));
-      }
-      asm volatile(
-          "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-              lane_base + kMasterCol + (uint32_t)(16 * piece)),
-          "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(c[8]), "r"(c[9]), "r"(c[10]),
-          "r"(c[11]), "r"(c[12]), "r"(c[13]), "r"(c[14]), "r"(c[15])
-          : "memory");
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    mbar_arrive(&acc_free[b]);
-  };
-  int next_drain = 0;
-  if (warp < 8) {
-    Stage4 ra0, rb0, ra1, rb1;
-    if (n_blocks > 0) {
-      if (!a_img) tc_load(ra0, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg, kend, tid);
-      if (!b_img) tc_load(rb0, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg, kend, tid);
-    }
-    if (n_blocks > 1) {
-      if (!a_img) tc_load(ra1, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + TK, kend, tid);
-      if (!b_img) tc_load(rb1, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + TK, kend, tid);
-    }
-    auto body = [&](int blk, Stage4& ra, Stage4& rb) {
-      const int s = blk % kStages;
-      uint8_t* st = tiles + (size_t)s * kStageBytes;
-      // the MMAs that last read this stage (block blk - kStages) must have finished
-      if (blk >= kStages) {
-        mbar_wait(&mma_done[s], phase[s]);
-        phase[s] ^= 1;
-      }
-      if (tid == 0 && (a_img || b_img)) {   // operands that come as tile images: one bulk copy each, counted in bytes on `full`
-        const int kb = kbeg / TK + blk;
-        mbar_expect_tx(&full[s], (uint32_t)((a_img ? 2 : 0) + (b_img ? 2 : 0)) * kTileBytes);
-        if (a_img) bulk_g2s(st, a_img + (size_t)kb * (2 * kTileBytes / 4), 2 * kTileBytes, &full[s]);
-        if (b_img) bulk_g2s(st + 2 * kTileBytes, b_img + (size_t)kb * (2 * kTileBytes / 4), 2 * kTileBytes, &full[s]);
-      }
-      if (!a_img) tc_store(st, st + kTileBytes, ra, g.a_kcontig, tid);
-      if (!b_img) tc_store(st + 2 * kTileBytes, st + 3 * kTileBytes, rb, g.b_kcontig, tid);
-      if (blk + 2 < n_blocks) {
-        if (!a_img) tc_load(ra, g.A, g.lda, g.a_kcontig, m0, g.M, kbeg + (blk + 2) * TK, kend, tid);
-        if (!b_img) tc_load(rb, g.B, g.ldb, g.b_kcontig, n0, g.N, kbeg + (blk + 2) * TK, kend, tid);
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-      mbar_arrive(&full[s]);
-      // one group behind the staging: the group before the one just completed has long been multiplied
-      if (blk % kGroup == kGroup - 1 && blk / kGroup >= 1) drain(next_drain++);
-    };
-    for (int blk = 0; blk < n_blocks; blk += 2) {
-      body(blk, ra0, rb0);
-      if (blk + 1 < n_blocks) body(blk + 1, ra1, rb1);
-    }
-    while (next_drain < n_groups) drain(next_drain++);
-  } else {
-    uint32_t fphase[kStages] = {0, 0, 0};
-    for (int blk = 0; blk < n_blocks; ++blk) {
-      const int s = blk % kStages;
-      const int grp = blk / kGroup, kb = blk - grp * kGroup, ab = grp & 1;
-      // a buffer is reused by group g + 2: its previous contents (group g) must have been drained
-      if (kb == 0 && grp >= 2) mbar_wait(&acc_free[ab], (uint32_t)(((grp >> 1) - 1) & 1));
-      mbar_wait(&full[s], fphase[s]);
-      fphase[s] ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t tmem_acc = tmem_d + (uint32_t)(128 * ab);
-        const uint32_t a_hi = smem_u32(tiles + (size_t)s * kStageBytes);
-        const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + kTileBytes), db_hi = umma_desc(a_hi + 2 * kTileBytes),
-                       db_lo = umma_desc(a_hi + 3 * kTileBytes);
-#pragma unroll
-        for (int kk = 0; kk < TK / 8; ++kk) {
-          const uint64_t ko = (uint64_t)(kk * 32 >> 4);   // 8 TF32 = 32 bytes along K inside the swizzle row (address field: >> 4)
-          umma_tf32(tmem_acc, da_hi + ko, db_hi + ko, (kb | kk) != 0);
-          umma_tf32(tmem_acc, da_lo + ko, db_hi + ko, 1);
-          umma_tf32(tmem_acc, da_hi + ko, db_lo + ko, 1);
-        }
-        umma_commit(&mma_done[s]);
-        if (kb == kGroup - 1 || blk == n_blocks - 1) umma_commit(&acc_full[ab]);
-      }
-      __syncwarp();
-    }
-  }
-  // every group has been added onto the master tile (each drain waited for the commit that covers the group's MMAs)
-
-  // epilogue: warp w reads lanes 32 (w % 4) .. +31 (rows) and columns 64 (w / 4) .. +63.  Besides C (row-major fp32) it writes the
-  // operand images of C that later products read (cvf_gemm.cuh): the thread's 32 values of a row are one 128-byte row of a K-major
-  // tile (eight 16-byte chunks at their swizzled places), and for a fixed column the warp's 32 rows are one 128-byte row of the
-  // transposed tile (32 scalar stores = one full line).
-  float* C = g.C ? g.C + (size_t)blockIdx.z * g.c_split_stride : nullptr;
-  const int row = m0 + 32 * (warp & 3) + lane;
-  const bool row_ok = row < g.M;
-#pragma unroll 1
-  for (int cb = 0; cb < (warp < 8 ? 2 : 0); ++cb) {
-    const int col0 = 64 * (warp >> 2) + 32 * cb;
-    float v[32];
-    if (n_blocks > 0) {
-      uint32_t lo[16], hi[16];
-      const uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + kMasterCol + (uint32_t)col0;
-      ld16(taddr, lo);
-      ld16(taddr + 16, hi);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(lo[c]), v[16 + c] = __uint_as_float(hi[c]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] = 0.0f;
-    }
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const int n = n0 + col0 + 4 * c4;
-      float o[4] = {v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]};
-      if (row_ok && n < g.N) {
-        if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (n + c < g.N) {
-              o[c] += g.bias[n + c];
-              if (g.epi == EPI_BIAS_TANH) o[c] = cvf_tanh(o[c]);
-            }
-        } else if (g.epi == EPI_MUL_OM) {
-          const float4 a4 = *reinterpret_cast<const float4*>(g.act + (size_t)row * g.ldc + n);
-          o[0] *= fmaf(-a4.x, a4.x, 1.0f), o[1] *= fmaf(-a4.y, a4.y, 1.0f), o[2] *= fmaf(-a4.z, a4.z, 1.0f), o[3] *= fmaf(-a4.w, a4.w, 1.0f);
-        }
-        if (C != nullptr) {
-          if (n + 3 < g.N) {
-            *reinterpret_cast<float4*>(C + (size_t)row * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (n + c < g.N) C[(size_t)row * g.ldc + n + c] = o[c];
-          }
-        }
-      }
-      // what lies outside the matrix is zero in the images
-#pragma unroll
-      for (int c = 0; c < 4; ++c) v[4 * c4 + c] = (row_ok && n + c < g.N) ? o[c] : 0.0f;
-    }
-    if (g.c_img_k != nullptr) {
-      const int kb = (n0 + col0) >> 5;
-      if (kb < g.c_img_k_kblocks) {
-        uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_k + ((size_t)blockIdx.y * g.c_img_k_kblocks + kb) * (2 * kTileBytes / 4));
-        const int r = 32 * (warp & 3) + lane;
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float h[4], l[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) split_tf32(v[4 * ch + c], h[c], l[c]);
-          const uint32_t o = sw_off(r, ch);
-          *reinterpret_cast<float4*>(tile + o) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(tile + kTileBytes + o) = make_float4(l[0], l[1], l[2], l[3]);
-        }
-      }
-    }
-    if (g.c_img_t != nullptr) {
-      const int kbt = (m0 >> 5) + (warp & 3);
-      if (kbt < g.c_img_t_kblocks) {
-        uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_t + ((size_t)blockIdx.x * g.c_img_t_kblocks + kbt) * (2 * kTileBytes / 4));
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int nl = col0 + c;
-          float x = v[c];
-          if (g.c_img_t_ones > 0 && n0 + nl == g.c_img_t_ones && row_ok) x = 1.0f;
-          float h, l;
-          split_tf32(x, h, l);
-          const uint32_t o = sw_off(nl, lane >> 2) + 4 * (lane & 3);
-          *reinterpret_cast<float*>(tile + o) = h;
-          *reinterpret_cast<float*>(tile + kTileBytes + o) = l;
-        }
-        // the row of ones starts a row tile of its own when N is a multiple of 128: the last column tile's CTAs write it
-        if (g.c_img_t_ones == n0 + TN && col0 == 0) {
-          uint8_t* t2 = reinterpret_cast<uint8_t*>(g.c_img_t + ((size_t)(blockIdx.x + 1) * g.c_img_t_kblocks + kbt) * (2 * kTileBytes / 4));
-          const uint32_t o = sw_off(0, lane >> 2) + 4 * (lane & 3);
-          *reinterpret_cast<float*>(t2 + o) = row_ok ? 1.0f : 0.0f;
-          *reinterpret_cast<float*>(t2 + kTileBytes + o) = 0.0f;
-        }
-      }
-    }
-  }
-  // every warp's tensor-memory reads are done before the allocation is returned
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
-  }
-}
-
 // One CTA per (row tile, k-block): the same load / split / swizzled store as the product kernel's staging, into shared memory,
 // then the finished 32 KB image (hi tile | lo tile) goes out as coalesced 16-byte stores.  ones_row > 0: the operand has one more
 // row, all ones (k < K), at that index (>= rows).
@@ -463,19 +493,28 @@ int launch_tile_image(const float* X, long long ld, int kcontig, int rows, int K
 }
 
 int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream) {
+  if (g.a_img == nullptr || g.b_img == nullptr) {
+    set_error("tc_gemm_kernel: both operands must be given as tile images");
+    return CVF_E_ARG;
+  }
+  if (splits > 1 && (g.c_img_k != nullptr || g.c_img_t != nullptr || g.epi == EPI_BIAS_LOSS)) {
+    set_error("tc_gemm_kernel: image outputs and the loss epilogue need a single k-split");
+    return CVF_E_ARG;
+  }
   const size_t smem = (size_t)kStages * kStageBytes + 1024;
   static bool configured = false;
   if (!configured) {
     CVF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((g.N + TN - 1) / TN, (g.M + TM - 1) / TM, splits);
-  CVF_LAUNCH(K_AE_STEP, stream, tc_gemm_kernel<<<grid, 288, smem, stream>>>(g));
+  const int nx = (g.N + TN - 1) / TN, ny = (g.M + TM - 1) / TM, n_tiles = nx * ny * splits;
+  const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+  CVF_LAUNCH(K_AE_STEP, stream, tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(g, nx, ny, n_tiles));
   {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-      set_error("tc_gemm_kernel launch failed: grid (%u,%u,%u), %zu B shared memory, M %d N %d K %d: %s", grid.x, grid.y, grid.z, smem,
-                g.M, g.N, g.K, cudaGetErrorString(e));
+      set_error("tc_gemm_kernel launch failed: grid %d, %zu B shared memory, M %d N %d K %d: %s", grid, smem, g.M, g.N, g.K,
+                cudaGetErrorString(e));
       return (int)e;
     }
   }
