@@ -346,6 +346,21 @@ static size_t part_slots(const WidePlan& P) {
 }
 std::atomic<int> g_wide_mode{0};   // 0: tensor-core products (tcgen05, 3 x TF32; default), 1: fp32 SIMT products
 
+// k-splits of a weight-gradient product on the persistent tensor-core kernel: tiles * splits work items are walked by one CTA per
+// SM, so the time is (waves of items) x (k-blocks per item + the fixed cost of an item, about a dozen k-blocks' worth of
+// prologue, drain and epilogue); take the split count that minimises it
+static int pick_splits(int tiles, int K) {
+  const int sms = sm_count(), kblocks = (K + 31) / 32;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= kMaxSplits && s <= kblocks; ++s) {
+    const long long waves = ((long long)tiles * s + sms - 1) / sms;
+    const long long cost = waves * ((kblocks + s - 1) / s + 12);
+    if (best_cost < 0 || cost < best_cost) best = s, best_cost = cost;
+  }
+  return best;
+}
+
 static int launch_gemm(const Gemm& g, int splits, cudaStream_t stream) {
   if (g_wide_mode == 0) return launch_gemm_tc(g, splits, stream);
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
@@ -530,7 +545,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
       {
         const int rows = P.dims[l + 1], cols = P.dims[l] + 1;
         const int tiles = ((rows + BM - 1) / BM) * ((cols + BN - 1) / BN);
-        int splits = (2 * sm_count() + tiles - 1) / tiles;
+        int splits = tc ? pick_splits(tiles, M) : (2 * sm_count() + tiles - 1) / tiles;
         if (splits > kMaxSplits) splits = kMaxSplits;
         int kps = ((M + splits - 1) / splits + 31) / 32 * 32;
         splits = (M + kps - 1) / kps;
