@@ -502,7 +502,8 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
       if (tc) {
         g.a_img = imgK[l], g.a_img_kblocks = (P.dims[l] + 31) / 32;
         g.b_img = Wimg + P.wf_off[l], g.b_img_kblocks = (P.dims[l] + 31) / 32;
-        if (l + 1 < L) {
+        if (l + 1 < L) {   // the next layer and the backward pass read A_{l+1} from its images: no row-major copy
+          g.C = nullptr;
           g.c_img_k = imgK[l + 1], g.c_img_k_kblocks = (P.dims[l + 1] + 31) / 32;
           if (grad_out) g.c_img_t = imgT[l + 1], g.c_img_t_kblocks = fblocks, g.c_img_t_ones = P.dims[l + 1];
         } else if (fused_loss) {
@@ -581,6 +582,7 @@ int wide_ae_step(const NetPlan& np, const float* feat, const float* w, long long
           g.a_img = dK[cur], g.a_img_kblocks = (P.dims[l + 1] + 31) / 32;
           g.b_img = Wimg + P.wb_off[l], g.b_img_kblocks = (P.dims[l + 1] + 31) / 32;
           g.C = nullptr;
+          g.act_img = imgK[l], g.act_img_kblocks = (P.dims[l] + 31) / 32;
           g.c_img_t = dT[cur ^ 1], g.c_img_t_kblocks = fblocks;
           if (l >= 2) g.c_img_k = dK[cur ^ 1], g.c_img_k_kblocks = (P.dims[l] + 31) / 32;
         }

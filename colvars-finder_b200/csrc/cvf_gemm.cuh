@@ -24,6 +24,10 @@ struct Gemm {
   int epi;
   const float* bias;   // [N]
   const float* act;    // EPI_MUL_OM: [M][ldc] activations A with C *= 1 - A^2
+  // tensor-core path: the same activations as their K-major image (rows = m, K = n; hi + lo restores the fp32 value exactly),
+  // so that the forward products need not store a row-major copy; used instead of `act` when not NULL
+  const float* act_img;
+  int act_img_kblocks;
   // Tensor-core path only: operand "tile images".  An image holds the operand already split into TF32 hi / lo parts and laid
   // out exactly as the kernel's shared-memory stage wants it (K-major 128 x 32 tiles, 128-byte swizzle, zero padded):
   // image[(row_tile * kblocks + k_block) * 8192 floats] = hi tile (4096 floats) | lo tile, k_block counted from K = 0.  A stage

@@ -133,6 +133,13 @@ __device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 __device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// shared -> global bulk copy (TMA), one bulk group per copy; wait until the groups' shared-memory reads / everything is done
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const Gemm g, int nx, int ny, int n_tiles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -231,6 +238,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const Gemm g, 
     // so the drains and the epilogue of one thread never touch another thread's part: no barrier between them.
     uint32_t gi = 0;
     const uint32_t lane_base = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(64 * (warp >> 2));
+    uint8_t* slab = tiles + (size_t)kStages * kStageBytes + 4096 * warp;   // this warp's 4 KB for outgoing image pieces
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       int x, y, z, kbeg;
       const int n_blocks = tile_blocks(t, x, y, z, kbeg);
@@ -274,40 +282,88 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const Gemm g, 
 #pragma unroll 1
       for (int cb = 0; cb < 2; ++cb) {
         const int col0 = 64 * (warp >> 2) + 32 * cb;
-        float v[32];
+        // everything this half-row needs from memory is requested before the first use, so that one latency is exposed per
+        // half-row, not one per element: the accumulators (tensor memory), the bias (the same 32 values for every lane) and the
+        // row's 32 values of the side input (activations for 1 - act^2, or the reconstruction target)
+        float v[32], bb[32];
+        float4 aa[8];
+        uint32_t lo[16], hi[16];
         {
-          uint32_t lo[16], hi[16];
           const uint32_t taddr = lane_base + kMasterCol + (uint32_t)(32 * cb);
           ld16(taddr, lo);
           ld16(taddr + 16, hi);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(lo[c]), v[16 + c] = __uint_as_float(hi[c]);
         }
+        const bool has_bias = g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH || g.epi == EPI_BIAS_LOSS;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int n = n0 + col0 + c;
+          bb[c] = (has_bias && n < g.N) ? __ldg(g.bias + n) : 0.0f;
+        }
+        const bool act_from_img = g.epi == EPI_MUL_OM && g.act_img != nullptr;
+        const float* side = act_from_img ? nullptr
+                            : g.epi == EPI_MUL_OM ? g.act + (size_t)row * g.ldc
+                            : g.epi == EPI_BIAS_LOSS ? g.loss_in + (size_t)row * g.loss_ld : nullptr;
+        if (act_from_img) {
+          // this thread's row of the activations' K-major tile (row tile y, k-block = this half-row's 32 columns): hi + lo
+          const int kb = (n0 + col0) >> 5;
+          const uint8_t* tile = reinterpret_cast<const uint8_t*>(g.act_img + ((size_t)y * g.act_img_kblocks + kb) * kImgTile);
+          const int r = 32 * (warp & 3) + lane;
+          const bool in = kb < g.act_img_kblocks;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in) {
+              const uint32_t o = sw_off(r, c4);
+              const float4 h4 = __ldg(reinterpret_cast<const float4*>(tile + o));
+              const float4 l4 = __ldg(reinterpret_cast<const float4*>(tile + kTileBytes + o));
+              t4 = make_float4(h4.x + l4.x, h4.y + l4.y, h4.z + l4.z, h4.w + l4.w);
+            }
+            aa[c4] = t4;
+          }
+        } else {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const int n = n0 + col0 + 4 * c4;
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (side != nullptr && row_ok && n < g.N) {
+              if (n + 3 < g.N) {
+                t4 = __ldg(reinterpret_cast<const float4*>(side + n));
+              } else {
+                t4.x = __ldg(side + n);
+                if (n + 1 < g.N) t4.y = __ldg(side + n + 1);
+                if (n + 2 < g.N) t4.z = __ldg(side + n + 2);
+              }
+            }
+            aa[c4] = t4;
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(lo[c]), v[16 + c] = __uint_as_float(hi[c]);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
           const int n = n0 + col0 + 4 * c4;
           float o[4] = {v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]};
+          const float sd[4] = {aa[c4].x, aa[c4].y, aa[c4].z, aa[c4].w};
           if (row_ok && n < g.N) {
-            if (g.epi == EPI_BIAS || g.epi == EPI_BIAS_TANH || g.epi == EPI_BIAS_LOSS) {
+            if (has_bias) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (n + c < g.N) {
-                  o[c] += g.bias[n + c];
-                  if (g.epi == EPI_BIAS_TANH) o[c] = cvf_tanh(o[c]);
-                }
+              for (int c = 0; c < 4; ++c) {
+                o[c] += bb[4 * c4 + c];
+                if (g.epi == EPI_BIAS_TANH) o[c] = cvf_tanh(o[c]);
+              }
               if (g.epi == EPI_BIAS_LOSS) {   // e = out - in, sum of e^2 per row, delta = 2 w e
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                   if (n + c < g.N) {
-                    const float e = o[c] - __ldg(g.loss_in + (size_t)row * g.loss_ld + n + c);
+                    const float e = o[c] - sd[c];
                     e2 = fmaf(e, e, e2);
                     o[c] = 2.0f * wf * e;
                   }
               }
             } else if (g.epi == EPI_MUL_OM) {
-              const float4 a4 = *reinterpret_cast<const float4*>(g.act + (size_t)row * g.ldc + n);
-              o[0] *= fmaf(-a4.x, a4.x, 1.0f), o[1] *= fmaf(-a4.y, a4.y, 1.0f), o[2] *= fmaf(-a4.z, a4.z, 1.0f), o[3] *= fmaf(-a4.w, a4.w, 1.0f);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) o[c] *= fmaf(-sd[c], sd[c], 1.0f);
             }
             if (C != nullptr) {
               if (n + 3 < g.N) {
@@ -324,18 +380,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const Gemm g, 
           for (int c = 0; c < 4; ++c) v[4 * c4 + c] = (row_ok && n + c < g.N) ? o[c] : 0.0f;
         }
         if (g.c_img_k != nullptr) {
+          // K-major image: the warp's 32 rows x 32 columns are a contiguous 4 KB piece (four 8-row groups) of the hi tile and of
+          // the lo tile; it is put together in the warp's shared-memory slab (16-byte chunks at their swizzled places,
+          // conflict-free) and leaves as one bulk copy (TMA) per piece instead of 32-line scattered stores
           const int kb = (n0 + col0) >> 5;
           if (kb < g.c_img_k_kblocks) {
-            uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_k + ((size_t)y * g.c_img_k_kblocks + kb) * kImgTile);
-            const int r = 32 * (warp & 3) + lane;
+            uint8_t* tile = reinterpret_cast<uint8_t*>(g.c_img_k + ((size_t)y * g.c_img_k_kblocks + kb) * kImgTile) + 4096 * (warp & 3);
+            const uint32_t so = (uint32_t)((lane >> 3) * 1024 + (lane & 7) * 128);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              float h[4], l[4];
+            for (int part = 0; part < 2; ++part) {
+              if (lane == 0) bulk_wait_read();   // the slab's previous piece has left
+              __syncwarp();
 #pragma unroll
-              for (int c = 0; c < 4; ++c) split_tf32(v[4 * ch + c], h[c], l[c]);
-              const uint32_t o = sw_off(r, ch);
-              *reinterpret_cast<float4*>(tile + o) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(tile + kTileBytes + o) = make_float4(l[0], l[1], l[2], l[3]);
+              for (int ch = 0; ch < 8; ++ch) {
+                float h[4], l[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) split_tf32(v[4 * ch + c], h[c], l[c]);
+                *reinterpret_cast<float4*>(slab + so + ((ch ^ (lane & 7)) << 4)) =
+                    part == 0 ? make_float4(h[0], h[1], h[2], h[3]) : make_float4(l[0], l[1], l[2], l[3]);
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) bulk_s2g(tile + part * kTileBytes, slab, 4096);
             }
           }
         }
@@ -380,6 +446,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) tc_gemm_kernel(const Gemm g, 
       }
     }
   }
+  if (warp < 8 && lane == 0) bulk_wait_all();   // outgoing image pieces have left shared memory and are written
   // every warp's tensor-memory reads are done before the allocation is returned
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -501,7 +568,7 @@ int launch_gemm_tc(const Gemm& g, int splits, cudaStream_t stream) {
     set_error("tc_gemm_kernel: image outputs and the loss epilogue need a single k-split");
     return CVF_E_ARG;
   }
-  const size_t smem = (size_t)kStages * kStageBytes + 1024;
+  const size_t smem = (size_t)kStages * kStageBytes + 8 * 4096 + 1024;   // stages, the epilogue warps' slabs, alignment slack
   static bool configured = false;
   if (!configured) {
     CVF_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
