@@ -205,7 +205,14 @@ __device__ __forceinline__ void tanh2(float (&a)[2][N], const float2 (&z)[2][NP 
 #pragma unroll
   for (int f = 0; f < 2; ++f)
 #pragma unroll
-    for (int j = 0; j < N; ++j) a[f][j] = cvf_tanh((j & 1) ? z[f][j >> 1].y : z[f][j >> 1].x);
+    for (int j = 0; j < N; j += 2) {
+      if (j + 1 < N) {   // two at a time, packed (bit-identical to cvf_tanh)
+        const float2 t = cvf_tanh2(z[f][j >> 1]);
+        a[f][j] = t.x, a[f][j + 1] = t.y;
+      } else {
+        a[f][j] = cvf_tanh(z[f][j >> 1].x);
+      }
+    }
 }
 template <int N, int NP>
 __device__ __forceinline__ void unpack2(float (&a)[2][N], const float2 (&z)[2][NP / 2]) {

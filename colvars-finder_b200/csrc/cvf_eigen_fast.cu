@@ -38,37 +38,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
       : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)), "l"(*reinterpret_cast<u64*>(&c)));
   return *reinterpret_cast<float2*>(&d);
 }
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)));
-  return *reinterpret_cast<float2*>(&d);
-}
 __device__ __forceinline__ float2 dup(float x) { return make_float2(x, x); }
-// cvf_tanh (cvf_common.cuh) on two values at once: the same operations in the same order -- bit-identical results -- with the
-// polynomial, the scaling and the final 1 - 2r as packed f32x2 instructions (10 instead of 16 issue slots per value)
-__device__ __forceinline__ float2 cvf_tanh2(float2 x) {
-  const float2 s = fmul2(x, x);
-  float2 p = ffma2(dup(-0.00622109929f), s, dup(0.0210381374f));
-  p = ffma2(p, s, dup(-0.0538453273f));
-  p = ffma2(p, s, dup(0.133325338f));
-  p = ffma2(p, s, dup(-0.333333164f));
-  const float2 small = ffma2(fmul2(x, s), p, x);
-  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
-  const float2 t = fmul2(ax, dup(2.885390082f));
-  float2 e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(t.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(t.y));
-  const float2 e1 = fadd2(e, dup(1.0f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e1.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e1.y));
-  const float2 b = ffma2(dup(-2.0f), r, dup(1.0f));
-  return make_float2(ax.x < 0.55f ? small.x : copysignf(b.x, x.x), ax.y < 0.55f ? small.y : copysignf(b.y, x.y));
-}
 __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 // 4-byte asynchronous global -> shared copy (LDGSTS): no register staging, any number in flight
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
@@ -1350,7 +1320,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll
       for (int j = 0; j < HP; ++j) {
         const float2 t2 = cvf_tanh2(z[j]);
-        const float2 g2 = fmul2(ffma2(make_float2(-t2.x, -t2.y), t2, dup(1.0f)), zd[j]);
+        const float2 g2 = cvf_fmul2(ffma2(make_float2(-t2.x, -t2.y), t2, dup(1.0f)), zd[j]);
         a[2 * j] = t2.x, a[2 * j + 1] = t2.y;
         tg[2 * j] = g2.x, tg[2 * j + 1] = g2.y;
       }
@@ -1377,7 +1347,7 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll
         for (int j = 0; j < HP; ++j) {
           const float2 t2 = cvf_tanh2(z[j]);
-          const float2 g2 = fmul2(ffma2(make_float2(-t2.x, -t2.y), t2, dup(1.0f)), zd[j]);
+          const float2 g2 = cvf_fmul2(ffma2(make_float2(-t2.x, -t2.y), t2, dup(1.0f)), zd[j]);
           a[2 * j] = t2.x, a[2 * j + 1] = t2.y;
           tg[2 * j] = g2.x, tg[2 * j + 1] = g2.y;
         }
