@@ -29,4 +29,8 @@ ncu --set full --clock-control none --import-source on -k regex:"pass1_kernel|pa
 hash=$(python -c "import __graft_entry__ as g; print(g.library_hash())")
 python profiles/ncu_traffic.py $out/${tag}_prof_c3.ncu-rep --workload c3 --frames 4194304 --source-hash $hash --out $out/ncu_traffic.json > /dev/null
 python profiles/ncu_summary.py $out/${tag}_prof_c3.ncu-rep > $out/${tag}_ncu_c3_summary.txt 2>&1
-ls -la $out | grep ${tag}_ | tail -30
+# C5: launch list of one step and a full capture of the forward products + the first two backward products of a chunk
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tc_gemm|tile_image|loss_delta|add_sums|accumulate_grad|stage_input" --launch-skip 150 --launch-count 60 --csv --log-file $out/${tag}_launches_c5.csv python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_launch_c5.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel --launch-skip 68 --launch-count 8 -o $out/${tag}_prof_c5 python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_full_c5.log 2>&1
+python profiles/ncu_summary.py $out/${tag}_prof_c5.ncu-rep > $out/${tag}_ncu_c5_summary.txt 2>&1
+ls -la $out | grep ${tag}_ | tail -40
