@@ -63,10 +63,11 @@ WORKLOADS = {
 METRIC = "train-step frames/sec"
 # fp32 flops per frame (FMA = 2) of the kernels that can dominate a step; derivation in DESIGN.md ("work per frame")
 KERNEL_FLOPS = {
-    # fast_pass2 = primal + tangent forward, reverse sweep of (G, s), every weight-gradient outer product incl. dW_1
-    ("c3", "fast_pass2"): 45240 + 15840, ("c3", "fast_pass1"): 25680,
-    ("c1", "fast_pass2"): 5240, ("c1", "fast_pass1"): 1760,
-    ("c4", "fast_pass2"): 48720 + 19440, ("c4", "fast_pass1"): 29160,
+    # fast_pass2 = tangent forward (the primal activations come back from pass 1), reverse sweep of (G, s), every weight-gradient
+    # outer product incl. dW_1: the flops the kernel EXECUTES (it is bound by the shared-memory pipe)
+    ("c3", "fast_pass2"): 45240 + 15840 - 12720, ("c3", "fast_pass1"): 25680,
+    ("c1", "fast_pass2"): 5240 - 1680, ("c1", "fast_pass1"): 1760,
+    ("c4", "fast_pass2"): 48720 + 19440 - 14520, ("c4", "fast_pass1"): 29160,
     ("c2", "ae_fast_main"): 9120, ("c2", "ae_fast_dw"): 6176,   # forward P + delta sweep (P - first layer); weight + bias products
 }
 def measured_traffic(workload, kernel, frames):

@@ -132,6 +132,7 @@ struct FastPlan {
   float* img;                    // [k][img_floats] followed by geo [geo_floats]
   float* Y;                      // [d_rp][Bp]
   float* Kinv;                   // [6][Bp]
+  float* A;                      // [k][NH * H][Bp] hidden activations A_l of pass 1, read back by pass 2 (which only propagates tangents)
   float* U;                      // [k][d_rp][Bp]
   float* JQ;                     // [k][12][Bp]   gm, q, dc, om
   float* Dq;                     // [k][Bp]
@@ -720,6 +721,7 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
       const float* W = wsm + n * P.img_floats;
       float om[NH][2][H];   // 1 - A_l^2
       float a[2][H];        // current activations
+      float* An = P.A + ((size_t)n * NH * H) * P.Bp + f0 + c0;   // A_l rows kept for pass 2
       // ---- layer 1: z = W1 r + b1 (nn.py:52-57), both frames share every weight load
       {
         float2 z[2][HP];
@@ -748,6 +750,8 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
             a[f][2 * j] = t2.x, a[f][2 * j + 1] = t2.y;
             om[0][f][2 * j] = o2.x, om[0][f][2 * j + 1] = o2.y;
           }
+#pragma unroll
+        for (int o = 0; o < H; ++o) *reinterpret_cast<float2*>(An + (size_t)o * P.Bp) = make_float2(a[0][o], a[1][o]);
       }
       // ---- hidden layers 2..NH
 #pragma unroll
@@ -777,6 +781,8 @@ __global__ void __launch_bounds__(kP1Threads, 1) pass1_kernel(const FastPlan P, 
             a[f][2 * j] = t2.x, a[f][2 * j + 1] = t2.y;
             om[l - 1][f][2 * j] = o2.x, om[l - 1][f][2 * j + 1] = o2.y;
           }
+#pragma unroll
+        for (int o = 0; o < H; ++o) *reinterpret_cast<float2*>(An + (size_t)((l - 1) * H + o) * P.Bp) = make_float2(a[0][o], a[1][o]);
       }
       // ---- output y and the reverse sweep G_l = (1 - A_l^2) .* (W_{l+1}^T G_{l+1}),  G_{NH} seed = Wout
       float yv[2] = {W[I::bout(drp)], W[I::bout(drp)]};
@@ -1230,16 +1236,18 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
       const uint32_t tmn = tmw + (uint32_t)(n * tm_per_net);
       float* Ut = P.U + ((size_t)n * drp) * P.Bp + t * 32;
       __syncwarp();   // the previous network's flush has finished reading the X rows
-      stage_rows(Sr, P.Y + t * 32, d_r, P.Bp, lane);
+      if (P.kind == 1 || inline_dw1) stage_rows(Sr, P.Y + t * 32, d_r, P.Bp, lane);   // r: the alignment Jacobian / the in-row dW_1 read it
       stage_rows(Su, Ut, d_r, P.Bp, lane);
       if (P.kind == 1) stage_rows(Sj, P.JQ + ((size_t)n * 12) * P.Bp + t * 32, 12, P.Bp, lane);
       // L2 prefetch of what is read next: the next network's u rows, or the next tile's r rows and first u rows
       if (n + 1 < n_end) {
         prefetch_rows(P.U + ((size_t)(n + 1) * drp) * P.Bp + t * 32, d_r, P.Bp, lane);
+        prefetch_rows(P.A + ((size_t)(n + 1) * NH * H) * P.Bp + t * 32, NH * H, P.Bp, lane);
         if (P.kind == 1) prefetch_rows(P.JQ + ((size_t)(n + 1) * 12) * P.Bp + t * 32, 12, P.Bp, lane);
       } else if (t_next < n_tiles) {
         prefetch_rows(P.Y + t_next * 32, d_r, P.Bp, lane);
         prefetch_rows(P.U + t_next * 32, d_r, P.Bp, lane);
+        prefetch_rows(P.A + t_next * 32, NH * H, P.Bp, lane);
         if (P.kind == 1) prefetch_rows(P.JQ + t_next * 32, 12, P.Bp, lane);
         prefetch_rows(P.Ys + t_next * 32, k, P.Bp, lane);
         if (lane == 0) prefetch_l2_line(w + t_next * 32);
@@ -1254,10 +1262,12 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         if (seed_extra != nullptr && f < P.B) seed += __ldg(seed_extra + (size_t)n * P.B + f);   // transfer-operator term
       }
       const float scale = (float)(2.0 * (double)wf * c_cD[n]);
-      // ---- joint forward, layer 1: (z, zdot) = W1 (r, v) + (b1, 0); v = scale * J_r J_r^T u built on the fly
-      float2 z[HP], zd[HP];
+      // ---- tangent forward, layer 1: zdot = W1 v; v = scale * J_r J_r^T u built on the fly.  The primal activations A_l are
+      // not recomputed: pass 1 left them in P.A (same arithmetic, so the same values) and each lane reads its frame's column
+      const float* An = P.A + ((size_t)n * NH * H) * P.Bp + f;
+      float2 zd[HP];
 #pragma unroll
-      for (int j = 0; j < HP; ++j) z[j] = lds2(W + I::b1(drp) + 2 * j), zd[j] = make_float2(0.f, 0.f);
+      for (int j = 0; j < HP; ++j) zd[j] = make_float2(0.f, 0.f);
       if (P.kind == 1) {
         cp_async_wait_all();
         __syncwarp();
@@ -1277,16 +1287,14 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
           const cvf_v3 vh = (gp - dc) + cross(omv, yv3);   // vhat = J_r J_r^T u, kept for pass 2b in place of u
           Su[r * RP + lane] = vh.x, Su[(r + 1) * RP + lane] = vh.y, Su[(r + 2) * RP + lane] = vh.z;
           const cvf_v3 vv = scale * vh;
-          const float xin[3] = {yv3.x, yv3.y, yv3.z}, vin[3] = {vv.x, vv.y, vv.z};
+          const float vin[3] = {vv.x, vv.y, vv.z};
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float2 x0 = dup(xin[c]), x1 = dup(vin[c]);
+            const float2 x1 = dup(vin[c]);
             const float* wr = W + (r + c) * H;
 #pragma unroll
             for (int qq = 0; qq < TQ; ++qq) {
               const float4 wv = ld4(wr + 4 * qq);
-              z[2 * qq] = ffma2(make_float2(wv.x, wv.y), x0, z[2 * qq]);
-              z[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[2 * qq + 1]);
               zd[2 * qq] = ffma2(make_float2(wv.x, wv.y), x1, zd[2 * qq]);
               zd[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x1, zd[2 * qq + 1]);
             }
@@ -1297,31 +1305,29 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
         __syncwarp();
 #pragma unroll 2
         for (int r = 0; r < d_r; ++r) {
-          const float xin = Sr[r * RP + lane];
           const float vh = geo[r] * Su[r * RP + lane];
           Su[r * RP + lane] = vh;
           const float vin = scale * vh;
-          const float2 x0 = dup(xin), x1 = dup(vin);
+          const float2 x1 = dup(vin);
           const float* wr = W + r * H;
 #pragma unroll
           for (int qq = 0; qq < TQ; ++qq) {
             const float4 wv = ld4(wr + 4 * qq);
-            z[2 * qq] = ffma2(make_float2(wv.x, wv.y), x0, z[2 * qq]);
-            z[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[2 * qq + 1]);
             zd[2 * qq] = ffma2(make_float2(wv.x, wv.y), x1, zd[2 * qq]);
             zd[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x1, zd[2 * qq + 1]);
           }
         }
       }
+      float a[H], tg[H];   // A_l, T_l = (1 - A_l^2) zdot_l of the current layer
+#pragma unroll
+      for (int o = 0; o < H; ++o) a[o] = __ldg(An + (size_t)o * P.Bp);
       // vhat rows -> global memory (in place of u), 16 bytes per lane, before the Z rows take over the staging area
       __syncwarp();
       if (!inline_dw1) store_rows(Ut, Su, d_r, P.Bp, lane);
-      float a[H], tg[H];   // A_l, T_l = (1 - A_l^2) zdot_l of the current layer
 #pragma unroll
       for (int j = 0; j < HP; ++j) {
-        const float2 t2 = cvf_tanh2(z[j]);
+        const float2 t2 = make_float2(a[2 * j], a[2 * j + 1]);
         const float2 g2 = cvf_fmul2(ffma2(make_float2(-t2.x, -t2.y), t2, dup(1.0f)), zd[j]);
-        a[2 * j] = t2.x, a[2 * j + 1] = t2.y;
         tg[2 * j] = g2.x, tg[2 * j + 1] = g2.y;
       }
       __syncwarp();
@@ -1330,25 +1336,24 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
 #pragma unroll 1   // one copy of the layer code for every hidden layer: the kernel has to stay inside the instruction cache
       for (int l = 2; l <= NH; ++l) {
 #pragma unroll
-        for (int j = 0; j < HP; ++j) z[j] = lds2(W + I::bl(drp, l) + 2 * j), zd[j] = make_float2(0.f, 0.f);
+        for (int o = 0; o < H; ++o) a[o] = __ldg(An + (size_t)((l - 1) * H + o) * P.Bp);   // in flight under the products
+#pragma unroll
+        for (int j = 0; j < HP; ++j) zd[j] = make_float2(0.f, 0.f);
         const float* wt = W + I::wt(drp, l);
 #pragma unroll
         for (int kk = 0; kk < H; ++kk) {
-          const float2 x0 = dup(a[kk]), x1 = dup(tg[kk]);
+          const float2 x1 = dup(tg[kk]);
 #pragma unroll
           for (int qq = 0; qq < TQ; ++qq) {
             const float4 wv = ld4(wt + kk * H + 4 * qq);
-            z[2 * qq] = ffma2(make_float2(wv.x, wv.y), x0, z[2 * qq]);
-            z[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x0, z[2 * qq + 1]);
             zd[2 * qq] = ffma2(make_float2(wv.x, wv.y), x1, zd[2 * qq]);
             zd[2 * qq + 1] = ffma2(make_float2(wv.z, wv.w), x1, zd[2 * qq + 1]);
           }
         }
 #pragma unroll
         for (int j = 0; j < HP; ++j) {
-          const float2 t2 = cvf_tanh2(z[j]);
+          const float2 t2 = make_float2(a[2 * j], a[2 * j + 1]);
           const float2 g2 = cvf_fmul2(ffma2(make_float2(-t2.x, -t2.y), t2, dup(1.0f)), zd[j]);
-          a[2 * j] = t2.x, a[2 * j + 1] = t2.y;
           tg[2 * j] = g2.x, tg[2 * j + 1] = g2.y;
         }
 #pragma unroll
@@ -1795,6 +1800,7 @@ static size_t plan_scratch(FastPlan* P, const cvf_preproc* pp, const NetPlan& np
   P->Y = (float*)take((size_t)P->d_rp * P->Bp * sizeof(float));
   P->Kinv = (float*)take((size_t)6 * P->Bp * sizeof(float));
   P->U = (float*)take((size_t)k * P->d_rp * P->Bp * sizeof(float));
+  P->A = (float*)take((size_t)k * NH * H * P->Bp * sizeof(float));
   P->JQ = (float*)take((size_t)k * 12 * P->Bp * sizeof(float));
   P->Dq = (float*)take((size_t)k * P->Bp * sizeof(float));
   P->Ys = (float*)take((size_t)k * P->Bp * sizeof(float));
