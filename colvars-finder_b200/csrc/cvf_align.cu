@@ -17,31 +17,42 @@
 namespace cvf {
 
 // One frame held at `fr` (3N floats, stride 1): align in place.
-__device__ __forceinline__ void align_frame_inplace(float* fr, int n_atoms, const int32_t* __restrict__ aidx, int n_align,
-                                                    const float* __restrict__ ref, float* R9, float* c3) {
+// `off` = 3 * atom index and `refd` = reference positions in double, both shared-memory tables built once per CTA: the per-atom
+// loops cost one broadcast LDS where they used to load from global memory, scale and convert.
+__device__ __forceinline__ void align_frame_inplace(float* fr, int n_atoms, const int* __restrict__ off, int n_align,
+                                                    const double* __restrict__ refd, float* R9, float* c3) {
+  // one sweep over the alignment atoms (a coordinate is converted to double once): centroid and H = sum x (x) ref, then
+  // (x_A - c)^T ref = sum x (x) ref - c (x) sum ref, with sum ref (refd[3 n_align ..]) the rounding residue of the centred reference
   double cx = 0, cy = 0, cz = 0;
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
   for (int a = 0; a < n_align; ++a) {
-    const float* p = fr + 3 * aidx[a];
-    cx += p[0], cy += p[1], cz += p[2];
+    const float* p = fr + off[a];
+    const double px = p[0], py = p[1], pz = p[2];
+    const double rx = refd[3 * a], ry = refd[3 * a + 1], rz = refd[3 * a + 2];
+    cx += px, cy += py, cz += pz;
+    H[0] = fma(px, rx, H[0]), H[1] = fma(px, ry, H[1]), H[2] = fma(px, rz, H[2]);
+    H[3] = fma(py, rx, H[3]), H[4] = fma(py, ry, H[4]), H[5] = fma(py, rz, H[5]);
+    H[6] = fma(pz, rx, H[6]), H[7] = fma(pz, ry, H[7]), H[8] = fma(pz, rz, H[8]);
   }
   const double inv = 1.0 / n_align;
   cx *= inv, cy *= inv, cz *= inv;
-  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int a = 0; a < n_align; ++a) {
-    const float* p = fr + 3 * aidx[a];
-    const double px = p[0] - cx, py = p[1] - cy, pz = p[2] - cz;
-    const double rx = ref[3 * a], ry = ref[3 * a + 1], rz = ref[3 * a + 2];
-    H[0] += px * rx, H[1] += px * ry, H[2] += px * rz;
-    H[3] += py * rx, H[4] += py * ry, H[5] += py * rz;
-    H[6] += pz * rx, H[7] += pz * ry, H[8] += pz * rz;
+  {
+    const double sx = refd[3 * n_align], sy = refd[3 * n_align + 1], sz = refd[3 * n_align + 2];
+    H[0] = fma(-cx, sx, H[0]), H[1] = fma(-cx, sy, H[1]), H[2] = fma(-cx, sz, H[2]);
+    H[3] = fma(-cy, sx, H[3]), H[4] = fma(-cy, sy, H[4]), H[5] = fma(-cy, sz, H[5]);
+    H[6] = fma(-cz, sx, H[6]), H[7] = fma(-cz, sy, H[7]), H[8] = fma(-cz, sz, H[8]);
   }
   float R[9];
   double Rd[9];
   cvf_rotation(H, R, nullptr, Rd);
   const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+  const double tx = cx * Rd[0] + cy * Rd[3] + cz * Rd[6], ty = cx * Rd[1] + cy * Rd[4] + cz * Rd[7],
+               tz = cx * Rd[2] + cy * Rd[5] + cz * Rd[8];
+#pragma unroll 2
   for (int a = 0; a < n_atoms; ++a) {
     float* p = fr + 3 * a;
-    const cvf_v3 y = cvf_transform(p[0], p[1], p[2], cx, cy, cz, Rd);
+    const cvf_v3 y = cvf_transform_t(p[0], p[1], p[2], tx, ty, tz, Rd);
     p[0] = y.x, p[1] = y.y, p[2] = y.z;
   }
 #pragma unroll
@@ -59,6 +70,18 @@ align_tile_kernel(const float* __restrict__ x, long long B, int n_atoms, const i
   const int tid = threadIdx.x, nt = blockDim.x;
   const int fl = 3 * n_atoms;
   const long long n_tiles = (B + tile_f - 1) / tile_f;
+  // tables behind the frame tile (tile_f * fl floats, rounded up to 8 bytes)
+  double* s_ref = reinterpret_cast<double*>(stage + (((size_t)tile_f * fl + 1) & ~(size_t)1));
+  int* s_off = reinterpret_cast<int*>(s_ref + 3 * n_align + 3);
+  for (int a = tid; a < n_align; a += nt) {
+    s_off[a] = 3 * aidx[a];
+    s_ref[3 * a] = ref[3 * a], s_ref[3 * a + 1] = ref[3 * a + 1], s_ref[3 * a + 2] = ref[3 * a + 2];
+  }
+  if (tid < 3) {
+    double t = 0.0;
+    for (int a = 0; a < n_align; ++a) t += (double)ref[3 * a + tid];
+    s_ref[3 * n_align + tid] = t;
+  }
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
@@ -85,7 +108,7 @@ align_tile_kernel(const float* __restrict__ x, long long B, int n_atoms, const i
     }
     if (tid < nf) {
       float R9[9], c3[3];
-      align_frame_inplace(stage + (size_t)tid * fl, n_atoms, aidx, n_align, ref, R9, c3);
+      align_frame_inplace(stage + (size_t)tid * fl, n_atoms, s_off, n_align, s_ref, R9, c3);
       if (R_out) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) R_out[(f0 + tid) * 9 + i] = R9[i];
@@ -270,7 +293,7 @@ extern "C" int cvf_align_fwd(const float* x, int64_t B, int32_t n_atoms, const i
       break;
     }
   if (tile_f > 0) {
-    const size_t smem = (size_t)tile_f * frame_bytes;
+    const size_t smem = (((size_t)tile_f * frame_bytes + 7) & ~(size_t)7) + (size_t)n_align * (3 * sizeof(double) + sizeof(int)) + 3 * sizeof(double);
     CVF_CUDA(cudaFuncSetAttribute(align_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_tiles = (B + tile_f - 1) / tile_f;
     const int per_sm = (int)((size_t)max_smem_optin() / (smem + 1024));

@@ -348,11 +348,25 @@ __global__ void __launch_bounds__(128, 6) prep_align_kernel(const FastPlan P, co
   // arrives by ONE cp.async.bulk into rows of stride 3N; otherwise (tail tile, unaligned x) cooperative loads into rows of odd stride
   const int fl = 3 * P.n_atoms, S = bulk ? fl : (fl | 1);
   float* kin = st + 128 * (fl | 1);           // [6][128]
+  // the alignment set as shared-memory tables (offset of the atom inside a frame, reference position in double): the per-atom
+  // loops then cost one broadcast LDS where they used to load, scale and convert
+  double* s_ref = reinterpret_cast<double*>(kin + 6 * 128);   // [n_align][3]; 512 (fl|1) + 3072 bytes into the buffer: 8-byte aligned
+  int* s_off = reinterpret_cast<int*>(s_ref + 3 * P.n_align + 3);                       // [n_align]
+  for (int a = tid; a < P.n_align; a += 128) {
+    s_off[a] = 3 * P.align_idx[a];
+    s_ref[3 * a] = P.ref[3 * a], s_ref[3 * a + 1] = P.ref[3 * a + 1], s_ref[3 * a + 2] = P.ref[3 * a + 2];
+  }
+  if (tid < 3) {   // sum of the reference positions (zero up to the rounding of the centred reference), fixed order
+    double t = 0.0;
+    for (int a = 0; a < P.n_align; ++a) t += (double)P.ref[3 * a + tid];
+    s_ref[3 * P.n_align + tid] = t;
+  }
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_barrier_init();
   }
   __syncthreads();
+  const int n_align = P.n_align, n_atoms = P.n_atoms;
   uint32_t phase = 0;
   const long long n_tiles = P.Bp / 128;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -376,28 +390,38 @@ __global__ void __launch_bounds__(128, 6) prep_align_kernel(const FastPlan P, co
     }
     {
       float* fr = st + tid * S;
+      // ONE sweep over the alignment atoms: every coordinate becomes a double once (the float <-> double conversions are what
+      // the fp64 pipe spends most of its time on here) and feeds both the centroid and H = sum x (x) ref; the centroid leaves H
+      // as  (x_A - c)^T ref = sum x (x) ref - c (x) sum ref  (sum ref is the rounding residue of the centred reference)
       double cx = 0, cy = 0, cz = 0;
-      for (int a = 0; a < P.n_align; ++a) {
-        const float* p = fr + 3 * P.align_idx[a];
-        cx += p[0], cy += p[1], cz += p[2];
-      }
-      const double inv = 1.0 / P.n_align;
-      cx *= inv, cy *= inv, cz *= inv;
       double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int a = 0; a < P.n_align; ++a) {
-        const float* p = fr + 3 * P.align_idx[a];
-        const double px = p[0] - cx, py = p[1] - cy, pz = p[2] - cz;
-        const double rx = P.ref[3 * a], ry = P.ref[3 * a + 1], rz = P.ref[3 * a + 2];
-        Hm[0] += px * rx, Hm[1] += px * ry, Hm[2] += px * rz;
-        Hm[3] += py * rx, Hm[4] += py * ry, Hm[5] += py * rz;
-        Hm[6] += pz * rx, Hm[7] += pz * ry, Hm[8] += pz * rz;
+#pragma unroll 2
+      for (int a = 0; a < n_align; ++a) {
+        const float* p = fr + s_off[a];
+        const double px = p[0], py = p[1], pz = p[2];
+        const double rx = s_ref[3 * a], ry = s_ref[3 * a + 1], rz = s_ref[3 * a + 2];
+        cx += px, cy += py, cz += pz;
+        Hm[0] = fma(px, rx, Hm[0]), Hm[1] = fma(px, ry, Hm[1]), Hm[2] = fma(px, rz, Hm[2]);
+        Hm[3] = fma(py, rx, Hm[3]), Hm[4] = fma(py, ry, Hm[4]), Hm[5] = fma(py, rz, Hm[5]);
+        Hm[6] = fma(pz, rx, Hm[6]), Hm[7] = fma(pz, ry, Hm[7]), Hm[8] = fma(pz, rz, Hm[8]);
+      }
+      const double inv = 1.0 / n_align;
+      cx *= inv, cy *= inv, cz *= inv;
+      {
+        const double sx = s_ref[3 * n_align], sy = s_ref[3 * n_align + 1], sz = s_ref[3 * n_align + 2];
+        Hm[0] = fma(-cx, sx, Hm[0]), Hm[1] = fma(-cx, sy, Hm[1]), Hm[2] = fma(-cx, sz, Hm[2]);
+        Hm[3] = fma(-cy, sx, Hm[3]), Hm[4] = fma(-cy, sy, Hm[4]), Hm[5] = fma(-cy, sz, Hm[5]);
+        Hm[6] = fma(-cz, sx, Hm[6]), Hm[7] = fma(-cz, sy, Hm[7]), Hm[8] = fma(-cz, sz, Hm[8]);
       }
       float R[9], Ki[6];
       double Rd[9];
       cvf_rotation(Hm, R, Ki, Rd);
-      for (int a = 0; a < P.n_atoms; ++a) {
+      const double tx = cx * Rd[0] + cy * Rd[3] + cz * Rd[6], ty = cx * Rd[1] + cy * Rd[4] + cz * Rd[7],
+                   tz = cx * Rd[2] + cy * Rd[5] + cz * Rd[8];
+#pragma unroll 2
+      for (int a = 0; a < n_atoms; ++a) {
         float* p = fr + 3 * a;
-        const cvf_v3 q = cvf_transform(p[0], p[1], p[2], cx, cy, cz, Rd);
+        const cvf_v3 q = cvf_transform_t(p[0], p[1], p[2], tx, ty, tz, Rd);
         p[0] = q.x, p[1] = q.y, p[2] = q.z;
       }
 #pragma unroll
@@ -1826,7 +1850,7 @@ static int run_forward(const FastPlan& P, const float* x, const float* params, f
     CVF_LAUNCH(K_FAST_PREP, stream,
                prep_feat_kernel<<<(int)grid, 128 * ng, smem, stream>>>(P, x, prep_feat_bulk_ok(P.n_atoms, x) ? 1 : 0));
   } else if (P.kind == 1) {
-    const size_t smem = (size_t)(128 * ((3 * P.n_atoms) | 1) + 6 * 128) * sizeof(float);
+    const size_t smem = (size_t)(128 * ((3 * P.n_atoms) | 1) + 6 * 128) * sizeof(float) + (size_t)P.n_align * (3 * sizeof(double) + sizeof(int)) + 3 * sizeof(double);
     CVF_CUDA(cudaFuncSetAttribute(prep_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long per_sm = (long long)(228 * 1024) / (long long)(smem + 1024);
     per_sm = per_sm < 1 ? 1 : per_sm > 6 ? 6 : per_sm;

@@ -86,6 +86,29 @@ CVF_HD void cvf_jacobi_rot(float (&a)[4][4], float (&v)[4][4]) {
 }
 
 
+// Reciprocal and reciprocal square root of a double from a float seed and ONE Newton step in double (relative error ~1e-13):
+// a full-precision double division / square root is ~25-40 instructions on the fp64 pipe, which is the pipe the Kabsch kernels
+// are bound by; none of their uses (K^-1 of a Newton step, the quaternion norm before the polish) needs the last bits.
+CVF_HD double cvf_rcp_d(double x) {
+  const double ax = fabs(x);
+  if (!(ax > 1e-30 && ax < 1e30)) return 1.0 / x;
+#if defined(__CUDA_ARCH__)
+  const double r = (double)__frcp_rn((float)x);
+#else
+  const double r = (double)(1.0f / (float)x);
+#endif
+  return fma(r, fma(-x, r, 1.0), r);
+}
+CVF_HD double cvf_rsqrt_d(double x) {
+  if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt(x);
+#if defined(__CUDA_ARCH__)
+  const double r = (double)rsqrtf((float)x);
+#else
+  const double r = (double)(1.0f / sqrtf((float)x));
+#endif
+  return r * fma(-0.5 * x, r * r, 1.5);
+}
+
 // Largest eigenvalue / eigenvector of Horn's symmetric traceless 4x4 matrix `a` (entries O(1)) without iterating on the matrix:
 // Newton on its characteristic polynomial  P(l) = l^4 + c2 l^2 + c1 l + c0  from an upper bound of the largest root (all roots are
 // real, so the iteration descends monotonically onto it; Theobald 2005, "QCP"), then the eigenvector as the best-conditioned row
@@ -107,9 +130,9 @@ CVF_HD bool cvf_top_quaternion_qcp(const float (&a)[4][4], float& q0, float& qx,
   const double t3 = a00 * a00 * a00 + a11 * a11 * a11 + a22 * a22 * a22 + a33 * a33 * a33 +
                     3.0 * (a00 * (s01 + s02 + s03) + a11 * (s01 + s12 + s13) + a22 * (s02 + s12 + s23) + a33 * (s03 + s13 + s23)) +
                     6.0 * (a01 * a02 * a12 + a01 * a03 * a13 + a02 * a03 * a23 + a12 * a13 * a23);
-  const double c1 = -t3 / 3.0;
+  const double c1 = t3 * (-1.0 / 3.0);
   // sum of squared roots = -2 c2, zero sum  =>  largest root <= sqrt(3/4 * (-2 c2))
-  double l = sqrt(-1.5 * c2);
+  double l = (double)sqrtf((float)(-1.5 * c2)) * (1.0 + 1e-6);   // float square root, nudged up: it only has to stay an upper bound
   if (!(l > 0.0)) return false;
   for (int it = 0; it < 24; ++it) {
     const double l2 = l * l;
@@ -203,7 +226,7 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
   }
   double Rd[9];
   {
-    const double n = 1.0 / sqrt((double)q0 * q0 + (double)qx * qx + (double)qy * qy + (double)qz * qz);
+    const double n = cvf_rsqrt_d((double)q0 * q0 + (double)qx * qx + (double)qy * qy + (double)qz * qz);
     const double w = q0 * n, x = qx * n, y = qy * n, z = qz * n;
     // R = (column-convention rotation of q)^T
     Rd[0] = w * w + x * x - y * y - z * z;
@@ -231,7 +254,7 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
     const double c00 = kyy * kzz - kyz * kyz, c01 = kxz * kyz - kxy * kzz, c02 = kxy * kyz - kxz * kyy;
     const double c11 = kxx * kzz - kxz * kxz, c12 = kxy * kxz - kxx * kyz, c22 = kxx * kyy - kxy * kxy;
     const double det = kxx * c00 + kxy * c01 + kxz * c02;
-    const double idet = det != 0.0 ? 1.0 / det : 0.0;
+    const double idet = det != 0.0 ? cvf_rcp_d(det) : 0.0;
     Ki[0] = c00 * idet, Ki[1] = c01 * idet, Ki[2] = c02 * idet, Ki[3] = c11 * idet, Ki[4] = c12 * idet, Ki[5] = c22 * idet;
     // K^-1 of the polished rotation is what the Jacobian uses: stop after the planned evaluations once the last step was tiny
     if (it >= CVF_NEWTON_EVALS - 1 && (it == CVF_NEWTON_EVALS + 1 || last_th2 < 1e-16)) break;
@@ -242,8 +265,8 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
     const double th2 = d0 * d0 + d1 * d1 + d2 * d2;
     if (!(th2 < 0.01)) break;   // degenerate frame (K singular): keep the starting rotation
     last_th2 = th2;
-    const double A = 1.0 - th2 / 6.0 + th2 * th2 / 120.0;        // sin(th)/th
-    const double Bc = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;      // (1-cos th)/th^2
+    const double A = 1.0 - th2 * (1.0 / 6.0) + th2 * th2 * (1.0 / 120.0);     // sin(th)/th
+    const double Bc = 0.5 - th2 * (1.0 / 24.0) + th2 * th2 * (1.0 / 720.0);   // (1-cos th)/th^2
     // E = I + A [d]x + B [d]x^2
     double E[9];
     E[0] = 1.0 - Bc * (d1 * d1 + d2 * d2);
@@ -281,6 +304,14 @@ CVF_HD cvf_v3 cvf_transform(float px, float py, float pz, double cx, double cy, 
   const double dx = px - cx, dy = py - cy, dz = pz - cz;
   return v3((float)(dx * Rd[0] + dy * Rd[3] + dz * Rd[6]), (float)(dx * Rd[1] + dy * Rd[4] + dz * Rd[7]),
             (float)(dx * Rd[2] + dy * Rd[5] + dz * Rd[8]));
+}
+
+// the same with the centroid folded in once per frame, t = c R:  y = x R - t.  One subtraction per coordinate fewer, and the
+// only conversions left are x -> double and y -> float (the terms are O(|x|), the cancellation costs ~1e-15 in double)
+CVF_HD cvf_v3 cvf_transform_t(float px, float py, float pz, double tx, double ty, double tz, const double* Rd) {
+  const double dx = px, dy = py, dz = pz;
+  return v3((float)fma(dx, Rd[0], fma(dy, Rd[3], fma(dz, Rd[6], -tx))), (float)fma(dx, Rd[1], fma(dy, Rd[4], fma(dz, Rd[7], -ty))),
+            (float)fma(dx, Rd[2], fma(dy, Rd[5], fma(dz, Rd[8], -tz))));
 }
 
 // ---- feature stencils (values + gradient w.r.t. the atoms of the feature) -------------------------
