@@ -141,7 +141,7 @@ CVF_HD bool cvf_top_quaternion_qcp(const float (&a)[4][4], float& q0, float& qx,
     if (!(dP > 0.0)) return false;
     const double step = P * (double)(1.0f / (float)dP);   // approximate reciprocal: still a contraction, 3 instructions
     l -= step;
-    if (fabs(step) < 1e-11 * l) break;
+    if (fabs(step) < 1e-8 * l) break;   // the eigenvector below is formed in fp32: nothing finer survives
   }
   // k = a - l I; cofactors of the symmetric 4x4 (adjugate entries), fp32 is enough
   const float k00 = (float)(a00 - l), k11 = (float)(a11 - l), k22 = (float)(a22 - l), k33 = (float)(a33 - l);
@@ -257,7 +257,8 @@ CVF_HD void cvf_rotation(const double* H, float* R, float* Kinv, double* Rd_out 
     const double idet = det != 0.0 ? cvf_rcp_d(det) : 0.0;
     Ki[0] = c00 * idet, Ki[1] = c01 * idet, Ki[2] = c02 * idet, Ki[3] = c11 * idet, Ki[4] = c12 * idet, Ki[5] = c22 * idet;
     // K^-1 of the polished rotation is what the Jacobian uses: stop after the planned evaluations once the last step was tiny
-    if (it >= CVF_NEWTON_EVALS - 1 && (it == CVF_NEWTON_EVALS + 1 || last_th2 < 1e-16)) break;
+    // (a step of size th leaves an error O(th^2): after a step below 1e-5 rad the rotation is good to ~1e-10)
+    if (it >= CVF_NEWTON_EVALS - 1 && (it == CVF_NEWTON_EVALS + 1 || last_th2 < 1e-10)) break;
     const double t0 = M[7] - M[5], t1 = M[2] - M[6], t2 = M[3] - M[1];
     double d0 = Ki[0] * t0 + Ki[1] * t1 + Ki[2] * t2;
     double d1 = Ki[1] * t0 + Ki[3] * t1 + Ki[4] * t2;
