@@ -84,6 +84,8 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
   __trap();
 }
 __device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the 128-byte line at p (aligned) will not be read again: L2 may drop it without writing it back to HBM
+__device__ __forceinline__ void discard_l2_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 // warp prefetch of `nrows` row segments (one 128-byte line each: 32 frames of a frame-minor row)
 __device__ __forceinline__ void prefetch_rows(const float* base, int nrows, long long Bp, int lane) {
   for (int r = lane; r < nrows; r += 32) prefetch_l2_line(base + (size_t)r * Bp);
@@ -1519,6 +1521,9 @@ pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __rest
               __syncwarp();
               const float* R = Zr + (size_t)(c & 1) * 2 * CW * RP;
               const int c0 = c * CW;
+              // the chunk's vhat rows were written by this warp only to come back from L2 here; nothing reads them again
+              // (pass 2 consumes the scratch), so their lines need not reach HBM
+              for (int r = c0 + lane; r < d_r && r < c0 + CW; r += 32) discard_l2_line(Ut + (size_t)r * P.Bp);
               float2 acc[TQ][CI];
 #pragma unroll
               for (int j = 0; j < TQ; ++j)
