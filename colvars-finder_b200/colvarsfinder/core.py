@@ -184,6 +184,14 @@ class _GraphedStep:
         self.replays += 1
         return tuple(o.clone() for o in self.static_out)
 
+    def release(self):
+        """Drop the captured graph and its static buffers (the counters stay).  train() calls this when its loops are done: a
+        graph that captured NCCL all-reduces keeps a persistent reference on the communicator, and
+        torch.distributed.destroy_process_group() then waits for it forever (seen as a 2-rank run that never exits)."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.task.device)
+        self.graph, self.static_in, self.static_out, self._keep, self.shapes = None, None, None, None, None
+
     def _eager_after_graph(self, batch):
         # a batch of another size: run it eagerly on gradients of its own (the graph owns the static .grad tensors)
         if not self.train:
@@ -439,6 +447,7 @@ class EigenFunctionTask(TrainingTask):
             for i, name in enumerate(loss_names):
                 self.writer.add_scalar('%s/train' % name, mean_tr[i], epoch)
                 self.writer.add_scalar('%s/test' % name, mean_te[i], epoch)
+        graphed.release(), graphed_test.release()
         import pandas as pd
         self.train_loss_df = pd.DataFrame(torch.cat([torch.mean(l[0], dim=0, keepdim=True) for l in self.loss_list]).numpy(),
                                           columns=loss_names)
@@ -533,6 +542,7 @@ class AutoEncoderTask(TrainingTask):
             self.loss_list.append([tr, te])
             self.writer.add_scalar('Loss/train', torch.mean(tr), epoch)
             self.writer.add_scalar('Loss/test', torch.mean(te), epoch)
+        graphed.release(), graphed_test.release()
         import pandas as pd
         self.train_loss_df = pd.DataFrame(torch.stack([torch.mean(l[0]) for l in self.loss_list]).numpy(), columns=['loss'])
         self.test_loss_df = pd.DataFrame(torch.stack([torch.mean(l[1]) for l in self.loss_list]).numpy(), columns=['loss'])
@@ -820,6 +830,7 @@ class RegAutoEncoderTask(TrainingTask):
             for i, name in enumerate(loss_names):
                 self.writer.add_scalar('%s/train' % name, mean_tr[i], epoch)
                 self.writer.add_scalar('%s/test' % name, mean_te[i], epoch)
+        graphed.release(), graphed_test.release()
         import pandas as pd
         self.train_loss_df = pd.DataFrame(torch.cat([torch.mean(l[0], dim=0, keepdim=True) for l in self.loss_list]).numpy(),
                                           columns=loss_names)
