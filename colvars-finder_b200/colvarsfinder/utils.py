@@ -51,8 +51,9 @@ class WeightedTrajectory:
         if weight_filename:
             import pandas as pd
             w = pd.read_csv(weight_filename, usecols=[0], header=None)[0].to_numpy(dtype=np.float64)
-            if verbose:
+            if verbose:   # the reference's summary of the normalised weights (utils.py:147-149)
                 print('\nloading weights from file: ', weight_filename)
+                print('\nWeights:\n', pd.Series(w / w.mean()).describe(percentiles=[0.2, 0.4, 0.6, 0.8]))
             if self.n_frames != len(w):
                 raise ValueError('length in weight file does match the trajectory data!\n')
             if device is not None:
@@ -64,9 +65,11 @@ class WeightedTrajectory:
                 self.trajectory = self.trajectory[keep, ...]
                 w = w[keep]
                 self.weights = w / w.mean()
-            if verbose:
+            if verbose:   # utils.py:160-165
                 print('\nAfter selecting states whose weights are in [{:.3e}, {:.3e}] and renormalization:\n'
-                      '\nShape of trajectory: {}'.format(min_w, max_w, self.trajectory.shape))
+                      '\nShape of trajectory: {}'.format(min_w, max_w, tuple(self.trajectory.shape)))
+                w_sel = self.weights.detach().cpu().numpy() if torch.is_tensor(self.weights) else self.weights
+                print('\nWeights:\n', pd.Series(w_sel).describe(percentiles=[0.2, 0.4, 0.6, 0.8]))
         else:
             self.weights = np.ones(self.n_frames)
             if device is not None:
