@@ -14,10 +14,12 @@
 //   prep   : Kabsch alignment of every frame (pp_layer, core.py:403), written frame-minor ("SoA": row = coordinate,
 //            column = frame) with the 3x3 K^-1 of the alignment Jacobian;  Identity pp: a transpose
 //   pass 1 : y = model(r) (core.py:403), u = grad_r y (core.py:424) by a reverse sweep, Dirichlet density
-//            D = |J_r^T u|^2 (core.py:426) and the four 3-vectors of the alignment Jacobian applied to u;  2 frames / thread
+//            D = |J_r^T u|^2 (core.py:426) and the four 3-vectors of the alignment Jacobian applied to u;  2 frames / thread.
+//            The hidden activations A_l stay in global memory for pass 2
 //   stats  : fp64 batch sums (core.py:406-410,426)
-//   pass 2 : d loss / d theta (core.py:517): primal + tangent forward sweep fused (the tangent direction is
-//            v = J_r J_r^T u), reverse sweep of (G, s) fused, outer products per layer;  1 frame / lane
+//   pass 2 : d loss / d theta (core.py:517): tangent forward sweep (direction v = J_r J_r^T u; the primal
+//            activations are pass 1's), reverse sweep of (G, s) fused, outer products per layer;  1 frame / lane.
+//            Bound by the shared-memory pipe (operand loads of the outer products, weight broadcasts), not by the FMA count
 #include <math.h>
 #include <string.h>
 
@@ -1181,10 +1183,11 @@ __device__ __forceinline__ void outer_tile(float2 (&acc)[TO][TI], const float* _
 }
 
 // Pass 2.  One CTA per SM, up to 8 independent warps; a warp owns tiles of 32 frames (lane = frame) and a private set of
-// operand rows: Z rows (A_l | T_l of every hidden layer; during layer 1 they stage r and u) and X rows (s_l | G_l of the
-// layer being reduced, then the flush buffer).  The first layer's weight gradient needs r and vhat of every frame as operand
-// rows once (s_1, G_1) exist, when the Z rows are free again: they are re-staged from global memory (L2: the warp read r and
-// wrote vhat a few microseconds earlier) in double-buffered column chunks, so no intermediate of pass 2 goes through HBM.
+// operand rows: Z rows (A_l | T_l of every hidden layer -- A_l read back from pass 1's P.A, T_l propagated here; during layer 1
+// they stage r and u) and X rows (s_l | G_l of the layer being reduced, then the flush buffer).  The first layer's weight
+// gradient needs r and vhat of every frame as operand rows once (s_1, G_1) exist, when the Z rows are free again: they are
+// re-staged from global memory (L2: the warp read r and wrote vhat a few microseconds earlier) in double-buffered column chunks,
+// and the vhat lines are dropped from L2 once staged (discard.global.L2), so no intermediate of pass 2 goes through HBM.
 template <int H, int NH, int CW>
 __global__ void __launch_bounds__(256, 1)
 pass2_kernel(const FastPlan P, const float* __restrict__ w, const double* __restrict__ combine, int rows_per_warp,

@@ -122,7 +122,8 @@ int32_t cvf_eigen_num_stats(int32_t k);
  * batch sums fills the vector itself (colvarsfinder/_ops.py: cvf::eigen_stats backward). */
 int32_t cvf_eigen_num_combine(int32_t k);
 /* bytes of scratch needed by cvf_eigen_stats / cvf_eigen_grad on a batch of B frames: per-CTA partial sums and, on the
- * fast path, the frame-minor intermediates pass 1 leaves for pass 2 (aligned frames, grad_r y, Jacobian vectors). */
+ * fast path, the frame-minor intermediates pass 1 leaves for pass 2 (aligned frames, grad_r y, Jacobian vectors, hidden
+ * activations: about 2 KB per frame for three [66,20,20,20,1] networks). */
 size_t cvf_eigen_workspace_bytes(const cvf_preproc* pp, const cvf_mlp* net, int32_t k, int64_t B);
 /* 1 if (pp, net, k) runs on the thread-private FFMA2 kernels (cvf_eigen_fast.cu), 0 if on the general row-engine kernels */
 int cvf_eigen_path(const cvf_preproc* pp, const cvf_mlp* net, int32_t k);
