@@ -578,6 +578,21 @@ def test_eigen_determinism(tmp_path):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_eigen_second_backward_recomputes_consumed_scratch(tmp_path):
+    """Pass 2 consumes pass 1's intermediates (it overwrites grad_r y and drops those lines from L2): a second backward() of the
+    same loss must notice and run pass 1 again.  Deterministic kernels: the accumulated gradient is exactly twice the first."""
+    c = C.eigen_case("eigen_dipep_k3")
+    X = ref_torch.synth_frames(BASE, 5000, seed=3)
+    w = ref_torch.boltzmann_weights(5000, seed=3)
+    task, model = _eigen_task(c, tmp_path, X, w)
+    out = task.loss_func(task._traj, task._weights)
+    out[0].backward(retain_graph=True)
+    g1 = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+    out[0].backward()
+    g2 = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert torch.isfinite(g2).all() and torch.equal(g2, 2.0 * g1)
+
+
 def test_eigen_train_matches_reference_run(tmp_path):
     """Whole train(): same split (numpy global RNG drawn twice), same batches, Adam -- per-iteration losses and the final
     parameters follow the reference run stored in tests/golden/train_eigen_2d.npz."""
